@@ -1,0 +1,421 @@
+"""Operator layer.
+
+Every hot op has two implementations behind one function:
+  * **native**: hand-written sm_100a CUDA kernels from ``ops/csrc`` (tcgen05/TMEM/TMA GEMM, fused
+    norm / RoPE / SwiGLU / cross-entropy / AdamW, flash attention), loaded from the in-tree ``_C`` extension;
+  * **torch**: plain PyTorch (cuBLAS / SDPA on GPU, CPU kernels on the gloo plumbing path).  This is the
+    numerics oracle for the tests and the measured "NCCL + cuBLAS" baseline arm.
+
+Selection: ``set_backend("native" | "torch" | "auto")``.  ``auto`` (default) uses native kernels for
+CUDA tensors and torch for CPU tensors.  On a CUDA tensor with backend ``native``/``auto`` a missing
+extension is an error, never a silent fallback (set ``NXDT_ALLOW_TORCH_FALLBACK=1`` to override).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import native as _native_loader
+
+_BACKEND = os.environ.get("NXDT_OPS_BACKEND", "auto")
+_COUNTERS = {"native_launches": 0}
+
+
+def set_backend(name: str) -> None:
+    global _BACKEND
+    assert name in ("auto", "native", "torch")
+    _BACKEND = name
+
+
+def get_backend() -> str:
+    return _BACKEND
+
+
+def native_launch_count() -> int:
+    return _COUNTERS["native_launches"]
+
+
+def reset_native_launch_count() -> None:
+    _COUNTERS["native_launches"] = 0
+
+
+def _count(n: int = 1):
+    _COUNTERS["native_launches"] += n
+
+
+def _use_native(t: torch.Tensor) -> bool:
+    if _BACKEND == "torch" or not t.is_cuda:
+        return False
+    C = _native_loader.get()
+    if C is None:
+        if os.environ.get("NXDT_ALLOW_TORCH_FALLBACK", "0") == "1":
+            return False
+        raise RuntimeError("CUDA tensor given but the sm_100a extension (ops/_C*.so) is not built/loaded: "
+                           + str(_native_loader.load_error()) + "  Run `python -c 'import __graft_entry__ as g; g.build()'`.")
+    return True
+
+
+def C():
+    return _native_loader.get()
+
+
+# =====================================================================================================
+# GEMM
+# =====================================================================================================
+_GEMM_NATIVE_DTYPES = (torch.bfloat16,)
+
+
+def _gemm_native_ok(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int) -> bool:
+    if a.dtype not in _GEMM_NATIVE_DTYPES or b.dtype != a.dtype:
+        return False
+    # TMA needs 16-byte aligned row pitches
+    return (k % 8 == 0) and (n % 8 == 0) and (m % 8 == 0) and m > 0
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[N,K]^T   (linear forward)."""
+    if _use_native(a) and _gemm_native_ok(a, b, a.shape[0], b.shape[0], a.shape[1]):
+        a = a if a.is_contiguous() else a.contiguous()
+        b = b if b.is_contiguous() else b.contiguous()
+        if out is None:
+            out = torch.empty(a.shape[0], b.shape[0], dtype=a.dtype, device=a.device)
+        _count()
+        C().gemm(a, b, out, True, True, False)
+        return out
+    r = a @ b.t()
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[K,N]   (dgrad: dY @ W)."""
+    if _use_native(a) and _gemm_native_ok(a, b, a.shape[0], b.shape[1], a.shape[1]):
+        a = a if a.is_contiguous() else a.contiguous()
+        b = b if b.is_contiguous() else b.contiguous()
+        if out is None:
+            out = torch.empty(a.shape[0], b.shape[1], dtype=a.dtype, device=a.device)
+        _count()
+        C().gemm(a, b, out, True, False, False)
+        return out
+    r = a @ b
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+               accumulate: bool = False) -> torch.Tensor:
+    """out[N,K] (+)= dy[M,N]^T @ x[M,K]   (wgrad).  ``out`` may be fp32 (main_grad accumulation)."""
+    if _use_native(dy) and _gemm_native_ok(dy, x, dy.shape[1], x.shape[1], dy.shape[0]) and \
+            (out is None or out.dtype in (torch.float32, torch.bfloat16)):
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        x = x if x.is_contiguous() else x.contiguous()
+        if out is None:
+            out = torch.empty(dy.shape[1], x.shape[1], dtype=dy.dtype, device=dy.device)
+            accumulate = False
+        _count()
+        C().gemm(dy, x, out, False, False, accumulate)
+        return out
+    if out is None:
+        return dy.t() @ x
+    if accumulate:
+        if out.dtype == dy.dtype:
+            out.addmm_(dy.t(), x)
+        else:
+            out.add_((dy.t() @ x).to(out.dtype))
+    else:
+        out.copy_(dy.t() @ x)
+    return out
+
+
+# =====================================================================================================
+# RMSNorm / LayerNorm
+# =====================================================================================================
+def rmsnorm_ref(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    xf = x.float()
+    y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return (y * w.float()).to(x.dtype)
+
+
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        _count()
+        y, rstd = C().rmsnorm_fwd(x2, w, eps)
+        ctx.save_for_backward(x2, w, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        _count()
+        dx, dw = C().rmsnorm_bwd(dy2, x2, w, rstd)
+        return dx.view(ctx.shape), dw.to(w.dtype), None
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    if _use_native(x) and x.dtype in (torch.bfloat16, torch.float32) and x.shape[-1] % 8 == 0:
+        return _RMSNormFn.apply(x, w, eps)
+    return rmsnorm_ref(x, w, eps)
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float = 1e-5,
+              one_plus: bool = False) -> torch.Tensor:
+    ww = w + 1.0 if one_plus else w
+    return F.layer_norm(x.float(), (x.shape[-1],), ww.float(), None if b is None else b.float(), eps).to(x.dtype)
+
+
+# =====================================================================================================
+# RoPE   q/k: [..., S, H, D] with cos/sin broadcastable [S, 1, D] (rotate-half convention)
+# =====================================================================================================
+def rotate_half(x: torch.Tensor) -> torch.Tensor:
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def rope_ref(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """x [B,S,H,D]; cos/sin [S,D] (or [B,S,D]) fp32."""
+    c = cos.unsqueeze(-2)
+    s = sin.unsqueeze(-2)
+    return (x.float() * c + rotate_half(x.float()) * s).to(x.dtype)
+
+
+class _RopeFn(torch.autograd.Function):
+    """In-place-capable fused RoPE on q and k together (one launch)."""
+
+    @staticmethod
+    def forward(ctx, q, k, cos, sin):
+        ctx.save_for_backward(cos, sin)
+        _count()
+        qo, ko = C().rope_fwd(q, k, cos, sin, False)
+        return qo, ko
+
+    @staticmethod
+    def backward(ctx, dq, dk):
+        cos, sin = ctx.saved_tensors
+        _count()
+        dqo, dko = C().rope_fwd(dq.contiguous(), dk.contiguous(), cos, sin, True)
+        return dqo, dko, None, None
+
+
+def rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor):
+    """q [B,S,Hq,D], k [B,S,Hk,D], cos/sin [S,D] fp32 -> rotated (q, k)."""
+    if _use_native(q) and q.dtype == torch.bfloat16 and cos.dim() == 2 and q.shape[-1] % 8 == 0:
+        return _RopeFn.apply(q.contiguous(), k.contiguous(), cos.contiguous(), sin.contiguous())
+    return rope_ref(q, cos, sin), rope_ref(k, cos, sin)
+
+
+# =====================================================================================================
+# SwiGLU on fused gate||up  ([..., 2I] -> [..., I])
+# =====================================================================================================
+def swiglu_ref(gate_up: torch.Tensor) -> torch.Tensor:
+    g, u = gate_up.chunk(2, dim=-1)
+    return F.silu(g) * u
+
+
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate_up):
+        ctx.save_for_backward(gate_up)
+        _count()
+        return C().swiglu_fwd(gate_up)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (gate_up,) = ctx.saved_tensors
+        _count()
+        return C().swiglu_bwd(dout.contiguous(), gate_up)
+
+
+def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
+    if _use_native(gate_up) and gate_up.dtype == torch.bfloat16 and gate_up.is_contiguous() \
+            and gate_up.shape[-1] % 16 == 0:
+        return _SwiGLUFn.apply(gate_up)
+    return swiglu_ref(gate_up)
+
+
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], activation: str) -> torch.Tensor:
+    """bias + activation for the Megatron MLP (gelu / geglu / reglu / swiglu / relu / squared-relu)."""
+    if bias is not None:
+        x = x + bias
+    if activation == "gelu":
+        return F.gelu(x, approximate="tanh")
+    if activation in ("swiglu", "fast-swiglu"):
+        return swiglu(x) if bias is None else swiglu_ref(x)
+    if activation in ("geglu", "fast-geglu"):
+        g, u = x.chunk(2, dim=-1)
+        return F.gelu(g, approximate="tanh") * u
+    if activation in ("reglu", "fast-reglu"):
+        g, u = x.chunk(2, dim=-1)
+        return F.relu(g) * u
+    if activation == "relu":
+        return F.relu(x)
+    if activation == "squared-relu":
+        return F.relu(x) ** 2
+    if activation == "silu":
+        return F.silu(x)
+    raise ValueError(f"unknown activation {activation}")
+
+
+def bias_dropout_add(x: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor, p: float,
+                     training: bool) -> torch.Tensor:
+    if bias is not None:
+        x = x + bias
+    if p > 0.0 and training:
+        x = F.dropout(x, p=p, training=True)
+    return residual + x
+
+
+# =====================================================================================================
+# Attention   q [B,S,Hq,D], k/v [B,S,Hkv,D] -> [B,S,Hq,D]
+# =====================================================================================================
+def attention_ref(q, k, v, causal: bool = True, window: Optional[int] = None, scale: Optional[float] = None,
+                  q_offset: int = 0, return_lse: bool = False, dropout_p: float = 0.0):
+    """Eager fp32 attention (oracle).  ``q_offset`` = absolute position of q[0] relative to k[0]
+    (used by ring attention blocks)."""
+    B, Sq, Hq, D = q.shape
+    Sk, Hk = k.shape[1], k.shape[2]
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    qf = q.float().transpose(1, 2)
+    kf = k.float().transpose(1, 2).repeat_interleave(Hq // Hk, dim=1)
+    vf = v.float().transpose(1, 2).repeat_interleave(Hq // Hk, dim=1)
+    s = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    qi = torch.arange(Sq, device=q.device).unsqueeze(-1) + q_offset
+    ki = torch.arange(Sk, device=q.device).unsqueeze(0)
+    mask = torch.zeros(Sq, Sk, dtype=torch.bool, device=q.device)
+    if causal:
+        mask |= ki > qi
+    if window is not None and window > 0:
+        mask |= ki <= qi - window
+    s = s.masked_fill(mask, float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.exp(s - lse.masked_fill(lse == float("-inf"), 0.0).unsqueeze(-1))
+    if dropout_p > 0.0:
+        p = F.dropout(p, dropout_p)
+    o = torch.matmul(p, vf).transpose(1, 2).to(q.dtype)
+    return (o, lse) if return_lse else o
+
+
+class _FlashAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal, window, scale):
+        _count()
+        o, lse = C().flash_attn_fwd(q, k, v, causal, window, scale)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.cfg = (causal, window, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        causal, window, scale = ctx.cfg
+        _count(3)
+        dq, dk, dv = C().flash_attn_bwd(do.contiguous(), q, k, v, o, lse, causal, window, scale)
+        return dq, dk, dv, None, None, None
+
+
+def _sdpa(q, k, v, causal, scale):
+    # torch SDPA wants [B,H,S,D]
+    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                       is_causal=causal, scale=scale, enable_gqa=(q.shape[2] != k.shape[2]))
+    return o.transpose(1, 2)
+
+
+def flash_attention(q, k, v, causal: bool = True, window: Optional[int] = None, scale: Optional[float] = None):
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    if _use_native(q) and q.dtype == torch.bfloat16 and q.shape[-1] in (64, 128) and hasattr(C(), "flash_attn_fwd"):
+        return _FlashAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal,
+                                  int(window or 0), float(scale))
+    if q.is_cuda and (window is None or window <= 0):
+        return _sdpa(q, k, v, causal, scale)   # baseline arm: library flash attention through SDPA
+    return attention_ref(q, k, v, causal, window, scale)
+
+
+# =====================================================================================================
+# Cross entropy on (local) logits
+# =====================================================================================================
+def cross_entropy_ref(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """per-token loss [T] (0 where ignored)."""
+    return F.cross_entropy(logits.float(), labels, ignore_index=ignore_index, reduction="none")
+
+
+# =====================================================================================================
+# Optimizer kernels (flat buffers)
+# =====================================================================================================
+def adamw_step_flat(master: Optional[torch.Tensor], param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor,
+                    exp_avg_sq: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float,
+                    weight_decay: float, step: int, grad_scale: float = 1.0,
+                    decay_mask: Optional[torch.Tensor] = None, stochastic_rounding: bool = False,
+                    seed: int = 0, lr_mask: Optional[torch.Tensor] = None) -> None:
+    """One fused AdamW update over a flat shard.
+
+    ``master`` (fp32, may be None => update ``param`` in its own dtype with fp32 math), ``param`` (model
+    dtype, receives the rounded copy), ``grad`` (fp32 or bf16, multiplied by ``grad_scale`` = clip coeff
+    / loss scaling), fp32 moments.  ``decay_mask`` (uint8 per element) selects weight decay."""
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    if _use_native(param) and exp_avg.dtype == torch.float32:
+        _count()
+        if not torch.is_tensor(grad_scale):
+            grad_scale = torch.full((), float(grad_scale), dtype=torch.float32, device=param.device)
+        C().adamw_flat(master if master is not None else torch.empty(0, device=param.device), param, grad,
+                       exp_avg, exp_avg_sq, decay_mask if decay_mask is not None else torch.empty(0, dtype=torch.uint8, device=param.device),
+                       lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale.float(), stochastic_rounding, seed)
+        return
+    g = grad.float() * grad_scale
+    p32 = master if master is not None else param.float()
+    if weight_decay != 0.0:
+        if decay_mask is not None:
+            p32.mul_(1.0 - lr * weight_decay * decay_mask.to(p32.dtype))
+        else:
+            p32.mul_(1.0 - lr * weight_decay)
+    m32 = exp_avg.float() if exp_avg.dtype != torch.float32 else exp_avg
+    v32 = exp_avg_sq.float() if exp_avg_sq.dtype != torch.float32 else exp_avg_sq
+    m32.mul_(beta1).add_(g, alpha=1.0 - beta1)
+    v32.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    denom = (v32 / bc2).sqrt_().add_(eps)
+    p32.addcdiv_(m32 / bc1, denom, value=-lr)
+    if m32 is not exp_avg:
+        exp_avg.copy_(m32)
+    if v32 is not exp_avg_sq:
+        exp_avg_sq.copy_(v32)
+    if master is not None:
+        if stochastic_rounding and param.dtype == torch.bfloat16:
+            param.copy_(stochastic_round_bf16(master, seed))
+        else:
+            param.copy_(master)
+    elif p32 is not param:
+        if stochastic_rounding and param.dtype == torch.bfloat16:
+            param.copy_(stochastic_round_bf16(p32, seed))
+        else:
+            param.copy_(p32)
+
+
+def stochastic_round_bf16(x: torch.Tensor, seed: int = 0) -> torch.Tensor:
+    """fp32 -> bf16 with stochastic rounding (adds uniform noise to the 16 truncated mantissa bits)."""
+    g = torch.Generator(device=x.device)
+    g.manual_seed(int(seed) & 0x7FFFFFFF)
+    bits = x.contiguous().view(torch.int32)
+    noise = torch.randint(0, 1 << 16, bits.shape, generator=g, device=x.device, dtype=torch.int32)
+    rounded = (bits + noise) & ~0xFFFF
+    return rounded.view(torch.float32).to(torch.bfloat16)
+
+
+def sq_norm(t: torch.Tensor) -> torch.Tensor:
+    """sum of squares in fp32 (device scalar)."""
+    if _use_native(t) and t.is_contiguous() and t.dtype in (torch.float32, torch.bfloat16) and t.numel() > 0:
+        _count()
+        return C().sq_norm(t.view(-1))
+    return t.float().pow(2).sum()

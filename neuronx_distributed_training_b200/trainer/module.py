@@ -1,0 +1,252 @@
+"""Task-module base class: the extension point users subclass to bring a new model.
+
+Contract parity with the reference's ``BaseModelModule`` (reference
+lightning_modules/model/base.py:49-712 and docs/developer_guides/new_model_guide.rst:40-113):
+subclasses implement ``build_model()``, ``setup_optimizer_param_groups()``, ``init_weights(module,
+device)`` and may override ``model_fwd_calc_loss``, ``forward_backward_step``, ``process_global_batch``.
+
+One ``training_step`` = one optimizer step = one *global* batch: the per-DP-rank batch arrives on the
+host, is copied H2D once, split into microbatches, each microbatch runs fwd+bwd with the loss scaled
+by ``1/num_microbatches``, then the (ZeRO-1) optimizer steps.  Gradient accumulation is only ever
+expressed through GBS/MBS (reference nlp_overrides.py:949-952).
+"""
+from __future__ import annotations
+
+import contextlib
+import logging
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import ops
+from ..config import Config, ParallelDims, PrecisionPolicy
+from ..data.base import get_batch_on_this_context_parallel_rank
+from ..optim import DistributedOptimizer, get_optimizer, prepare_lr_scheduler
+from ..parallel import state as ps
+from ..parallel.layers import param_is_tp_duplicate
+from ..parallel.random import set_random_seed
+from ..utils.throughput import Throughput
+
+log = logging.getLogger("nxdt")
+
+
+def get_param_groups_by_weight_decay(named_params, weight_decay: float = 0.01, no_decay_norm: bool = True):
+    """bias (and optionally norm weights) -> no decay (reference utils/model_utils.py:4-22)."""
+    decay, no_decay = [], []
+    for n, p in named_params:
+        if not p.requires_grad:
+            continue
+        is_norm = ("norm" in n.lower()) or ("LayerNorm" in n)
+        if n.endswith("bias") or ".bias" in n or (no_decay_norm and is_norm):
+            no_decay.append(p)
+        else:
+            decay.append(p)
+    groups = [{"params": decay, "weight_decay": weight_decay}]
+    if no_decay:
+        groups.append({"params": no_decay, "weight_decay": 0.0})
+    return groups
+
+
+class BaseModelModule:
+    def __init__(self, cfg: Config, trainer=None):
+        self.cfg = cfg
+        self.config = cfg.model
+        self.trainer = trainer
+        ds = cfg.get("distributed_strategy", Config({}))
+        self.dims = ParallelDims(world_size=ps.get_world_size(), tp=ps.get_tensor_model_parallel_size(),
+                                 pp=ps.get_pipeline_model_parallel_size(), cp=ps.get_context_model_parallel_size(),
+                                 ep=ps.get_expert_model_parallel_size(),
+                                 vpp=int(ds.get("virtual_pipeline_model_parallel_size", 1) or 1))
+        self.micro_batch_size = int(cfg.data.micro_batch_size)
+        self.global_batch_size = int(cfg.data.global_batch_size)
+        self.num_microbatches = self.global_batch_size // (self.micro_batch_size * self.dims.dp)
+        self.sequence_parallel = bool(ds.get("sequence_parallel", False)) and self.dims.tp > 1
+        self.zero1 = bool(ds.get("zero1", True))
+        self.precision = PrecisionPolicy.from_config(cfg)
+        self.seed = int(cfg.get("seed", 1234))
+        set_random_seed(self.seed)
+        em = cfg.get("exp_manager", Config({}))
+        self.log_parameter_norm = bool(em.get("log_parameter_norm", False))
+        self.log_gradient_norm = bool(em.get("log_gradient_norm", False))
+        self.save_logits = bool(self.config.get("save_logits", False))
+        self.model: Optional[nn.Module] = None
+        self.optimizer: Optional[DistributedOptimizer] = None
+        self.lr_scheduler = None
+        self.throughput = Throughput(self.micro_batch_size, self.dims.dp, self.num_microbatches, 10)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self._logged: Dict[str, float] = {}
+
+    # ---- to be provided by subclasses -------------------------------------------------------------
+    def build_model(self) -> nn.Module:
+        raise NotImplementedError
+
+    def setup_optimizer_param_groups(self) -> List[Dict[str, Any]]:
+        wd = float(self.config.optim.get("weight_decay", 0.01))
+        return get_param_groups_by_weight_decay(self.local_named_parameters(), wd)
+
+    def init_weights(self, module: nn.Module, device) -> None:
+        for fn in ("init_weight_cpu", "initialize_weight_biases", "reset_parameters"):
+            if hasattr(module, fn):
+                getattr(module, fn)()
+                return
+
+    # ---- lifecycle ---------------------------------------------------------------------------------
+    def setup(self, stage: str = "fit"):
+        if self.model is None:
+            self.model = self.build_model()
+
+    def local_named_parameters(self):
+        m = self.model
+        if hasattr(m, "local_named_parameters"):
+            return list(m.local_named_parameters())
+        return list(m.named_parameters())
+
+    def configure_optimizers(self, max_steps: Optional[int] = None):
+        ocfg = self.config.optim
+        algo, extra = get_optimizer(str(ocfg.get("name", "adamw")))
+        groups = self.setup_optimizer_param_groups()
+        clip = self.cfg.trainer.get("gradient_clip_val", None)
+        pol = self.precision
+        self.optimizer = DistributedOptimizer(
+            groups, lr=float(ocfg.get("lr", 1e-4)), betas=tuple(ocfg.get("betas", (0.9, 0.999))),
+            eps=float(ocfg.get("eps", 1e-8)), weight_decay=float(ocfg.get("weight_decay", 0.01)),
+            algorithm=algo, momentum=float(ocfg.get("momentum", 0.0)), zero1=self.zero1,
+            master_weights=pol.master_weights, fp32_grad_acc=pol.fp32_grad_acc, max_grad_norm=clip,
+            stochastic_rounding=pol.stochastic_rounding, state_dtype=pol.optimizer_state_dtype)
+        sched = ocfg.get("sched", None)
+        self.lr_scheduler = prepare_lr_scheduler(self.optimizer, sched, max_steps) if sched is not None else None
+        return self.optimizer, self.lr_scheduler
+
+    # ---- step ----------------------------------------------------------------------------------------
+    def autocast_ctx(self):
+        if self.precision.autocast:
+            return torch.autocast(device_type=self.device.type, dtype=torch.bfloat16)
+        return contextlib.nullcontext()
+
+    def to_device(self, batch: Dict[str, Any]) -> Dict[str, Any]:
+        return {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+    def get_batch_iterator(self, batch: Dict[str, torch.Tensor]):
+        mbs = self.micro_batch_size
+        n = self.num_microbatches
+        for k in range(n):
+            yield {key: (v[k * mbs:(k + 1) * mbs] if torch.is_tensor(v) else v) for key, v in batch.items()}
+
+    def model_fwd_calc_loss(self, batch: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, Any]:
+        out = self.model(input_ids=batch["input_ids"], labels=batch["labels"],
+                         attention_mask=batch.get("attention_mask"), loss_mask=batch.get("loss_mask"))
+        return out[0], out[1]
+
+    def forward_backward_step(self, batch: Dict[str, torch.Tensor], is_training: bool = True) -> torch.Tensor:
+        if self.dims.pp > 1:
+            fn = self.model.run_train if is_training else self.model.run_eval
+            running = fn(**batch)
+        else:
+            running = torch.zeros((), dtype=torch.float32, device=self.device)
+            for mb in self.get_batch_iterator(batch):
+                with contextlib.nullcontext() if is_training else torch.no_grad():
+                    loss, _ = self.model_fwd_calc_loss(mb)
+                    loss = loss.float() / self.num_microbatches
+                if is_training:
+                    loss.backward()
+                running += loss.detach()
+        # loss mean over CP then DP (reference base.py:387-395)
+        cpg, dpg = ps.get_context_model_parallel_group(), ps.get_data_parallel_group()
+        if ps.group_size(cpg) > 1:
+            dist.all_reduce(running, group=cpg)
+            running /= ps.group_size(cpg)
+        if ps.group_size(dpg) > 1:
+            dist.all_reduce(running, group=dpg)
+            running /= ps.group_size(dpg)
+        return running
+
+    def training_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0) -> torch.Tensor:
+        self.optimizer.zero_grad()
+        seq = self.config.get("encoder_seq_length", None)
+        if seq is not None and "input_ids" in batch:
+            assert batch["input_ids"].shape[1] == int(seq), \
+                f"batch sequence length {batch['input_ids'].shape[1]} != model.encoder_seq_length {seq}"
+        batch = self.to_device(batch)
+        batch = get_batch_on_this_context_parallel_rank(batch)
+        with self.autocast_ctx():
+            loss_mean = self.forward_backward_step(batch, is_training=True)
+        ppg = ps.get_pipeline_model_parallel_group()
+        if ps.group_size(ppg) > 1:
+            dist.all_reduce(loss_mean, group=ppg)       # last stage holds the loss, the others 0
+        self.sync_special_grads()
+        self.optimizer.step()
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+        return loss_mean
+
+    def sync_special_grads(self):
+        """KV-replica gradient sums (GQA with kv_replicator > 1)."""
+        for m in self.model.modules():
+            if hasattr(m, "sync_kv_replica_grads"):
+                m.sync_kv_replica_grads()
+
+    @torch.no_grad()
+    def validation_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0) -> torch.Tensor:
+        batch = get_batch_on_this_context_parallel_rank(self.to_device(batch))
+        self.model.eval()
+        try:
+            with self.autocast_ctx():
+                loss = self.forward_backward_step(batch, is_training=False)
+        finally:
+            self.model.train()
+        ppg = ps.get_pipeline_model_parallel_group()
+        if ps.group_size(ppg) > 1:
+            dist.all_reduce(loss, group=ppg)
+        return loss
+
+    # ---- metrics -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def parameter_norm(self) -> torch.Tensor:
+        """L2 norm over de-duplicated params across TP / CP / PP (reference base.py:397-452)."""
+        tp_rank = ps.get_tensor_model_parallel_rank()
+        total = torch.zeros((), dtype=torch.float32, device=self.device)
+        for _, p in self.local_named_parameters():
+            if param_is_tp_duplicate(p) and tp_rank != 0:
+                continue
+            total += p.detach().float().pow(2).sum()
+        for grp in (ps.get_tensor_model_parallel_group(), ps.get_pipeline_model_parallel_group()):
+            if ps.group_size(grp) > 1:
+                dist.all_reduce(total, group=grp)
+        return total.sqrt()
+
+    def collect_metrics(self, loss: torch.Tensor, global_step: int, consumed_samples: int) -> Dict[str, float]:
+        m = {"reduced_train_loss": float(loss), "global_step": float(global_step),
+             "consumed_samples": float(consumed_samples)}
+        if self.optimizer is not None:
+            m["lr"] = float(self.optimizer.param_groups[0]["lr"])
+            if self.log_gradient_norm and self.optimizer.grad_norm is not None:
+                m["gradient_norm"] = float(self.optimizer.grad_norm)
+        if self.log_parameter_norm:
+            m["parameter_norm"] = float(self.parameter_norm())
+        m["throughput"] = self.throughput.get_throughput()
+        m["throughput_peak"] = self.throughput.throughput_peak
+        return m
+
+    # ---- hooks the trainer calls -----------------------------------------------------------------------
+    def on_train_start(self, trainer):
+        pass
+
+    def on_train_end(self, trainer):
+        pass
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return self.model.state_dict()
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
+        """Non-strict load that ignores rotary ``inv_freq`` buffers but raises on any other missing key
+        unless PEFT is active (reference nlp_overrides.py:1157-1200)."""
+        res = self.model.load_state_dict(sd, strict=False)
+        missing = [k for k in res.missing_keys if not k.endswith("rotary_emb.inv_freq")]
+        peft = self.cfg.get("model_alignment_strategy", None) is not None and \
+            self.cfg.model_alignment_strategy.get("peft", None) is not None
+        if missing and not peft:
+            raise RuntimeError(f"missing keys when loading checkpoint: {missing[:8]}{' ...' if len(missing) > 8 else ''}")
+        return res

@@ -1,0 +1,265 @@
+"""Training loop runtime.
+
+Capability parity with the reference's Lightning trainer stack (SURVEY §2.1 #5-#7, §3.3, §3.5;
+reference lightning_modules/nlp_overrides.py): ``max_steps`` / ``max_epochs`` / ``max_time``,
+``val_check_interval``, ``limit_val_batches``, ``log_every_n_steps``, checkpoint callback, full state
+restore (model, optimizer shards, LR schedule, loop progress, consumed samples), signal handling.
+
+What is deliberately different (B200-first): there is no lazy-graph cut / step closure machinery; a step
+is eager CUDA work on streams, metrics are read back only on logging steps, the step time reported is
+measured with CUDA events on the device, and a SIGTERM/SIGUSR1 triggers an emergency checkpoint at the
+next step boundary instead of relying on relaunch-only recovery.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import signal
+import time
+from typing import Any, Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..checkpoint import io as ckpt_io
+from ..config import Config
+from ..parallel import state as ps
+from ..utils.exp_manager import ExpManager, consumed_samples_from_path, step_from_path
+from ..utils.throughput import DeviceStepTimer
+
+log = logging.getLogger("nxdt")
+
+
+def _parse_max_time(v) -> Optional[float]:
+    """'DD:HH:MM:SS' (PTL style) or seconds."""
+    if v is None:
+        return None
+    if isinstance(v, (int, float)):
+        return float(v)
+    parts = [int(p) for p in str(v).split(":")]
+    while len(parts) < 4:
+        parts.insert(0, 0)
+    d, h, m, s = parts
+    return float(((d * 24 + h) * 60 + m) * 60 + s)
+
+
+class Trainer:
+    def __init__(self, devices: int = 1, num_nodes: int = 1, max_epochs: int = -1, max_steps: int = -1,
+                 log_every_n_steps: int = 10, val_check_interval: Any = None, check_val_every_n_epoch: Any = None,
+                 num_sanity_val_steps: int = 0, limit_val_batches: Any = 1.0, limit_test_batches: Any = 1.0,
+                 gradient_clip_val: Optional[float] = None, max_time: Any = None, accumulate_grad_batches: int = 1,
+                 enable_progress_bar: bool = False, **ignored):
+        if accumulate_grad_batches not in (None, 1):
+            raise ValueError("accumulate_grad_batches>1 is not supported; gradient accumulation is expressed "
+                             "through global_batch_size / micro_batch_size")
+        if ignored.get("gradient_clip_algorithm") not in (None, "norm"):
+            raise ValueError("only norm-based gradient clipping is supported")
+        self.devices, self.num_nodes = devices, num_nodes
+        self.max_epochs, self.max_steps = max_epochs, int(max_steps if max_steps is not None else -1)
+        self.log_every_n_steps = max(1, int(log_every_n_steps or 1))
+        self.val_check_interval = val_check_interval
+        self.limit_val_batches = limit_val_batches
+        self.limit_test_batches = limit_test_batches
+        self.num_sanity_val_steps = int(num_sanity_val_steps or 0)
+        self.gradient_clip_val = gradient_clip_val
+        self.max_time = _parse_max_time(max_time)
+        self.ignored_args = ignored           # Neuron-only knobs (lnc, sequential_move_factor, ...)
+        self.global_step = 0
+        self.current_epoch = 0
+        self.steps_since_resume = 0
+        self.exp_manager: Optional[ExpManager] = None
+        self.log_dir: Optional[str] = None
+        self.model = None
+        self.datamodule = None
+        self.should_stop = False
+        self._emergency = False
+        self.logged_metrics: Dict[str, float] = {}
+        self.callback_metrics: Dict[str, float] = {}
+        self.step_timer = DeviceStepTimer()
+        self.last_step_ms = []
+
+    # ---- signals ---------------------------------------------------------------------------------------
+    def _install_signal_handlers(self):
+        def handler(signum, frame):
+            log.warning("signal %s received: emergency checkpoint at next step boundary, then exit", signum)
+            self._emergency = True
+            self.should_stop = True
+        for sig in (signal.SIGTERM, signal.SIGUSR1):
+            try:
+                signal.signal(sig, handler)
+            except (ValueError, OSError):
+                pass
+
+    # ---- checkpoint ------------------------------------------------------------------------------------
+    def dump_checkpoint(self) -> Dict[str, Any]:
+        return {
+            "epoch": self.current_epoch, "global_step": self.global_step,
+            "pytorch-lightning_version": "2.5.0",
+            "loops": {"fit_loop": {"global_step": self.global_step, "epoch": self.current_epoch,
+                                   "consumed_samples": self.datamodule.consumed_samples if self.datamodule else 0}},
+            "lr_schedulers": [self.model.lr_scheduler.state_dict()] if self.model.lr_scheduler is not None else [],
+            "callbacks": {}, "hyper_parameters": {"cfg": self.model.cfg.to_dict()},
+            "datamodule": self.datamodule.state_dict() if self.datamodule is not None else {},
+        }
+
+    def save_checkpoint(self, filepath: str):
+        em = self.exp_manager.cfg if self.exp_manager else None
+        directory, tag = os.path.dirname(filepath), os.path.basename(filepath)
+        # strip the "-vN" version suffix PTL appends (reference nlp_overrides.py:572-578)
+        user_content = self.dump_checkpoint()
+        model_sd = self.model.state_dict()
+        opt = self.model.optimizer
+        if em is not None and em.checkpoint_callback_params.use_master_weights_in_ckpt and opt.master is not None:
+            user_content["master_weights_in_ckpt"] = True
+        opt_sd = opt.state_dict() if opt is not None else None
+        ckpt_io.save_checkpoint(directory, tag, model=model_sd, optimizer=opt_sd, user_content=user_content,
+                                use_xser=em.save_xser if em else True,
+                                async_save=em.async_checkpointing if em else False,
+                                zero1_optimizer=bool(opt is not None and opt.zero1))
+        if ps.get_rank() == 0:
+            log.info("saved checkpoint %s", filepath)
+
+    def restore(self, ckpt_path: str, weight_init_only: bool = False):
+        directory, tag = os.path.dirname(ckpt_path.rstrip("/")), os.path.basename(ckpt_path.rstrip("/"))
+        m, o, uc = ckpt_io.load_checkpoint(directory, tag, model=True, optimizer=not weight_init_only)
+        self.model.load_state_dict(m)
+        opt = self.model.optimizer
+        if weight_init_only or o is None:
+            opt.sync_master_from_params()
+            log.info("loaded weights only from %s", ckpt_path)
+            return
+        opt.load_state_dict(o)
+        if uc is not None:
+            if "pytorch-lightning_version" not in uc:
+                uc["pytorch-lightning_version"] = (self.exp_manager.cfg.ckpt_ptl_version if self.exp_manager else None) or "2.5.0"
+            self.global_step = int(uc.get("global_step", step_from_path(ckpt_path)))
+            self.current_epoch = int(uc.get("epoch", 0))
+            scheds = uc.get("lr_schedulers") or []
+            if scheds and self.model.lr_scheduler is not None:
+                self.model.lr_scheduler.load_state_dict(scheds[0])
+            if self.datamodule is not None and uc.get("datamodule"):
+                self.datamodule.load_state_dict(uc["datamodule"])
+        else:
+            self.global_step = step_from_path(ckpt_path)
+        if self.datamodule is not None and consumed_samples_from_path(ckpt_path) > 0:
+            self.datamodule.load_state_dict({"consumed_samples": consumed_samples_from_path(ckpt_path)})
+        log.info("resumed from %s at global_step=%d consumed_samples=%d", ckpt_path, self.global_step,
+                 self.datamodule.consumed_samples if self.datamodule else -1)
+
+    # ---- validation --------------------------------------------------------------------------------------
+    def _limit(self, limit, n_total: Optional[int]) -> int:
+        if limit is None:
+            return n_total if n_total is not None else 1 << 30
+        if isinstance(limit, float) and limit <= 1.0:
+            return int((n_total or 0) * limit)
+        return int(limit)
+
+    def validate(self) -> Optional[float]:
+        loader = self.datamodule.val_dataloader() if self.datamodule is not None else None
+        if loader is None:
+            return None
+        try:
+            n_total = len(loader)
+        except TypeError:
+            n_total = None
+        n = self._limit(self.limit_val_batches, n_total)
+        if n <= 0:
+            return None
+        losses = []
+        for i, batch in enumerate(loader):
+            if i >= n:
+                break
+            losses.append(self.model.validation_step(batch, i))
+        if not losses:
+            return None
+        val = float(torch.stack([l.detach().float() for l in losses]).mean())
+        self.callback_metrics["val_loss"] = val
+        if self.exp_manager:
+            self.exp_manager.log_metrics({"val_loss": val}, self.global_step)
+        log.info("validation: val_loss=%.5f (%d batches)", val, len(losses))
+        return val
+
+    # ---- fit -----------------------------------------------------------------------------------------------
+    def fit(self, model, datamodule, ckpt_path: Optional[str] = None):
+        self.model, self.datamodule = model, datamodule
+        model.trainer = self
+        self._install_signal_handlers()
+        if ckpt_path is None and self.exp_manager is not None:
+            ckpt_path = self.exp_manager.resume_from_checkpoint
+        datamodule.setup(ckpt_path)
+        model.setup("fit")
+        model.configure_optimizers(self.max_steps if self.max_steps > 0 else None)
+        weight_init_only = bool(model.cfg.model.get("weight_init_only", False))
+        if ckpt_path:
+            self.restore(ckpt_path, weight_init_only=weight_init_only and
+                         not os.path.dirname(ckpt_path.rstrip("/")).startswith(str(self.log_dir or "\0")))
+        model.on_train_start(self)
+        for i in range(self.num_sanity_val_steps and 1):
+            self.validate()
+        t_start = time.time()
+        cb = self.exp_manager.checkpoint_callback if self.exp_manager else None
+        try:
+            while not self.should_stop:
+                loader = datamodule.train_dataloader()
+                n_batches = 0
+                for batch_idx, batch in enumerate(loader):
+                    if self.max_steps > 0 and self.global_step >= self.max_steps:
+                        self.should_stop = True
+                        break
+                    self.step_timer.start()
+                    loss = model.training_step(batch, batch_idx)
+                    self.step_timer.stop()
+                    n_batches += 1
+                    self.global_step += 1
+                    self.steps_since_resume += 1
+                    datamodule.consumed_samples = datamodule.compute_consumed_samples(self.steps_since_resume)
+                    if self.global_step % self.log_every_n_steps == 0:
+                        self._log(loss)
+                    vci = self.val_check_interval
+                    if vci and isinstance(vci, int) and self.global_step % vci == 0:
+                        self.validate()
+                    if cb is not None and cb.should_save(self.global_step):
+                        cb.save(self, self._ckpt_metrics())
+                    if self.max_time is not None and time.time() - t_start > self.max_time:
+                        log.info("max_time reached")
+                        self.should_stop = True
+                    if self.should_stop:
+                        break
+                self.current_epoch += 1
+                if n_batches == 0:
+                    break
+                if self.max_epochs and self.max_epochs > 0 and self.current_epoch >= self.max_epochs:
+                    break
+                if self.max_steps > 0 and self.global_step >= self.max_steps:
+                    break
+            if cb is not None and (self._emergency or cb.p.save_last) and self.global_step != cb.last_saved_step \
+                    and self.global_step > 0:
+                cb.save(self, self._ckpt_metrics(), last=not self._emergency and cb.p.save_last)
+        finally:
+            model.on_train_end(self)
+            ckpt_io.finalize_checkpoint()
+            if self.exp_manager:
+                self.exp_manager.close()
+        return self
+
+    def _ckpt_metrics(self) -> Dict[str, Any]:
+        return {"step": self.global_step, "consumed_samples": float(self.datamodule.consumed_samples),
+                "epoch": self.current_epoch, **self.callback_metrics}
+
+    def _log(self, loss: torch.Tensor):
+        m = self.model.collect_metrics(loss, self.global_step, self.datamodule.consumed_samples)
+        ms = self.step_timer.elapsed_ms()
+        if ms:
+            m["step_time_ms_device"] = sum(ms) / len(ms)
+            self.last_step_ms = ms
+        self.step_timer.reset()
+        self.logged_metrics = m
+        self.callback_metrics.update({"reduced_train_loss": m["reduced_train_loss"]})
+        if self.exp_manager:
+            self.exp_manager.log_metrics(m, self.global_step)
+        if ps.get_rank() == 0:
+            log.info("step %d | %s", self.global_step,
+                     " | ".join(f"{k}={v:.6g}" for k, v in m.items() if k != "global_step"))
+
+
+NLPTrainer = Trainer
