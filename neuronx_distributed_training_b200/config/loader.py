@@ -347,7 +347,7 @@ def _eval_expr(expr: str, node) -> Any:
 
 def _coerce_scalar(s: str):
     try:
-        return yaml.safe_load(s)
+        return yaml.load(s, Loader=_Loader)
     except yaml.YAMLError:
         return s
 

@@ -1,0 +1,496 @@
+// Bandwidth-bound fused kernels for sm_100a: RMSNorm fwd/bwd, RoPE (fwd and conjugate), SwiGLU fwd/bwd,
+// flat AdamW (fp32 master + bf16 write-back, optional stochastic rounding, device-side clip scale),
+// squared-L2 norm.  All use 128-bit vector accesses; reductions are warp-shuffle + one smem hop.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace {
+
+constexpr int NUM_SMS_HINT = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < THREADS / 32) ? sm[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (l == 0) sm[0] = r;
+  }
+  __syncthreads();
+  r = sm[0];
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  bf16x8 v = *reinterpret_cast<const bf16x8*>(p);
+  unpack8(v, f);
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<bf16x8*>(p) = pack8(f);
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm forward: y = x * rsqrt(mean(x^2) + eps) * w      (fp32 math, one CTA per row)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                              T* __restrict__ y, float* __restrict__ rstd_out,
+                                                              int rows, int H, float eps) {
+  __shared__ float sm[32];
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const T* xr = x + (size_t)row * H;
+    float ss = 0.f;
+    for (int c = threadIdx.x * 8; c < H; c += THREADS * 8) {
+      float f[8];
+      load8<T>(xr + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+    }
+    ss = block_sum<THREADS>(ss, sm);
+    const float rstd = rsqrtf(ss / H + eps);
+    if (threadIdx.x == 0) rstd_out[row] = rstd;
+    T* yr = y + (size_t)row * H;
+    for (int c = threadIdx.x * 8; c < H; c += THREADS * 8) {
+      float f[8], g[8];
+      load8<T>(xr + c, f);   // second read is served by L1/L2
+      load8<T>(w + c, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = f[i] * rstd * g[i];
+      store8<T>(yr + c, f);
+    }
+  }
+}
+
+// backward: dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) ; dw[c] += sum_rows dy * xhat   (persistent grid)
+template <typename T, int THREADS, int MAXV>
+__global__ void __launch_bounds__(THREADS) rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                              const T* __restrict__ w, const float* __restrict__ rstd,
+                                                              T* __restrict__ dx, float* __restrict__ dw, int rows,
+                                                              int H) {
+  __shared__ float sm[32];
+  float dw_acc[MAXV][8];
+#pragma unroll
+  for (int v = 0; v < MAXV; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dw_acc[v][i] = 0.f;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const T* xr = x + (size_t)row * H;
+    const T* gr = dy + (size_t)row * H;
+    const float rs = rstd[row];
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int c = (v * THREADS + threadIdx.x) * 8;
+      if (c < H) {
+        float fx[8], fg[8], fw[8];
+        load8<T>(xr + c, fx);
+        load8<T>(gr + c, fg);
+        load8<T>(w + c, fw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = fx[i] * rs;
+          dot += fg[i] * fw[i] * xh;
+          dw_acc[v][i] += fg[i] * xh;
+        }
+      }
+    }
+    dot = block_sum<THREADS>(dot, sm) / H;
+    T* dxr = dx + (size_t)row * H;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int c = (v * THREADS + threadIdx.x) * 8;
+      if (c < H) {
+        float fx[8], fg[8], fw[8], o[8];
+        load8<T>(xr + c, fx);
+        load8<T>(gr + c, fg);
+        load8<T>(w + c, fw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (fg[i] * fw[i] - fx[i] * rs * dot);
+        store8<T>(dxr + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < MAXV; ++v) {
+    const int c = (v * THREADS + threadIdx.x) * 8;
+    if (c < H) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(dw + c + i, dw_acc[v][i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (rotate-half).  x: [T, NH, D] tokens-major with token t using position (t / tokens_per_pos_div) ...
+// layout here: x [B, S, NH, D] contiguous, cos/sin [S, D] fp32.  conj=1 applies the transpose (backward).
+// One thread rotates 8 elements of the first half together with their partners in the second half.
+// ------------------------------------------------------------------------------------------------
+__global__ void rope_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                            const float* __restrict__ cs, const float* __restrict__ sn, int B, int S, int NH, int D,
+                            int conj, size_t total_units) {
+  const int half = D / 2;
+  const int units_per_head = half / 8;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < total_units; u += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(u % units_per_head);
+    const size_t head_lin = u / units_per_head;          // (b*S + s)*NH + h
+    const size_t tok = head_lin / NH;
+    const int s = (int)(tok % S);
+    const size_t base = head_lin * D + j * 8;
+    float a[8], b[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
+    load8<__nv_bfloat16>(x + base, a);
+    load8<__nv_bfloat16>(x + base + half, b);
+    load8<float>(cs + (size_t)s * D + j * 8, c1);
+    load8<float>(cs + (size_t)s * D + half + j * 8, c2);
+    load8<float>(sn + (size_t)s * D + j * 8, s1);
+    load8<float>(sn + (size_t)s * D + half + j * 8, s2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!conj) {
+        o1[i] = a[i] * c1[i] - b[i] * s1[i];
+        o2[i] = b[i] * c2[i] + a[i] * s2[i];
+      } else {
+        o1[i] = a[i] * c1[i] + b[i] * s2[i];
+        o2[i] = b[i] * c2[i] - a[i] * s1[i];
+      }
+    }
+    store8<__nv_bfloat16>(y + base, o1);
+    store8<__nv_bfloat16>(y + base + half, o2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SwiGLU on fused gate||up rows: in [T, 2I] -> out [T, I]
+// ------------------------------------------------------------------------------------------------
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, size_t T,
+                                  int I) {
+  const size_t units = T * (size_t)(I / 8);
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = u / (I / 8);
+    const int c = (int)(u % (I / 8)) * 8;
+    float g[8], v[8], o[8];
+    load8<__nv_bfloat16>(gu + t * 2 * I + c, g);
+    load8<__nv_bfloat16>(gu + t * 2 * I + I + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = g[i] / (1.f + __expf(-g[i])) * v[i];
+    store8<__nv_bfloat16>(out + t * I + c, o);
+  }
+}
+
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ gu,
+                                  __nv_bfloat16* __restrict__ dgu, size_t T, int I) {
+  const size_t units = T * (size_t)(I / 8);
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = u / (I / 8);
+    const int c = (int)(u % (I / 8)) * 8;
+    float g[8], v[8], d[8], dg[8], dv[8];
+    load8<__nv_bfloat16>(gu + t * 2 * I + c, g);
+    load8<__nv_bfloat16>(gu + t * 2 * I + I + c, v);
+    load8<__nv_bfloat16>(dout + t * I + c, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float sig = 1.f / (1.f + __expf(-g[i]));
+      const float silu = g[i] * sig;
+      dv[i] = d[i] * silu;
+      dg[i] = d[i] * v[i] * sig * (1.f + g[i] * (1.f - sig));
+    }
+    store8<__nv_bfloat16>(dgu + t * 2 * I + c, dg);
+    store8<__nv_bfloat16>(dgu + t * 2 * I + I + c, dv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat AdamW.  master may be null (update `param` in place with fp32 math).  grad fp32 or bf16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ __nv_bfloat16 f2bf_sr(float f, uint32_t rnd16) {
+  uint32_t bits = __float_as_uint(f);
+  bits += (rnd16 & 0xFFFFu);
+  bits &= 0xFFFF0000u;
+  return __float2bfloat16_rn(__uint_as_float(bits));   // exact: low 16 bits are zero
+}
+
+template <typename PT, typename GT>
+__global__ void adamw_flat_kernel(float* __restrict__ master, PT* __restrict__ param, const GT* __restrict__ grad,
+                                  float* __restrict__ m, float* __restrict__ v, const uint8_t* __restrict__ decay_mask,
+                                  size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
+                                  const float* __restrict__ grad_scale, int sr, uint32_t seed) {
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  const float inv_bc1 = 1.f / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const size_t n8 = n / 8;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < n8; u += (size_t)gridDim.x * blockDim.x) {
+    const size_t i0 = u * 8;
+    float g[8], mm[8], vv[8], p[8];
+    load8<GT>(grad + i0, g);
+    load8<float>(m + i0, mm);
+    load8<float>(v + i0, vv);
+    if (master) load8<float>(master + i0, p); else load8<PT>(param + i0, p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gi = g[i] * gs;
+      const float d = (decay_mask ? (float)decay_mask[i0 + i] : 1.f) * wd;
+      p[i] *= (1.f - lr * d);
+      mm[i] = b1 * mm[i] + (1.f - b1) * gi;
+      vv[i] = b2 * vv[i] + (1.f - b2) * gi * gi;
+      const float denom = sqrtf(vv[i]) * inv_sqrt_bc2 + eps;
+      p[i] -= lr * (mm[i] * inv_bc1) / denom;
+    }
+    store8<float>(m + i0, mm);
+    store8<float>(v + i0, vv);
+    if (master) store8<float>(master + i0, p);
+    if constexpr (std::is_same<PT, __nv_bfloat16>::value) {
+      if (sr) {
+        __nv_bfloat16 o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = f2bf_sr(p[i], hash32(seed ^ hash32((uint32_t)(i0 + i))));
+        *reinterpret_cast<uint4*>(param + i0) = *reinterpret_cast<uint4*>(o);
+      } else {
+        store8<PT>(param + i0, p);
+      }
+    } else {
+      store8<PT>(param + i0, p);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum of squares -> fp32 scalar (pre-zeroed)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sq_norm_kernel(const T* __restrict__ x, size_t n, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  const size_t n8 = n / 8;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < n8; u += (size_t)gridDim.x * blockDim.x) {
+    float f[8];
+    load8<T>(x + u * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += f[i] * f[i];
+  }
+  // tail
+  for (size_t i = n8 * 8 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float f = to_f(x[i]);
+    acc += f * f;
+  }
+  acc = block_sum<256>(acc, sm);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+inline int grid_for(size_t units, int threads, int per_sm) {
+  size_t blocks = (units + threads - 1) / threads;
+  size_t cap = (size_t)at::cuda::getCurrentDeviceProperties()->multiProcessorCount * per_sm;
+  return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+}  // namespace
+
+// ====================================================================================================
+std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, const at::Tensor& w, double eps) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && w.is_contiguous());
+  TORCH_CHECK(x.scalar_type() == w.scalar_type(), "rmsnorm: x and weight dtypes must match");
+  const int rows = x.size(0), H = x.size(1);
+  TORCH_CHECK(H % 8 == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({rows}, x.options().dtype(at::kFloat));
+  auto stream = at::cuda::getCurrentCUDAStream();
+  constexpr int TH = 256;
+  const int grid = std::min(rows, at::cuda::getCurrentDeviceProperties()->multiProcessorCount * 8);
+  if (x.scalar_type() == at::kBFloat16)
+    rmsnorm_fwd_kernel<__nv_bfloat16, TH><<<grid, TH, 0, stream>>>(
+        (const __nv_bfloat16*)x.data_ptr(), (const __nv_bfloat16*)w.data_ptr(), (__nv_bfloat16*)y.data_ptr(),
+        rstd.data_ptr<float>(), rows, H, (float)eps);
+  else
+    rmsnorm_fwd_kernel<float, TH><<<grid, TH, 0, stream>>>(x.data_ptr<float>(), w.data_ptr<float>(),
+                                                           y.data_ptr<float>(), rstd.data_ptr<float>(), rows, H,
+                                                           (float)eps);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {y, rstd};
+}
+
+std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w,
+                                    const at::Tensor& rstd) {
+  const int rows = x.size(0), H = x.size(1);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dx = at::empty_like(x);
+  auto dw = at::zeros({H}, x.options().dtype(at::kFloat));
+  auto stream = at::cuda::getCurrentCUDAStream();
+  constexpr int TH = 256;
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int grid = std::min(rows, sms * 4);
+  const int need_v = (H + TH * 8 - 1) / (TH * 8);
+  TORCH_CHECK(need_v <= 8, "rmsnorm_bwd: hidden size too large");
+#define RUN(T, MAXV)                                                                                          \
+  rmsnorm_bwd_kernel<T, TH, MAXV><<<grid, TH, 0, stream>>>((const T*)dy.data_ptr(), (const T*)x.data_ptr(),     \
+                                                            (const T*)w.data_ptr(), rstd.data_ptr<float>(),      \
+                                                            (T*)dx.data_ptr(), dw.data_ptr<float>(), rows, H)
+  if (x.scalar_type() == at::kBFloat16) {
+    if (need_v <= 1) RUN(__nv_bfloat16, 1); else if (need_v <= 2) RUN(__nv_bfloat16, 2);
+    else if (need_v <= 4) RUN(__nv_bfloat16, 4); else RUN(__nv_bfloat16, 8);
+  } else {
+    if (need_v <= 1) RUN(float, 1); else if (need_v <= 2) RUN(float, 2);
+    else if (need_v <= 4) RUN(float, 4); else RUN(float, 8);
+  }
+#undef RUN
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {dx, dw};
+}
+
+// q [B,S,Hq,D], k [B,S,Hk,D] contiguous bf16, cos/sin [S,D] fp32
+std::vector<at::Tensor> rope_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& cos,
+                                 const at::Tensor& sin, bool conj) {
+  TORCH_CHECK(q.is_cuda() && q.is_contiguous() && k.is_contiguous() && cos.is_contiguous() && sin.is_contiguous());
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 && cos.scalar_type() == at::kFloat);
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4);
+  const int B = q.size(0), S = q.size(1), D = q.size(3);
+  TORCH_CHECK(cos.size(0) == S && cos.size(1) == D && D % 16 == 0);
+  c10::cuda::CUDAGuard guard(q.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  auto qo = at::empty_like(q), ko = at::empty_like(k);
+  for (int which = 0; which < 2; ++which) {
+    const at::Tensor& in = which == 0 ? q : k;
+    at::Tensor& out = which == 0 ? qo : ko;
+    const int NH = in.size(2);
+    const size_t units = (size_t)B * S * NH * (D / 16);
+    if (units == 0) continue;
+    const int grid = grid_for(units, 256, 8);
+    rope_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)in.data_ptr(), (__nv_bfloat16*)out.data_ptr(),
+                                          cos.data_ptr<float>(), sin.data_ptr<float>(), B, S, NH, D, conj ? 1 : 0,
+                                          units);
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {qo, ko};
+}
+
+at::Tensor swiglu_fwd(const at::Tensor& gu) {
+  TORCH_CHECK(gu.is_cuda() && gu.is_contiguous() && gu.scalar_type() == at::kBFloat16);
+  const int two_i = gu.size(-1);
+  const int I = two_i / 2;
+  TORCH_CHECK(I % 8 == 0);
+  const size_t T = gu.numel() / two_i;
+  c10::cuda::CUDAGuard guard(gu.device());
+  auto sizes = gu.sizes().vec();
+  sizes.back() = I;
+  auto out = at::empty(sizes, gu.options());
+  const size_t units = T * (I / 8);
+  swiglu_fwd_kernel<<<grid_for(units, 256, 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      (const __nv_bfloat16*)gu.data_ptr(), (__nv_bfloat16*)out.data_ptr(), T, I);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return out;
+}
+
+at::Tensor swiglu_bwd(const at::Tensor& dout, const at::Tensor& gu) {
+  TORCH_CHECK(dout.is_cuda() && dout.is_contiguous() && gu.is_contiguous());
+  const int I = gu.size(-1) / 2;
+  const size_t T = gu.numel() / (2 * I);
+  c10::cuda::CUDAGuard guard(gu.device());
+  auto dgu = at::empty_like(gu);
+  const size_t units = T * (I / 8);
+  swiglu_bwd_kernel<<<grid_for(units, 256, 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      (const __nv_bfloat16*)dout.data_ptr(), (const __nv_bfloat16*)gu.data_ptr(), (__nv_bfloat16*)dgu.data_ptr(), T, I);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return dgu;
+}
+
+void adamw_flat(at::Tensor master, at::Tensor param, const at::Tensor& grad, at::Tensor m, at::Tensor v,
+                const at::Tensor& decay_mask, double lr, double b1, double b2, double eps, double wd, double bc1,
+                double bc2, const at::Tensor& grad_scale, bool sr, int64_t seed) {
+  TORCH_CHECK(param.is_cuda() && param.is_contiguous() && grad.is_contiguous() && m.is_contiguous() && v.is_contiguous());
+  const size_t n = param.numel();
+  TORCH_CHECK(n % 8 == 0, "adamw_flat: segment length must be a multiple of 8");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(param.data_ptr()) % 16) == 0 && (reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16) == 0 &&
+              (reinterpret_cast<uintptr_t>(m.data_ptr()) % 16) == 0, "adamw_flat: 16-byte aligned segments required");
+  if (n == 0) return;
+  c10::cuda::CUDAGuard guard(param.device());
+  float* mp = master.numel() ? master.data_ptr<float>() : nullptr;
+  const uint8_t* dm = decay_mask.numel() ? decay_mask.data_ptr<uint8_t>() : nullptr;
+  const float* gs = grad_scale.numel() ? grad_scale.data_ptr<float>() : nullptr;
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int grid = grid_for(n / 8, 256, 8);
+#define RUN(PT, GT)                                                                                             \
+  adamw_flat_kernel<PT, GT><<<grid, 256, 0, stream>>>(mp, (PT*)param.data_ptr(), (const GT*)grad.data_ptr(),       \
+                                                       m.data_ptr<float>(), v.data_ptr<float>(), dm, n, (float)lr, \
+                                                       (float)b1, (float)b2, (float)eps, (float)wd, (float)bc1,    \
+                                                       (float)bc2, gs, sr ? 1 : 0, (uint32_t)seed)
+  const bool pb = param.scalar_type() == at::kBFloat16, gb = grad.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(pb || param.scalar_type() == at::kFloat);
+  TORCH_CHECK(gb || grad.scalar_type() == at::kFloat);
+  if (pb && gb) RUN(__nv_bfloat16, __nv_bfloat16);
+  else if (pb && !gb) RUN(__nv_bfloat16, float);
+  else if (!pb && gb) RUN(float, __nv_bfloat16);
+  else RUN(float, float);
+#undef RUN
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+at::Tensor sq_norm(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous());
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = at::zeros({}, x.options().dtype(at::kFloat));
+  const size_t n = x.numel();
+  if (n == 0) return out;
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) % 16) == 0, "sq_norm: 16-byte aligned input required");
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int grid = grid_for((n + 7) / 8, 256, 8);
+  if (x.scalar_type() == at::kBFloat16)
+    sq_norm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x.data_ptr(), n, out.data_ptr<float>());
+  else if (x.scalar_type() == at::kFloat)
+    sq_norm_kernel<float><<<grid, 256, 0, stream>>>(x.data_ptr<float>(), n, out.data_ptr<float>());
+  else
+    TORCH_CHECK(false, "sq_norm: bf16/fp32 only");
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return out;
+}

@@ -1,0 +1,254 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma (fp32 accumulators
+// in TMEM, double buffered) -> tcgen05.ld epilogue -> swizzled smem -> TMA store / TMA reduce-add.
+//
+//   D[M,N] (+)= A * B      A: [M,K] (K-major) or stored [K,M] (MN-major)
+//                          B: stored [N,K] (K-major) or stored [K,N] (MN-major)
+//
+// One kernel serves the three GEMMs of a linear layer without any transposes:
+//   forward  Y  = X  W^T   (A K-major,  B K-major)
+//   dgrad    dX = dY W     (A K-major,  B MN-major)
+//   wgrad    dW += dY^T X  (A MN-major, B MN-major, fp32 reduce-add epilogue into main_grad)
+//
+// Warp roles (192 threads, 1 CTA / SM, grid = #SMs, static round-robin tile schedule with M-grouping for L2):
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..5  : epilogue (TMEM lane quarter = warp_idx % 4)
+// The optional `TileGate` hook lets the fused all-gather->GEMM kernel make the producer wait (acquire at
+// system scope) until the rows of A that a tile needs have arrived from the peer GPU.
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace gemm100 {
+
+using namespace sm100;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
+constexpr int C_STAGE_BYTES = BLOCK_M * 128;           // 128 rows x 128 B (64 bf16 or 32 fp32 columns)
+constexpr int C_BUFS = 2;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + C_BUFS * C_STAGE_BYTES + 1024 /*align slack*/ + 256;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;        // 512
+
+enum OutKind : int { OUT_BF16_STORE = 0, OUT_F32_STORE = 1, OUT_F32_ADD = 2, OUT_BF16_ADD = 3 };
+
+struct Params {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_tiles;
+  int group_m;   // tile-order grouping along M (L2 reuse of B)
+};
+
+struct NoGate {
+  __device__ __forceinline__ void wait_rows(int /*m_blk*/) const {}
+};
+
+__device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, int& n_blk) {
+  const int per_group = p.group_m * p.num_n_blocks;
+  const int g = t / per_group;
+  const int first_m = g * p.group_m;
+  const int gsz = min(p.group_m, p.num_m_blocks - first_m);
+  const int r = t - g * per_group;
+  m_blk = first_m + r % gsz;
+  n_blk = r / gsz;
+}
+
+template <bool A_MN, bool B_MN, int OUT, class TileGate = NoGate>
+__device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a, const CUtensorMap* __restrict__ tma_b,
+                                          const CUtensorMap* __restrict__ tma_c, const Params& p, uint8_t* smem_raw,
+                                          const TileGate& gate, int cta_first_tile, int cta_tile_stride) {
+  const uint32_t warp_idx = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* smem_c = smem_b + STAGES * B_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + C_BUFS * C_STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;         // [ACC_STAGES]
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  if (warp_idx == 0 && elect_one()) {
+    tma_prefetch_desc(tma_a);
+    tma_prefetch_desc(tma_b);
+    tma_prefetch_desc(tma_c);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc<1>(tmem_ptr, TMEM_COLS);
+    tmem_relinquish<1>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp_idx == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
+        int m_blk, n_blk;
+        tile_coords(p, t, m_blk, n_blk);
+        gate.wait_rows(m_blk);
+        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, tma_a, &full_bar[stage], k0, m0);                       // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)                                  // boxes {64 m, 64 k}
+              tma_load_2d(sa + i * (64 * BLOCK_K * 2), tma_a, &full_bar[stage], m0 + i * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, tma_b, &full_bar[stage], k0, n0);                       // box {64 k, 256 n}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i)                                  // boxes {64 n, 64 k}
+              tma_load_2d(sb + i * (64 * BLOCK_K * 2), tma_b, &full_bar[stage], n0 + i * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row.  MN-major: 16 k-rows of 128 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
+            umma_f16<1>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const uint32_t q = warp_idx & 3;                 // TMEM lane quarter this warp may touch
+    const uint32_t row = q * 32 + lane;              // row inside the 128-row tile
+    const bool issuer = (warp_idx == 2 && lane == 0);
+    constexpr bool F32 = (OUT == OUT_F32_STORE || OUT == OUT_F32_ADD);
+    constexpr int COLS_PER_CHUNK = F32 ? 32 : 64;
+    constexpr int NCHUNK = BLOCK_N / COLS_PER_CHUNK;
+    uint32_t acc = 0, acc_phase = 0, cbuf = 0;
+    for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
+      int m_blk, n_blk;
+      tile_coords(p, t, m_blk, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        if (issuer) tma_store_wait_read<C_BUFS - 1>();          // the buffer we are about to overwrite is drained
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* cb = smem_c + cbuf * C_STAGE_BYTES + row * 128;
+        if constexpr (F32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 o = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<uint4*>(cb + ((j ^ (row & 7)) * 16)) = o;
+          }
+        } else {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(taddr + c * 64, v0);
+          tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
+            *reinterpret_cast<uint4*>(cb + ((j ^ (row & 7)) * 16)) = o;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
+            *reinterpret_cast<uint4*>(cb + (((j + 4) ^ (row & 7)) * 16)) = o;
+          }
+        }
+        if (c == NCHUNK - 1) {
+          // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          const int cn = n_blk * BLOCK_N + c * COLS_PER_CHUNK;
+          const int cm = m_blk * BLOCK_M;
+          if (cn < p.N) {
+            if constexpr (OUT == OUT_F32_ADD || OUT == OUT_BF16_ADD)
+              tma_reduce_add_2d(tma_c, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
+            else
+              tma_store_2d(tma_c, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
+          }
+          tma_store_commit();
+        }
+        cbuf ^= 1;
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace gemm100

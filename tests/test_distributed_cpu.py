@@ -1,0 +1,37 @@
+"""Multi-process gloo tests (world_size > 1 on the CPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT = [29600]
+
+
+def run_dist(script, nproc, env=None, timeout=600):
+    _PORT[0] += 1
+    e = dict(os.environ)
+    e.update({"OMP_NUM_THREADS": "1"})
+    e.update(env or {})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_PORT[0]), os.path.join(HERE, "dist_scripts", script)]
+    r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=timeout, cwd=os.path.join(HERE, "dist_scripts"))
+    assert r.returncode == 0 and "DIST_TEST_OK" in r.stdout, f"{script} failed:\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
+
+
+pytestmark = pytest.mark.dist
+
+
+@pytest.mark.parametrize("tp", [2, 4])
+def test_tp_sp_layers_match_dense(tp):
+    run_dist("tp_layers.py", tp, {"TP": str(tp)})
+
+
+def test_zero1_matches_adamw():
+    run_dist("zero1.py", 2)
+
+
+@pytest.mark.parametrize("pp,vpp,tp,nmb", [(2, 1, 1, 4), (4, 1, 1, 6), (2, 2, 1, 4), (2, 1, 2, 3), (4, 2, 1, 8)])
+def test_pipeline_matches_unpipelined(pp, vpp, tp, nmb):
+    run_dist("pipeline.py", pp * tp, {"PP": str(pp), "VPP": str(vpp), "TP": str(tp), "NMB": str(nmb)})

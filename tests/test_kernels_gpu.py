@@ -1,0 +1,144 @@
+"""sm_100a kernels vs plain PyTorch fp32 references (run on the B200 box: pytest -m gpu)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from neuronx_distributed_training_b200 import ops
+    c = ops.C()
+    assert c is not None, f"native extension missing: {ops._native_loader.load_error()}"
+    return c
+
+
+def _rel_err(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (1024, 768, 4096), (8192, 4096, 512),
+                                   (200, 264, 136), (4096, 3584, 4096), (72, 8, 40)])
+@pytest.mark.parametrize("layout", ["nt", "nn", "tn"])
+def test_gemm_layouts(C, M, N, K, layout):
+    torch.manual_seed(0)
+    dev = "cuda"
+    if layout == "nt":      # out = a[M,K] @ b[N,K]^T
+        a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
+        ref = a.float() @ b.float().t(); flags = (True, True)
+    elif layout == "nn":    # out = a[M,K] @ b[K,N]
+        a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(K, N, device=dev).bfloat16()
+        ref = a.float() @ b.float(); flags = (True, False)
+    else:                   # out = a[K,M]^T @ b[K,N]
+        a = torch.randn(K, M, device=dev).bfloat16(); b = torch.randn(K, N, device=dev).bfloat16()
+        ref = a.float().t() @ b.float(); flags = (False, False)
+    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    C.gemm(a, b, out, flags[0], flags[1], False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert _rel_err(out, ref) < 6e-3, f"{layout} {M}x{N}x{K}: rel err {_rel_err(out, ref)}"
+
+
+def test_gemm_fp32_accumulate(C):
+    torch.manual_seed(1)
+    K, M, N = 2048, 384, 520
+    a = torch.randn(K, M, device="cuda").bfloat16(); b = torch.randn(K, N, device="cuda").bfloat16()
+    acc = torch.randn(M, N, device="cuda")
+    ref = acc + a.float().t() @ b.float()
+    C.gemm(a, b, acc, False, False, True)
+    C.gemm(a, b, acc, False, False, True)
+    ref = ref + a.float().t() @ b.float()
+    assert _rel_err(acc, ref) < 1e-3
+    out = torch.empty(M, N, device="cuda")
+    C.gemm(a, b, out, False, False, False)
+    assert _rel_err(out, a.float().t() @ b.float()) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,H", [(64, 1024), (1000, 4096), (33, 8192)])
+def test_rmsnorm(C, dtype, rows, H):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(rows, H, device="cuda", dtype=dtype, requires_grad=True)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(dtype).requires_grad_(True)
+    y = ops.rmsnorm(x, w, 1e-5)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr = x.detach().float().requires_grad_(True); wr = w.detach().float().requires_grad_(True)
+    yr = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5) * wr
+    yr.backward(g.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+    assert _rel_err(y, yr) < tol
+    assert _rel_err(x.grad, xr.grad) < tol
+    assert _rel_err(w.grad, wr.grad) < tol
+
+
+def test_rope(C):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    B, S, Hq, Hk, D = 2, 384, 8, 2, 128
+    q = torch.randn(B, S, Hq, D, device="cuda").bfloat16().requires_grad_(True)
+    k = torch.randn(B, S, Hk, D, device="cuda").bfloat16().requires_grad_(True)
+    inv = 1.0 / (10000 ** (torch.arange(0, D, 2, device="cuda").float() / D))
+    fr = torch.outer(torch.arange(S, device="cuda").float(), inv)
+    emb = torch.cat([fr, fr], -1)
+    cos, sin = emb.cos(), emb.sin()
+    qo, ko = ops.rope(q, k, cos, sin)
+    gq, gk = torch.randn_like(qo), torch.randn_like(ko)
+    torch.autograd.backward([qo, ko], [gq, gk])
+    q2 = q.detach().float().requires_grad_(True); k2 = k.detach().float().requires_grad_(True)
+    qr, kr = ops.rope_ref(q2, cos, sin), ops.rope_ref(k2, cos, sin)
+    torch.autograd.backward([qr, kr], [gq.float(), gk.float()])
+    assert _rel_err(qo, qr) < 1e-2 and _rel_err(ko, kr) < 1e-2
+    assert _rel_err(q.grad, q2.grad) < 1e-2 and _rel_err(k.grad, k2.grad) < 1e-2
+
+
+def test_swiglu(C):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(513, 2 * 1792, device="cuda").bfloat16().requires_grad_(True)
+    y = ops.swiglu(x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    x2 = x.detach().float().requires_grad_(True)
+    y2 = ops.swiglu_ref(x2)
+    y2.backward(g.float())
+    assert _rel_err(y, y2) < 1e-2 and _rel_err(x.grad, x2.grad) < 1e-2
+
+
+@pytest.mark.parametrize("gdtype", [torch.float32, torch.bfloat16])
+def test_adamw_flat(C, gdtype):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    n = 8 * 12345
+    master = torch.randn(n, device="cuda")
+    p = master.bfloat16()
+    g = torch.randn(n, device="cuda").to(gdtype)
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    ref = torch.nn.Parameter(master.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    scale = torch.tensor(0.5, device="cuda")
+    for step in range(1, 4):
+        ref.grad = g.float() * 0.5
+        opt.step()
+        ops.adamw_step_flat(master, p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.1, step, grad_scale=scale)
+    assert _rel_err(master, ref.data) < 1e-5
+    assert _rel_err(p, ref.data) < 5e-3
+    # stochastic rounding is unbiased
+    master2 = torch.full((8 * 4096,), 1.0 + 2 ** -10, device="cuda")
+    p2 = torch.zeros_like(master2, dtype=torch.bfloat16)
+    ops.adamw_step_flat(master2, p2, torch.zeros_like(master2), torch.zeros_like(master2), torch.zeros_like(master2),
+                        0.0, 0.9, 0.95, 1e-8, 0.0, 1, stochastic_rounding=True, seed=3)
+    assert abs(p2.float().mean().item() - (1.0 + 2 ** -10)) < 2e-4
+    assert p2.float().unique().numel() == 2
+
+
+def test_sq_norm(C):
+    from neuronx_distributed_training_b200 import ops
+    x = torch.randn(1_000_003 + 5, device="cuda")[:1_000_003]
+    xa = x[:1_000_000].contiguous()
+    assert abs(ops.sq_norm(xa).item() - xa.double().pow(2).sum().item()) / xa.double().pow(2).sum().item() < 1e-5
+    xb = torch.randn(777_776, device="cuda").bfloat16()
+    assert abs(ops.sq_norm(xb).item() - xb.double().pow(2).sum().item()) / xb.double().pow(2).sum().item() < 1e-4
