@@ -374,6 +374,19 @@ def adamw_step_flat(master: Optional[torch.Tensor], param: torch.Tensor, grad: t
                        exp_avg, exp_avg_sq, decay_mask if decay_mask is not None else torch.empty(0, dtype=torch.uint8, device=param.device),
                        lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale.float(), stochastic_rounding, seed)
         return
+    # torch path: walk the flat segment in bounded chunks so temporaries stay small (the full-segment
+    # form needs ~4 fp32 temporaries of the whole shard, i.e. >100 GB for an 8B model on one GPU)
+    n = param.numel()
+    CH = 1 << 26
+    for lo in range(0, n, CH):
+        hi = min(n, lo + CH)
+        _adamw_chunk_torch(None if master is None else master[lo:hi], param[lo:hi], grad[lo:hi], exp_avg[lo:hi],
+                           exp_avg_sq[lo:hi], lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
+                           None if decay_mask is None else decay_mask[lo:hi], stochastic_rounding, seed + lo)
+
+
+def _adamw_chunk_torch(master, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                       grad_scale, decay_mask, stochastic_rounding, seed):
     g = grad.float() * grad_scale
     p32 = master if master is not None else param.float()
     if weight_decay != 0.0:
@@ -386,7 +399,7 @@ def adamw_step_flat(master: Optional[torch.Tensor], param: torch.Tensor, grad: t
     m32.mul_(beta1).add_(g, alpha=1.0 - beta1)
     v32.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
     denom = (v32 / bc2).sqrt_().add_(eps)
-    p32.addcdiv_(m32 / bc1, denom, value=-lr)
+    p32.addcdiv_(m32, denom, value=-lr / bc1)
     if m32 is not exp_avg:
         exp_avg.copy_(m32)
     if v32 is not exp_avg_sq:

@@ -143,7 +143,10 @@ def initialize_model_parallel(tensor_model_parallel_size: int = 1, pipeline_mode
                 g = dist.new_group(ranks=ranks) if len(ranks) > 1 else None
             if rank in ranks:
                 mine = (g, ranks)
-        assert mine is not None, f"rank {rank} is in no {kind} group"
+        if mine is None:
+            # only first/last pipeline stages belong to an embedding group
+            assert kind == "embed", f"rank {rank} is in no {kind} group"
+            mine = (None, [])
         _GROUPS[kind], _GROUP_RANKS[kind] = mine
 
 

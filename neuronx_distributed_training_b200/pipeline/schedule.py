@@ -53,17 +53,20 @@ class P2PCommunicator:
     def exchange(self, send_next: Optional[torch.Tensor] = None, send_prev: Optional[torch.Tensor] = None,
                  recv_prev: bool = False, recv_next: bool = False):
         """One batched p2p round.  Returns (tensor_from_prev, tensor_from_next)."""
+        # Ordering matters when prev == next (pipeline size 2 with virtual stages): messages between one
+        # pair of ranks are matched in issue order, so receives must mirror the peer's send order
+        # (gradients first, then activations).
         ops, from_prev, from_next = [], None, None
         if send_prev is not None:
             ops.append(dist.P2POp(dist.isend, send_prev.contiguous(), self.prev, self.group))
-        if recv_prev:
-            from_prev = self._buf()
-            ops.append(dist.P2POp(dist.irecv, from_prev, self.prev, self.group))
         if send_next is not None:
             ops.append(dist.P2POp(dist.isend, send_next.contiguous(), self.next, self.group))
         if recv_next:
             from_next = self._buf()
             ops.append(dist.P2POp(dist.irecv, from_next, self.next, self.group))
+        if recv_prev:
+            from_prev = self._buf()
+            ops.append(dist.P2POp(dist.irecv, from_prev, self.prev, self.group))
         self._run(ops)
         return from_prev, from_next
 
