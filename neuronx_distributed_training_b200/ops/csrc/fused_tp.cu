@@ -1,0 +1,367 @@
+// Fused tensor-parallel kernels for sm_100a over NVSwitch peer memory.
+//
+//   all-gather -> GEMM     : a few "comm" CTAs pull the peers' sequence shards with TMA bulk copies
+//                            (peer HBM -> smem ring -> local gathered buffer) and publish per-row-block ready flags;
+//                            the remaining CTAs run the tcgen05 GEMM, whose TMA producer waits (acquire) on the
+//                            flag of the rows a tile / k-block needs.  Tile order is rotated so every rank starts
+//                            on its own shard and walks the ring, i.e. transfer and math overlap block by block.
+//   GEMM -> reduce-scatter : the GEMM epilogue writes each finished partial tile straight into the staging
+//                            buffer of the rank that owns those rows (st.global to a peer-mapped pointer) and
+//                            bumps that rank's per-row-block arrival counter (red.release.sys); after its last
+//                            tile every CTA turns into a reducer that sums the TP partial slabs of the row-blocks
+//                            that have fully arrived (fp32 accumulate) into the local output.
+// Cross-GPU ordering: one monotonically increasing epoch per call.  Kernels start with an all-peer
+// handshake (st.release.sys of the epoch into every peer's slot, ld.acquire.sys on the own slots) which both
+// publishes "my input shard is ready" and proves "the peer has finished the call that last used this
+// double-buffer parity", so buffers are reused safely two calls later.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "gemm_sm100.cuh"
+#include "tma_utils.h"
+
+namespace gemm100 {
+Params make_params(int M, int N, int K);
+void make_operand_maps(const void* a, const void* b, int M, int N, int K, bool a_kmajor, bool b_kmajor,
+                       CUtensorMap& ta, CUtensorMap& tb);
+CUtensorMap make_out_map(void* out, int M, int N, bool f32);
+}  // namespace gemm100
+
+namespace fused {
+
+using namespace gemm100;
+constexpr int MAX_TP = 8;
+constexpr int RING_SLOTS = 6;
+constexpr int PIECE_BYTES = 32 * 1024;
+
+struct CommArgs {
+  const uint8_t* peer_x[MAX_TP];   // every rank's input shard (symmetric buffer, this call's parity)
+  uint32_t* hs_peer[MAX_TP];       // every rank's handshake array
+  uint32_t* hs_local;              // my handshake array [tp]
+  uint8_t* xg;                     // local gathered buffer [tp * rows_per_rank, row_bytes]
+  uint32_t* flags;                 // local ready flags, one per 128-row block of xg
+  uint32_t epoch;
+  int rank, tp, rows_per_rank, row_bytes, num_comm_ctas;
+};
+
+struct AgGate {
+  const uint32_t* flags;
+  uint32_t epoch;
+  int mode;   // 0: gathered operand indexed by m-block, 1: by k-block (wgrad)
+  __device__ __forceinline__ void wait_flag(int blk) const {
+    while (ld_acquire_gpu(flags + blk) != epoch) __nanosleep(64);
+    fence_proxy_async_all();   // generic-proxy acquire -> subsequent async-proxy (TMA) reads
+  }
+  __device__ __forceinline__ void wait_m(int m_blk) const {
+    if (mode == 0) wait_flag(m_blk);
+  }
+  __device__ __forceinline__ void wait_k(int kb) const {
+    if (mode == 1) wait_flag(kb >> 1);   // BLOCK_K = 64 rows, flags are per 128 rows
+  }
+  __device__ __forceinline__ void before_first_store() const {}
+  __device__ __forceinline__ __nv_bfloat16* peer_row_ptr(int, int) const { return nullptr; }
+  __device__ __forceinline__ void tile_done(int) const {}
+};
+
+__device__ __forceinline__ void send_handshake(uint32_t* const* hs_peer, int rank, int tp, uint32_t epoch) {
+  for (int p = 0; p < tp; ++p) st_release_sys(hs_peer[p] + rank, epoch);
+}
+
+// One thread per comm CTA drives: peer/global --bulk--> smem ring --bulk--> local gathered buffer.
+__device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING_SLOTS * PIECE_BYTES);
+  if (threadIdx.x != 0) return;
+  if (blockIdx.x == 0) send_handshake(a.hs_peer, a.rank, a.tp, a.epoch);
+  for (int i = 0; i < RING_SLOTS; ++i) mbar_init(&full[i], 1);
+  fence_barrier_init();
+  const int blocks_per_rank = a.rows_per_rank / 128;
+  const int total_blocks = blocks_per_rank * a.tp;
+  const size_t block_bytes = (size_t)128 * a.row_bytes;
+  const int pieces = (int)((block_bytes + PIECE_BYTES - 1) / PIECE_BYTES);
+  uint32_t slot_phase = 0;   // bit i = phase parity of ring slot i
+  int waited_rank_mask = 0;
+  for (int idx = blockIdx.x; idx < total_blocks; idx += a.num_comm_ctas) {
+    int blk = idx + a.rank * blocks_per_rank;
+    if (blk >= total_blocks) blk -= total_blocks;
+    const int src_rank = blk / blocks_per_rank;
+    if (!((waited_rank_mask >> src_rank) & 1)) {
+      // the peer's shard for this epoch is in place (and it is done with the previous use of my buffers)
+      while (ld_acquire_sys(a.hs_local + src_rank) < a.epoch) __nanosleep(100);
+      waited_rank_mask |= 1 << src_rank;
+    }
+    const uint8_t* src = a.peer_x[src_rank] + (size_t)(blk - src_rank * blocks_per_rank) * block_bytes;
+    uint8_t* dst = a.xg + (size_t)blk * block_bytes;
+    auto piece_bytes = [&](int p) -> uint32_t {
+      const size_t off = (size_t)p * PIECE_BYTES;
+      return (uint32_t)min((size_t)PIECE_BYTES, block_bytes - off);
+    };
+    const int prime = min(pieces, RING_SLOTS);
+    for (int p = 0; p < prime; ++p) {
+      mbar_expect_tx(&full[p], piece_bytes(p));
+      bulk_g2s(ring + p * PIECE_BYTES, src + (size_t)p * PIECE_BYTES, piece_bytes(p), &full[p]);
+    }
+    for (int p = 0; p < pieces; ++p) {
+      const int s = p % RING_SLOTS;
+      mbar_wait(&full[s], (slot_phase >> s) & 1);
+      slot_phase ^= 1u << s;
+      bulk_s2g(dst + (size_t)p * PIECE_BYTES, ring + s * PIECE_BYTES, piece_bytes(p));
+      tma_store_commit();
+      const int np = p + RING_SLOTS;
+      if (np < pieces) {
+        tma_store_wait_read<0>();   // smem slot drained by the store before the next load lands in it
+        mbar_expect_tx(&full[s], piece_bytes(np));
+        bulk_g2s(ring + s * PIECE_BYTES, src + (size_t)np * PIECE_BYTES, piece_bytes(np), &full[s]);
+      }
+    }
+    tma_store_wait<0>();           // all bytes of this row-block are written
+    fence_proxy_async_all();
+    __threadfence();
+    st_release_gpu(a.flags + blk, a.epoch);
+  }
+}
+
+template <bool A_MN, bool B_MN, int OUT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const Params p, const CommArgs comm, const int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  if ((int)blockIdx.x < comm.num_comm_ctas) {
+    comm_cta(comm, smem_raw);
+    return;
+  }
+  AgGate gate{comm.flags, comm.epoch, mode};
+  gemm_body<A_MN, B_MN, OUT, AgGate>(&tma_a, &tma_b, &tma_c, p, smem_raw, gate, (int)blockIdx.x - comm.num_comm_ctas,
+                                     (int)gridDim.x - comm.num_comm_ctas);
+}
+
+// pure all-gather (same comm CTAs, no GEMM): used where the gathered tensor is needed on its own
+__global__ void __launch_bounds__(NUM_THREADS, 1) ag_only_kernel(const CommArgs comm) {
+  extern __shared__ uint8_t smem_raw[];
+  comm_cta(comm, smem_raw);
+}
+
+// --------------------------------------------------------------------------------------------------
+struct RsArgs {
+  __nv_bfloat16* stage_peer[MAX_TP];   // every rank's staging buffer [tp][rows_per_rank][N] (this parity)
+  uint32_t* counter_peer[MAX_TP];      // every rank's arrival counters [blocks_per_rank] (this parity)
+  uint32_t* hs_peer[MAX_TP];
+  uint32_t* hs_local;
+  const __nv_bfloat16* stage_local;
+  uint32_t* counter_local;
+  __nv_bfloat16* out;                  // [rows_per_rank, N]
+  uint32_t epoch;
+  int rank, tp, rows_per_rank, N, num_n_blocks;
+};
+
+struct RsGate {
+  RsArgs a;
+  __device__ __forceinline__ void wait_m(int) const {}
+  __device__ __forceinline__ void wait_k(int) const {}
+  __device__ __forceinline__ void before_first_store() const {
+    if (threadIdx.x == 64) {
+      for (int p = 0; p < a.tp; ++p)
+        while (ld_acquire_sys(a.hs_local + p) < a.epoch) __nanosleep(100);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  __device__ __forceinline__ __nv_bfloat16* peer_row_ptr(int grow, int gcol) const {
+    const int d = grow / a.rows_per_rank;
+    const int l = grow - d * a.rows_per_rank;
+    return a.stage_peer[d] + ((size_t)a.rank * a.rows_per_rank + l) * a.N + gcol;
+  }
+  __device__ __forceinline__ void tile_done(int m_blk) const {
+    const int bpr = a.rows_per_rank / 128;
+    const int d = m_blk / bpr;
+    red_add_release_sys(a.counter_peer[d] + (m_blk - d * bpr), 1u);
+  }
+};
+
+template <bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const Params p, const RsArgs rs) {
+  extern __shared__ uint8_t smem_raw[];
+  if (blockIdx.x == 0 && threadIdx.x == 0) send_handshake(rs.hs_peer, rs.rank, rs.tp, rs.epoch);
+  RsGate gate{rs};
+  gemm_body<false, B_MN, OUT_BF16_PEER, RsGate>(&tma_a, &tma_b, &tma_c, p, smem_raw, gate, blockIdx.x, gridDim.x);
+  // ---------------- reduce phase: sum the TP partial slabs of my rows ----------------
+  const int bpr = rs.rows_per_rank / 128;
+  const int n_chunks = (rs.N + 255) / 256;
+  const uint32_t target = (uint32_t)(rs.tp * rs.num_n_blocks);
+  for (int item = blockIdx.x; item < bpr * n_chunks; item += gridDim.x) {
+    const int rb = item / n_chunks, nc = item - rb * n_chunks;
+    if (threadIdx.x == 0) {
+      while (ld_acquire_sys(rs.counter_local + rb) < target) __nanosleep(200);
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < 128 * 32; u += NUM_THREADS) {
+      const int r = u >> 5, c8 = (u & 31) * 8;
+      const int col = nc * 256 + c8;
+      if (col >= rs.N) continue;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int s = 0; s < rs.tp; ++s) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(
+            rs.stage_local + ((size_t)s * rs.rows_per_rank + rb * 128 + r) * rs.N + col));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(rs.out + ((size_t)rb * 128 + r) * rs.N + col) = o;
+    }
+    __syncthreads();
+  }
+}
+
+template <class K>
+static void set_smem(K kern) {
+  C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+}
+
+static void fill_ptrs(const std::vector<int64_t>& v, int tp, void** dst) {
+  TORCH_CHECK((int)v.size() == tp, "expected one pointer per TP rank");
+  for (int i = 0; i < MAX_TP; ++i) dst[i] = i < tp ? reinterpret_cast<void*>(v[i]) : nullptr;
+}
+
+}  // namespace fused
+
+// mode 0: out[M_total,N] = xg[M_total,K] * op(b)            (b: [N,K] if b_kmajor else [K,N])
+// mode 1: out[N',K'] (+)= other[M_total,N']^T * xg[M_total,K']   (wgrad; `b` unused)
+// xg is filled inside the kernel from the peers' shards `peer_x` ([rows_per_rank, K] each).
+void ag_gemm(at::Tensor xg, const at::Tensor& b, at::Tensor out, const at::Tensor& other, std::vector<int64_t> peer_x,
+             int64_t flags_ptr, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank,
+             int64_t tp, int64_t mode, bool b_kmajor, bool accumulate, int64_t num_comm_ctas) {
+  using namespace fused;
+  TORCH_CHECK(xg.is_cuda() && xg.is_contiguous() && xg.scalar_type() == at::kBFloat16 && xg.dim() == 2);
+  TORCH_CHECK(tp >= 2 && tp <= MAX_TP);
+  const int M_total = xg.size(0), Kx = xg.size(1);
+  const int rows_per_rank = M_total / tp;
+  TORCH_CHECK(rows_per_rank * tp == M_total && rows_per_rank % 128 == 0, "ag_gemm: rows per rank must be a multiple of 128");
+  c10::cuda::CUDAGuard guard(xg.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  CommArgs comm;
+  fill_ptrs(peer_x, tp, (void**)comm.peer_x);
+  fill_ptrs(hs_peer, tp, (void**)comm.hs_peer);
+  comm.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
+  comm.xg = reinterpret_cast<uint8_t*>(xg.data_ptr());
+  comm.flags = reinterpret_cast<uint32_t*>(flags_ptr);
+  comm.epoch = (uint32_t)epoch;
+  comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
+  comm.num_comm_ctas = num_comm_ctas;
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  TORCH_CHECK(num_comm_ctas >= 1 && num_comm_ctas < sms);
+  CUtensorMap ta, tb, tc;
+  Params p;
+  if (mode == 0) {
+    const int N = b_kmajor ? b.size(0) : b.size(1);
+    TORCH_CHECK((b_kmajor ? b.size(1) : b.size(0)) == Kx && b.is_contiguous());
+    TORCH_CHECK(out.size(0) == M_total && out.size(1) == N && out.scalar_type() == at::kBFloat16 && out.is_contiguous());
+    make_operand_maps(xg.data_ptr(), b.data_ptr(), M_total, N, Kx, true, b_kmajor, ta, tb);
+    tc = make_out_map(out.data_ptr(), M_total, N, false);
+    p = make_params(M_total, N, Kx);
+    p.group_m = 1;                                         // all n-tiles of one row-block before the next
+    p.m_first = rank * (rows_per_rank / 128);
+    auto run = [&](auto kern) {
+      static bool once = false;
+      if (!once) { set_smem(kern); once = true; }
+      kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p, comm, 0);
+    };
+    if (b_kmajor) run(ag_gemm_kernel<false, false, OUT_BF16_STORE>);
+    else run(ag_gemm_kernel<false, true, OUT_BF16_STORE>);
+  } else {
+    // wgrad: A = other (dY, stored [M_total, N'] => MN-major), B = xg (stored [M_total, K'] => MN-major)
+    const int Np = other.size(1);
+    TORCH_CHECK(other.size(0) == M_total && other.is_contiguous() && other.scalar_type() == at::kBFloat16);
+    TORCH_CHECK(out.size(0) == Np && out.size(1) == Kx && out.is_contiguous());
+    const bool f32 = out.scalar_type() == at::kFloat;
+    make_operand_maps(other.data_ptr(), xg.data_ptr(), Np, Kx, M_total, false, false, ta, tb);
+    tc = make_out_map(out.data_ptr(), Np, Kx, f32);
+    p = make_params(Np, Kx, M_total);
+    p.k_first = rank * (rows_per_rank / 64);
+    auto run = [&](auto kern) {
+      static bool once = false;
+      if (!once) { set_smem(kern); once = true; }
+      kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p, comm, 1);
+    };
+    if (f32) { if (accumulate) run(ag_gemm_kernel<true, true, OUT_F32_ADD>); else run(ag_gemm_kernel<true, true, OUT_F32_STORE>); }
+    else { if (accumulate) run(ag_gemm_kernel<true, true, OUT_BF16_ADD>); else run(ag_gemm_kernel<true, true, OUT_BF16_STORE>); }
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void ag_only(at::Tensor xg, std::vector<int64_t> peer_x, int64_t flags_ptr, int64_t hs_local_ptr,
+             std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t num_comm_ctas) {
+  using namespace fused;
+  const int M_total = xg.size(0), Kx = xg.size(1);
+  const int rows_per_rank = M_total / tp;
+  TORCH_CHECK(rows_per_rank % 128 == 0);
+  c10::cuda::CUDAGuard guard(xg.device());
+  CommArgs comm;
+  fill_ptrs(peer_x, tp, (void**)comm.peer_x);
+  fill_ptrs(hs_peer, tp, (void**)comm.hs_peer);
+  comm.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
+  comm.xg = reinterpret_cast<uint8_t*>(xg.data_ptr());
+  comm.flags = reinterpret_cast<uint32_t*>(flags_ptr);
+  comm.epoch = (uint32_t)epoch;
+  comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
+  comm.num_comm_ctas = num_comm_ctas;
+  static bool once = false;
+  if (!once) { set_smem(ag_only_kernel); once = true; }
+  ag_only_kernel<<<num_comm_ctas, NUM_THREADS, SMEM_BYTES, at::cuda::getCurrentCUDAStream()>>>(comm);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// out[rows_per_rank, N] = reduce_scatter_rows( a[M_total, K] * op(b) )
+void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
+             std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
+             int64_t rank, int64_t tp, bool b_kmajor) {
+  using namespace fused;
+  TORCH_CHECK(a.is_cuda() && a.is_contiguous() && b.is_contiguous() && out.is_contiguous());
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16);
+  const int M_total = a.size(0), K = a.size(1);
+  const int N = b_kmajor ? b.size(0) : b.size(1);
+  TORCH_CHECK((b_kmajor ? b.size(1) : b.size(0)) == K);
+  const int rows_per_rank = M_total / tp;
+  TORCH_CHECK(rows_per_rank * tp == M_total && rows_per_rank % 128 == 0 && N % 8 == 0);
+  TORCH_CHECK(out.size(0) == rows_per_rank && out.size(1) == N);
+  c10::cuda::CUDAGuard guard(a.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  RsArgs rs;
+  fill_ptrs(stage_peer, tp, (void**)rs.stage_peer);
+  fill_ptrs(counter_peer, tp, (void**)rs.counter_peer);
+  fill_ptrs(hs_peer, tp, (void**)rs.hs_peer);
+  rs.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
+  rs.stage_local = rs.stage_peer[rank];
+  rs.counter_local = rs.counter_peer[rank];
+  rs.out = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
+  rs.epoch = (uint32_t)epoch;
+  rs.rank = rank; rs.tp = tp; rs.rows_per_rank = rows_per_rank; rs.N = N;
+  CUtensorMap ta, tb, tc;
+  make_operand_maps(a.data_ptr(), b.data_ptr(), M_total, N, K, true, b_kmajor, ta, tb);
+  tc = ta;   // unused by the peer epilogue
+  Params p = make_params(M_total, N, K);
+  rs.num_n_blocks = p.num_n_blocks;
+  p.group_m = 1;
+  // start with the rows owned by rank+1 and finish with my own rows: what I need from the others arrives
+  // while I am still computing, and what the others need from me is produced in ring order
+  p.m_first = ((rank + 1) % tp) * (rows_per_rank / 128);
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  C10_CUDA_CHECK(cudaMemsetAsync(rs.counter_local, 0, sizeof(uint32_t) * (rows_per_rank / 128), stream));
+  auto run = [&](auto kern) {
+    static bool once = false;
+    if (!once) { set_smem(kern); once = true; }
+    kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p, rs);
+  };
+  if (b_kmajor) run(gemm_rs_kernel<false>); else run(gemm_rs_kernel<true>);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}

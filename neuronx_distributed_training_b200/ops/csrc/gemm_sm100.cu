@@ -29,6 +29,11 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+Params make_params(int M, int N, int K);
+void make_operand_maps(const void* a, const void* b, int M, int N, int K, bool a_kmajor, bool b_kmajor,
+                       CUtensorMap& ta, CUtensorMap& tb);
+CUtensorMap make_out_map(void* out, int M, int N, bool f32);
+
 Params make_params(int M, int N, int K) {
   Params p;
   p.M = M; p.N = N; p.K = K;
@@ -36,6 +41,8 @@ Params make_params(int M, int N, int K) {
   p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
   p.num_tiles = p.num_m_blocks * p.num_n_blocks;
   p.group_m = 8;
+  p.m_first = 0;
+  p.k_first = 0;
   return p;
 }
 

@@ -36,16 +36,26 @@ constexpr int NUM_THREADS = 192;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + C_BUFS * C_STAGE_BYTES + 1024 /*align slack*/ + 256;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;        // 512
 
-enum OutKind : int { OUT_BF16_STORE = 0, OUT_F32_STORE = 1, OUT_F32_ADD = 2, OUT_BF16_ADD = 3 };
+enum OutKind : int { OUT_BF16_STORE = 0, OUT_F32_STORE = 1, OUT_F32_ADD = 2, OUT_BF16_ADD = 3, OUT_BF16_PEER = 4 };
 
 struct Params {
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_tiles;
   int group_m;   // tile-order grouping along M (L2 reuse of B)
+  int m_first;   // rotation of the m-block order (fused collectives start at a rank-dependent shard)
+  int k_first;   // rotation of the k-block order (all-gather fused into the K loop of wgrad)
 };
 
+// Hook object threaded through the kernel.  The plain GEMM uses NoGate; the fused collectives provide
+//   wait_m / wait_k : block the TMA producer until the rows of the gathered operand have arrived
+//   peer_row_ptr    : destination of an output row in a peer GPU's staging buffer (GEMM -> reduce-scatter)
+//   tile_done       : publish a finished tile to its owner rank
 struct NoGate {
-  __device__ __forceinline__ void wait_rows(int /*m_blk*/) const {}
+  __device__ __forceinline__ void wait_m(int /*m_blk*/) const {}
+  __device__ __forceinline__ void wait_k(int /*k_blk*/) const {}
+  __device__ __forceinline__ void before_first_store() const {}
+  __device__ __forceinline__ __nv_bfloat16* peer_row_ptr(int /*grow*/, int /*gcol*/) const { return nullptr; }
+  __device__ __forceinline__ void tile_done(int /*m_blk*/) const {}
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, int& n_blk) {
@@ -56,6 +66,8 @@ __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, 
   const int r = t - g * per_group;
   m_blk = first_m + r % gsz;
   n_blk = r / gsz;
+  m_blk += p.m_first;
+  if (m_blk >= p.num_m_blocks) m_blk -= p.num_m_blocks;
 }
 
 template <bool A_MN, bool B_MN, int OUT, class TileGate = NoGate>
@@ -107,9 +119,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
       for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
         int m_blk, n_blk;
         tile_coords(p, t, m_blk, n_blk);
-        gate.wait_rows(m_blk);
+        gate.wait_m(m_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kbi = 0; kbi < num_k_blocks; ++kbi) {
+          int kb = kbi + p.k_first;
+          if (kb >= num_k_blocks) kb -= num_k_blocks;
+          gate.wait_k(kb);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
@@ -173,12 +188,56 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
     constexpr int COLS_PER_CHUNK = F32 ? 32 : 64;
     constexpr int NCHUNK = BLOCK_N / COLS_PER_CHUNK;
     uint32_t acc = 0, acc_phase = 0, cbuf = 0;
+    bool first_store = true;
     for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
       int m_blk, n_blk;
       tile_coords(p, t, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BLOCK_N;
+      if constexpr (OUT == OUT_BF16_PEER) {
+        // GEMM -> reduce-scatter: every thread owns one output row and writes it straight into the staging
+        // buffer of the rank that owns that row (peer memory over NVLink), 128 B at a time.
+        if (first_store) { gate.before_first_store(); first_store = false; }
+        const int grow = m_blk * BLOCK_M + (int)row;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(taddr + c * 64, v0);
+          tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
+          tmem_ld_wait();
+          const int gcol = n_blk * BLOCK_N + c * 64;
+          if (grow < p.M && gcol < p.N) {
+            uint4* dst = reinterpret_cast<uint4*>(gate.peer_row_ptr(grow, gcol));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
+              o.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
+              o.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
+              dst[j] = o;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
+              o.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
+              o.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
+              dst[4 + j] = o;
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        __threadfence_system();                          // this thread's peer stores are visible system-wide
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) gate.tile_done(m_blk);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
         if (issuer) tma_store_wait_read<C_BUFS - 1>();          // the buffer we are about to overwrite is drained
@@ -240,7 +299,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-    if (issuer) tma_store_wait<0>();
+    if constexpr (OUT != OUT_BF16_PEER) {
+      if (issuer) tma_store_wait<0>();
+    }
   }
 
   tcgen05_fence_before();

@@ -1,0 +1,207 @@
+"""Host side of the fused tensor-parallel kernels (``ops/csrc/fused_tp.cu``).
+
+One ``FusedTP`` object per tensor-parallel group owns a *symmetric* workspace (same layout on every rank,
+peer-mapped over NVLink through ``torch.distributed._symmetric_memory``):
+
+    [ handshake slots | RS arrival counters x2 | input-shard buffers x2 | RS staging slabs x2 ]
+
+and a monotonically increasing ``epoch`` (every fused call on every rank of the group advances it in
+lock-step, which is what makes the double-buffer parity protocol safe - see the kernel file).
+It offers the four conjugate ops the Column/Row parallel linears need with sequence parallelism:
+
+    all_gather_gemm(x_local, W)              Y  = AG(X) W^T           (column fwd, row dgrad with trans_b=False)
+    gemm_reduce_scatter(A, W)                Z  = RS(A W^T)           (row fwd, column dgrad with trans_b=False)
+    all_gather_wgrad(dY, x_local, W)         dW += dY^T AG(X)         (column wgrad; gather fused into the K loop)
+    all_gather(x_local)                      AG(X)                    (comm CTAs only)
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import ops
+from . import state as ps
+
+_HS_OFF = 0
+_CNT_OFF = 4096
+_CNT_BYTES = 4096            # per parity: up to 1024 row-blocks of 128 rows
+_DATA_OFF = _CNT_OFF + 2 * _CNT_BYTES
+
+
+def _align(n: int, a: int = 4096) -> int:
+    return (n + a - 1) // a * a
+
+
+class FusedTP:
+    def __init__(self, group, max_shard_bytes: int, max_stage_bytes: int, num_comm_ctas: int = 0):
+        assert torch.cuda.is_available() and dist.is_initialized()
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.tp = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        assert 2 <= self.tp <= 8, "fused TP kernels support 2..8 ranks per group"
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_comm_ctas = int(num_comm_ctas or os.environ.get("NXDT_AG_COMM_CTAS", 0)) or (8 if self.tp >= 4 else 4)
+        self.max_shard_bytes = _align(max_shard_bytes)
+        self.max_stage_bytes = _align(max_stage_bytes)
+        self.x_off = [_DATA_OFF, _DATA_OFF + self.max_shard_bytes]
+        self.stage_off = [_DATA_OFF + 2 * self.max_shard_bytes, _DATA_OFF + 2 * self.max_shard_bytes + self.max_stage_bytes]
+        total = self.stage_off[1] + self.max_stage_bytes
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
+        self.base_ptrs: List[int] = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(self.base_ptrs) == self.tp
+        self.flags = torch.zeros(4096, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _next_epoch(self) -> Tuple[int, int]:
+        self.epoch += 1
+        return self.epoch, self.epoch & 1
+
+    def _hs(self) -> Tuple[int, List[int]]:
+        return self.base_ptrs[self.rank] + _HS_OFF, [p + _HS_OFF for p in self.base_ptrs]
+
+    def _stage_shard(self, x2d: torch.Tensor, parity: int) -> List[int]:
+        nbytes = x2d.numel() * x2d.element_size()
+        if nbytes > self.max_shard_bytes:
+            raise ValueError(f"shard of {nbytes} bytes exceeds the fused-TP workspace ({self.max_shard_bytes}); "
+                             "raise max_shard_bytes")
+        dst = self.buf[self.x_off[parity]: self.x_off[parity] + nbytes].view(torch.bfloat16).view(x2d.shape)
+        dst.copy_(x2d)
+        return [p + self.x_off[parity] for p in self.base_ptrs]
+
+    def supports(self, rows_local: int, *dims: int) -> bool:
+        return rows_local % 128 == 0 and all(d % 8 == 0 for d in dims)
+
+    # ---- ops ---------------------------------------------------------------------------------------
+    def all_gather_gemm(self, x2d: torch.Tensor, w: torch.Tensor, trans_b: bool = True, return_gathered: bool = False):
+        """``AG_rows(x2d) @ (w.T if trans_b else w)``; x2d [m, K] bf16 local shard."""
+        m, K = x2d.shape
+        N = w.shape[0] if trans_b else w.shape[1]
+        epoch, par = self._next_epoch()
+        peer_x = self._stage_shard(x2d.contiguous(), par)
+        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        out = torch.empty(m * self.tp, N, dtype=x2d.dtype, device=x2d.device)
+        hs_local, hs_peer = self._hs()
+        ops._count()
+        ops.C().ag_gemm(xg, w, out, out, peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank, self.tp,
+                        0, trans_b, False, self.num_comm_ctas)
+        return (out, xg) if return_gathered else out
+
+    def all_gather_wgrad(self, dy2d: torch.Tensor, x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
+        """``out (+)= dy2d^T @ AG_rows(x2d)``; dy2d [M_total, N'], x2d [m, K'] local shard, out [N', K']."""
+        m, K = x2d.shape
+        epoch, par = self._next_epoch()
+        peer_x = self._stage_shard(x2d.contiguous(), par)
+        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        hs_local, hs_peer = self._hs()
+        ops._count()
+        ops.C().ag_gemm(xg, xg, out, dy2d.contiguous(), peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank,
+                        self.tp, 1, True, accumulate, self.num_comm_ctas)
+        return out
+
+    def all_gather(self, x2d: torch.Tensor) -> torch.Tensor:
+        m, K = x2d.shape
+        epoch, par = self._next_epoch()
+        peer_x = self._stage_shard(x2d.contiguous(), par)
+        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        hs_local, hs_peer = self._hs()
+        ops._count()
+        ops.C().ag_only(xg, peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank, self.tp, self.num_comm_ctas * 2)
+        return xg
+
+    def gemm_reduce_scatter(self, a2d: torch.Tensor, w: torch.Tensor, trans_b: bool = True) -> torch.Tensor:
+        """``RS_rows(a2d @ (w.T if trans_b else w))``; a2d [M_total, K_local]."""
+        M, K = a2d.shape
+        N = w.shape[0] if trans_b else w.shape[1]
+        rows = M // self.tp
+        need = self.tp * rows * N * 2
+        if need > self.max_stage_bytes:
+            raise ValueError(f"reduce-scatter staging of {need} bytes exceeds the workspace ({self.max_stage_bytes})")
+        epoch, par = self._next_epoch()
+        stage = [p + self.stage_off[par] for p in self.base_ptrs]
+        cnt = [p + _CNT_OFF + par * _CNT_BYTES for p in self.base_ptrs]
+        out = torch.empty(rows, N, dtype=a2d.dtype, device=a2d.device)
+        hs_local, hs_peer = self._hs()
+        ops._count()
+        ops.C().gemm_rs(a2d.contiguous(), w, out, stage, cnt, hs_local, hs_peer, epoch, self.rank, self.tp, trans_b)
+        return out
+
+
+class _FusedLayerAdapter:
+    """What ``parallel.layers`` sees: falls back to ``None`` semantics per call when shapes are unsupported."""
+
+    def __init__(self, ftp: FusedTP):
+        self.ftp = ftp
+
+    def ok(self, rows_local: int, *dims: int) -> bool:
+        return self.ftp.supports(rows_local, *dims)
+
+    def all_gather_gemm(self, x2d, w, trans_b=True, return_gathered=False):
+        return self.ftp.all_gather_gemm(x2d, w, trans_b, return_gathered)
+
+    def gemm_reduce_scatter(self, a2d, w, trans_b=True):
+        return self.ftp.gemm_reduce_scatter(a2d, w, trans_b)
+
+    def all_gather(self, x2d):
+        return self.ftp.all_gather(x2d)
+
+    def all_gather_wgrad(self, dy2d, x2d, out, accumulate):
+        return self.ftp.all_gather_wgrad(dy2d, x2d, out, accumulate)
+
+
+_FTP_CACHE = {}
+
+
+def get_fused_tp(group=None, max_shard_bytes: int = 64 << 20, max_stage_bytes: int = 256 << 20) -> FusedTP:
+    group = group if group is not None else ps.get_tensor_model_parallel_group()
+    key = id(group)
+    if key not in _FTP_CACHE:
+        _FTP_CACHE[key] = FusedTP(group, max_shard_bytes, max_stage_bytes)
+    return _FTP_CACHE[key]
+
+
+def enable_fused_tp(model: nn.Module, seq_len: Optional[int] = None, micro_batch: int = 1) -> int:
+    """Attach the fused kernels to every sequence-parallel Column/Row/GQA linear of ``model``.
+    Returns the number of layers switched."""
+    from .layers import ColumnParallelLinear, RowParallelLinear, GQAQKVColumnParallelLinear
+    if not torch.cuda.is_available() or ops.C() is None or not hasattr(ops.C(), "ag_gemm"):
+        raise RuntimeError("fused TP kernels need the sm_100a extension")
+    tp = ps.get_tensor_model_parallel_size()
+    if tp < 2:
+        return 0
+    mods = [m for m in model.modules() if isinstance(m, (ColumnParallelLinear, RowParallelLinear, GQAQKVColumnParallelLinear))
+            and getattr(m, "sequence_parallel_enabled", False)]
+    if not mods:
+        return 0
+    # size the workspace from the largest linear: shard = tokens_local x max(in features), staging = tp x
+    # tokens_local x max(out features of a reduce-scatter)
+    tokens_total = (seq_len or 8192) * micro_batch
+    tokens_local = tokens_total // tp
+    max_in = 0
+    max_rs_out = 0
+    for m in mods:
+        if isinstance(m, RowParallelLinear):
+            max_in = max(max_in, m.output_size)          # backward gathers dZ [tokens_local, out]
+            max_rs_out = max(max_rs_out, m.output_size)  # forward reduce-scatters [tokens, out]
+        else:
+            max_in = max(max_in, m.input_size)
+            max_rs_out = max(max_rs_out, m.input_size)   # dgrad reduce-scatters [tokens, in]
+    ftp = get_fused_tp(mods[0].group, max_shard_bytes=tokens_local * max_in * 2,
+                       max_stage_bytes=tokens_total * max_rs_out * 2)
+    adapter = _FusedLayerAdapter(ftp)
+    for m in mods:
+        m.fused = adapter
+    return len(mods)

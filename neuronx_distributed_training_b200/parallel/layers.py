@@ -111,6 +111,17 @@ def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, weight: torch.Tensor) -> Optio
     return ops.gemm_wgrad(dy2d, x2d).to(weight.dtype)
 
 
+def _wgrad_fused_gather(fused, dy2d: torch.Tensor, x_local2d: torch.Tensor, weight: torch.Tensor):
+    """dW = dY^T @ AG(X) with the all-gather of X fused into the GEMM's K loop."""
+    main_grad = getattr(weight, "main_grad", None)
+    if main_grad is not None:
+        fused.all_gather_wgrad(dy2d, x_local2d, main_grad, True)
+        weight.grad_added_to_main_grad = True
+        return None
+    out = torch.empty(weight.shape, dtype=weight.dtype, device=weight.device)
+    return fused.all_gather_wgrad(dy2d, x_local2d, out, False)
+
+
 class _ColumnParallelLinearFn(torch.autograd.Function):
     """Y = AG_seq(X) @ W^T (+b).  Backward: dX = RS_seq(dY @ W) (or all-reduce without SP),
     dW = AG_seq(X)^T dY."""
@@ -122,14 +133,15 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         ctx.x_shape = x.shape
         tp = ps.group_size(group)
         x2d = x.reshape(-1, x.shape[-1])
+        use_fused = fused is not None and sequence_parallel and tp > 1 and x2d.dtype == torch.bfloat16 and \
+            fused.ok(x2d.shape[0], x2d.shape[1], weight.shape[0])
+        ctx.use_fused = use_fused
         if sequence_parallel and tp > 1:
-            if fused is not None:
+            if use_fused:
                 y2d = fused.all_gather_gemm(x2d, weight)
-                total_rows = x2d.shape[0] * tp
             else:
                 total_x = mp.all_gather_dim0(x2d, group)
                 y2d = ops.gemm_nt(total_x, weight)
-                total_rows = total_x.shape[0]
                 del total_x
             out_shape = (x.shape[0] * tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
         else:
@@ -150,9 +162,10 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         need_dw = ctx.needs_input_grad[1]
         handle = None
         total_x = x2d
+        fused_wgrad = ctx.use_fused and need_dw
         if ctx.sp and tp > 1 and need_dw:
-            if ctx.fused is not None:
-                total_x = ctx.fused.all_gather(x2d)
+            if fused_wgrad:
+                pass   # the gather is fused into the K loop of the wgrad GEMM below
             else:
                 # re-gather X asynchronously; it is only needed for wgrad, after dgrad
                 total_x = torch.empty((x2d.shape[0] * tp, x2d.shape[1]), dtype=x2d.dtype, device=x2d.device)
@@ -161,7 +174,7 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         rs_handle = None
         if need_dx:
             if ctx.sp and tp > 1:
-                if ctx.fused is not None:
+                if ctx.use_fused:
                     dx = ctx.fused.gemm_reduce_scatter(dy2d, weight, trans_b=False)
                 else:
                     dx_total = ops.gemm_nn(dy2d, weight)
@@ -176,7 +189,10 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         if need_dw:
             if handle is not None:
                 handle.wait()
-            dw = _wgrad(dy2d, total_x, weight)
+            if fused_wgrad:
+                dw = _wgrad_fused_gather(ctx.fused, dy2d, x2d, weight)
+            else:
+                dw = _wgrad(dy2d, total_x, weight)
         db = dy2d.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         if rs_handle is not None:
             rs_handle.wait()
@@ -195,8 +211,11 @@ class _RowParallelLinearFn(torch.autograd.Function):
         ctx.x_shape = x.shape
         tp = ps.group_size(group)
         x2d = x.reshape(-1, x.shape[-1])
+        use_fused = fused is not None and sequence_parallel and tp > 1 and x2d.dtype == torch.bfloat16 and \
+            fused.ok(x2d.shape[0] // tp, x2d.shape[1], weight.shape[0]) and x2d.shape[0] % tp == 0
+        ctx.use_fused = use_fused
         if tp > 1 and sequence_parallel:
-            if fused is not None:
+            if use_fused:
                 y2d = fused.gemm_reduce_scatter(x2d, weight, trans_b=True)
             else:
                 y2d = mp.reduce_scatter_dim0(ops.gemm_nt(x2d, weight), group, reduce_dtype)
@@ -217,7 +236,7 @@ class _RowParallelLinearFn(torch.autograd.Function):
         x2d = x.reshape(-1, x.shape[-1])
         dx = dw = None
         if ctx.sp and tp > 1:
-            if ctx.fused is not None:
+            if ctx.use_fused:
                 # one fused kernel gathers dZ and multiplies; the gathered dZ is kept for wgrad
                 dx, dy_total = ctx.fused.all_gather_gemm(dy2d, weight, trans_b=False, return_gathered=True)
             else:
