@@ -137,6 +137,7 @@ def initialize_parallel_model(module, provider: Callable[..., nn.Module], transf
             last = pp_rank == pp - 1 and c == vpp - 1
             chunks.append(provider(device=dev, layer_range=(lo, hi), with_embedding=first, with_head=last))
     for ch in chunks:
+        ch.pipeline_num_microbatches = module.num_microbatches
         if lora_config is not None:
             from ..models.lora import inject_lora
             inject_lora(ch, lora_config)
