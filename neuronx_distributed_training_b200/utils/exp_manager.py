@@ -160,7 +160,7 @@ class TimingCallback:
 
 
 # ---- resume --------------------------------------------------------------------------------------------
-_CKPT_RE = re.compile(r"consumed_samples=([0-9.]+)")
+_CKPT_RE = re.compile(r"consumed_samples=([0-9]+(?:\.[0-9]+)?)")
 _STEP_RE = re.compile(r"step=([0-9]+)")
 
 
