@@ -226,6 +226,7 @@ class BaseModelModule:
                 m["gradient_norm"] = float(self.optimizer.grad_norm)
         if self.log_parameter_norm:
             m["parameter_norm"] = float(self.parameter_norm())
+        m.update(self._logged)
         m["throughput"] = self.throughput.get_throughput()
         m["throughput_peak"] = self.throughput.throughput_peak
         return m
@@ -238,15 +239,33 @@ class BaseModelModule:
         pass
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
+        a = self.cfg.get("model_alignment_strategy", None)
+        peft = a.get("peft", None) if a is not None else None
+        if peft is not None:
+            from ..models import lora
+            if bool(peft.get("merge_lora", False)):
+                return {k: v for c in self.model.chunks for k, v in lora.merged_state_dict(c).items()}
+            if not bool(peft.get("save_lora_base", False)):
+                return {k: v for c in self.model.chunks for k, v in lora.lora_state_dict(c).items()}
         return self.model.state_dict()
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
         """Non-strict load that ignores rotary ``inv_freq`` buffers but raises on any other missing key
         unless PEFT is active (reference nlp_overrides.py:1157-1200)."""
-        res = self.model.load_state_dict(sd, strict=False)
-        missing = [k for k in res.missing_keys if not k.endswith("rotary_emb.inv_freq")]
         peft = self.cfg.get("model_alignment_strategy", None) is not None and \
             self.cfg.model_alignment_strategy.get("peft", None) is not None
+        if peft:
+            # checkpoints of the base model use the un-wrapped names: route them to ``<module>.base_layer.*``
+            own = self.model.state_dict()
+            remapped = dict(sd)
+            for k in own:
+                if ".base_layer." in k:
+                    plain = k.replace(".base_layer.", ".")
+                    if plain in sd and k not in sd:
+                        remapped[k] = remapped.pop(plain)
+            sd = remapped
+        res = self.model.load_state_dict(sd, strict=False)
+        missing = [k for k in res.missing_keys if not k.endswith("rotary_emb.inv_freq")]
         if missing and not peft:
             raise RuntimeError(f"missing keys when loading checkpoint: {missing[:8]}{' ...' if len(missing) > 8 else ''}")
         return res
