@@ -20,6 +20,7 @@
 
 #include "gemm_sm100.cuh"
 #include "tma_utils.h"
+#include <set>
 
 namespace gemm100 {
 Params make_params(int M, int N, int K);
@@ -32,7 +33,7 @@ namespace fused {
 
 using namespace gemm100;
 constexpr int MAX_TP = 8;
-constexpr int RING_SLOTS = 6;
+constexpr int RING_SLOTS = 7;
 constexpr int PIECE_BYTES = 32 * 1024;
 
 struct CommArgs {
@@ -49,7 +50,9 @@ struct AgGate {
   const uint32_t* flags;
   uint32_t epoch;
   int mode;   // 0: gathered operand indexed by m-block, 1: by k-block (wgrad)
+  int local_lo, local_hi;   // row-blocks of my own shard: already in place, never waited on
   __device__ __forceinline__ void wait_flag(int blk) const {
+    if (blk >= local_lo && blk < local_hi) return;
     while (ld_acquire_gpu(flags + blk) != epoch) __nanosleep(64);
     fence_proxy_async_all();   // generic-proxy acquire -> subsequent async-proxy (TMA) reads
   }
@@ -60,7 +63,8 @@ struct AgGate {
     if (mode == 1) wait_flag(kb >> 1);   // BLOCK_K = 64 rows, flags are per 128 rows
   }
   __device__ __forceinline__ void before_first_store() const {}
-  __device__ __forceinline__ __nv_bfloat16* peer_row_ptr(int, int) const { return nullptr; }
+  __device__ __forceinline__ const CUtensorMap* out_map(int) const { return nullptr; }
+  __device__ __forceinline__ int out_row(int m_blk) const { return m_blk * BLOCK_M; }
   __device__ __forceinline__ void tile_done(int) const {}
 };
 
@@ -86,6 +90,7 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
     int blk = idx + a.rank * blocks_per_rank;
     if (blk >= total_blocks) blk -= total_blocks;
     const int src_rank = blk / blocks_per_rank;
+    if (src_rank == a.rank) continue;     // my own shard was placed into xg by the host-side copy
     if (!((waited_rank_mask >> src_rank) & 1)) {
       // the peer's shard for this epoch is in place (and it is done with the previous use of my buffers)
       while (ld_acquire_sys(a.hs_local + src_rank) < a.epoch) __nanosleep(100);
@@ -131,7 +136,8 @@ ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     comm_cta(comm, smem_raw);
     return;
   }
-  AgGate gate{comm.flags, comm.epoch, mode};
+  const int bpr = comm.rows_per_rank / 128;
+  AgGate gate{comm.flags, comm.epoch, mode, comm.rank * bpr, (comm.rank + 1) * bpr};
   gemm_body<A_MN, B_MN, OUT, AgGate>(&tma_a, &tma_b, &tma_c, p, smem_raw, gate, (int)blockIdx.x - comm.num_comm_ctas,
                                      (int)gridDim.x - comm.num_comm_ctas);
 }
@@ -155,8 +161,13 @@ struct RsArgs {
   int rank, tp, rows_per_rank, N, num_n_blocks;
 };
 
+struct RsMaps {
+  CUtensorMap m[MAX_TP];   // one store map per destination rank: its staging buffer [tp * rows_per_rank, N]
+};
+
 struct RsGate {
   RsArgs a;
+  const CUtensorMap* maps;
   __device__ __forceinline__ void wait_m(int) const {}
   __device__ __forceinline__ void wait_k(int) const {}
   __device__ __forceinline__ void before_first_store() const {
@@ -166,10 +177,13 @@ struct RsGate {
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
-  __device__ __forceinline__ __nv_bfloat16* peer_row_ptr(int grow, int gcol) const {
-    const int d = grow / a.rows_per_rank;
-    const int l = grow - d * a.rows_per_rank;
-    return a.stage_peer[d] + ((size_t)a.rank * a.rows_per_rank + l) * a.N + gcol;
+  __device__ __forceinline__ const CUtensorMap* out_map(int m_blk) const {
+    return maps + m_blk / (a.rows_per_rank / 128);
+  }
+  __device__ __forceinline__ int out_row(int m_blk) const {
+    const int bpr = a.rows_per_rank / 128;
+    const int d = m_blk / bpr;
+    return a.rank * a.rows_per_rank + (m_blk - d * bpr) * 128;
   }
   __device__ __forceinline__ void tile_done(int m_blk) const {
     const int bpr = a.rows_per_rank / 128;
@@ -181,10 +195,11 @@ struct RsGate {
 template <bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const Params p, const RsArgs rs) {
+               const __grid_constant__ RsMaps maps, const Params p, const RsArgs rs) {
   extern __shared__ uint8_t smem_raw[];
   if (blockIdx.x == 0 && threadIdx.x == 0) send_handshake(rs.hs_peer, rs.rank, rs.tp, rs.epoch);
-  RsGate gate{rs};
+  RsGate gate{rs, maps.m};
+  const CUtensorMap& tma_c = maps.m[0];
   gemm_body<false, B_MN, OUT_BF16_PEER, RsGate>(&tma_a, &tma_b, &tma_c, p, smem_raw, gate, blockIdx.x, gridDim.x);
   // ---------------- reduce phase: sum the TP partial slabs of my rows ----------------
   const int bpr = rs.rows_per_rank / 128;
@@ -225,7 +240,11 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
 template <class K>
 static void set_smem(K kern) {
-  C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  // keyed by the function address: kernels of different template arguments share one signature type
+  static std::set<const void*> done;
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (done.insert(key).second)
+    C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
 }
 
 static void fill_ptrs(const std::vector<int64_t>& v, int tp, void** dst) {
@@ -272,8 +291,7 @@ void ag_gemm(at::Tensor xg, const at::Tensor& b, at::Tensor out, const at::Tenso
     p.group_m = 1;                                         // all n-tiles of one row-block before the next
     p.m_first = rank * (rows_per_rank / 128);
     auto run = [&](auto kern) {
-      static bool once = false;
-      if (!once) { set_smem(kern); once = true; }
+      set_smem(kern);
       kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p, comm, 0);
     };
     if (b_kmajor) run(ag_gemm_kernel<false, false, OUT_BF16_STORE>);
@@ -289,8 +307,7 @@ void ag_gemm(at::Tensor xg, const at::Tensor& b, at::Tensor out, const at::Tenso
     p = make_params(Np, Kx, M_total);
     p.k_first = rank * (rows_per_rank / 64);
     auto run = [&](auto kern) {
-      static bool once = false;
-      if (!once) { set_smem(kern); once = true; }
+      set_smem(kern);
       kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p, comm, 1);
     };
     if (f32) { if (accumulate) run(ag_gemm_kernel<true, true, OUT_F32_ADD>); else run(ag_gemm_kernel<true, true, OUT_F32_STORE>); }
@@ -315,8 +332,7 @@ void ag_only(at::Tensor xg, std::vector<int64_t> peer_x, int64_t flags_ptr, int6
   comm.epoch = (uint32_t)epoch;
   comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
   comm.num_comm_ctas = num_comm_ctas;
-  static bool once = false;
-  if (!once) { set_smem(ag_only_kernel); once = true; }
+  set_smem(ag_only_kernel);
   ag_only_kernel<<<num_comm_ctas, NUM_THREADS, SMEM_BYTES, at::cuda::getCurrentCUDAStream()>>>(comm);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
@@ -346,9 +362,11 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   rs.out = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
   rs.epoch = (uint32_t)epoch;
   rs.rank = rank; rs.tp = tp; rs.rows_per_rank = rows_per_rank; rs.N = N;
-  CUtensorMap ta, tb, tc;
+  CUtensorMap ta, tb;
   make_operand_maps(a.data_ptr(), b.data_ptr(), M_total, N, K, true, b_kmajor, ta, tb);
-  tc = ta;   // unused by the peer epilogue
+  RsMaps maps;
+  for (int d = 0; d < MAX_TP; ++d)
+    maps.m[d] = make_out_map(rs.stage_peer[d < tp ? d : 0], M_total, N, false);
   Params p = make_params(M_total, N, K);
   rs.num_n_blocks = p.num_n_blocks;
   p.group_m = 1;
@@ -358,9 +376,8 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   C10_CUDA_CHECK(cudaMemsetAsync(rs.counter_local, 0, sizeof(uint32_t) * (rows_per_rank / 128), stream));
   auto run = [&](auto kern) {
-    static bool once = false;
-    if (!once) { set_smem(kern); once = true; }
-    kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p, rs);
+    set_smem(kern);
+    kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, maps, p, rs);
   };
   if (b_kmajor) run(gemm_rs_kernel<false>); else run(gemm_rs_kernel<true>);
   C10_CUDA_KERNEL_LAUNCH_CHECK();

@@ -48,13 +48,14 @@ struct Params {
 
 // Hook object threaded through the kernel.  The plain GEMM uses NoGate; the fused collectives provide
 //   wait_m / wait_k : block the TMA producer until the rows of the gathered operand have arrived
-//   peer_row_ptr    : destination of an output row in a peer GPU's staging buffer (GEMM -> reduce-scatter)
+//   out_map/out_row : tensor map + row of a tile in the owner rank's staging buffer (GEMM -> reduce-scatter)
 //   tile_done       : publish a finished tile to its owner rank
 struct NoGate {
   __device__ __forceinline__ void wait_m(int /*m_blk*/) const {}
   __device__ __forceinline__ void wait_k(int /*k_blk*/) const {}
   __device__ __forceinline__ void before_first_store() const {}
-  __device__ __forceinline__ __nv_bfloat16* peer_row_ptr(int /*grow*/, int /*gcol*/) const { return nullptr; }
+  __device__ __forceinline__ const CUtensorMap* out_map(int /*m_blk*/) const { return nullptr; }
+  __device__ __forceinline__ int out_row(int m_blk) const { return m_blk * BLOCK_M; }
   __device__ __forceinline__ void tile_done(int /*m_blk*/) const {}
 };
 
@@ -195,48 +196,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BLOCK_N;
+      const CUtensorMap* cmap = tma_c;
+      int cm = m_blk * BLOCK_M;
       if constexpr (OUT == OUT_BF16_PEER) {
-        // GEMM -> reduce-scatter: every thread owns one output row and writes it straight into the staging
-        // buffer of the rank that owns that row (peer memory over NVLink), 128 B at a time.
+        // GEMM -> reduce-scatter: the tile is TMA-stored into the staging buffer of the rank that owns these rows
+        // (a tensor map over peer-mapped memory), full 128 B lines over NVLink.
         if (first_store) { gate.before_first_store(); first_store = false; }
-        const int grow = m_blk * BLOCK_M + (int)row;
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 64; ++c) {
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32b_x32(taddr + c * 64, v0);
-          tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
-          tmem_ld_wait();
-          const int gcol = n_blk * BLOCK_N + c * 64;
-          if (grow < p.M && gcol < p.N) {
-            uint4* dst = reinterpret_cast<uint4*>(gate.peer_row_ptr(grow, gcol));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
-              o.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
-              o.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
-              o.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
-              dst[j] = o;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
-              o.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
-              o.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
-              o.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
-              dst[4 + j] = o;
-            }
-          }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        __threadfence_system();                          // this thread's peer stores are visible system-wide
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (issuer) gate.tile_done(m_blk);
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-        continue;
+        cmap = gate.out_map(m_blk);
+        cm = gate.out_row(m_blk);
       }
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
@@ -286,22 +253,27 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (issuer) {
           const int cn = n_blk * BLOCK_N + c * COLS_PER_CHUNK;
-          const int cm = m_blk * BLOCK_M;
           if (cn < p.N) {
             if constexpr (OUT == OUT_F32_ADD || OUT == OUT_BF16_ADD)
-              tma_reduce_add_2d(tma_c, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
+              tma_reduce_add_2d(cmap, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
             else
-              tma_store_2d(tma_c, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
+              tma_store_2d(cmap, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
           }
           tma_store_commit();
         }
         cbuf ^= 1;
       }
+      if constexpr (OUT == OUT_BF16_PEER) {
+        if (issuer) {
+          tma_store_wait<0>();          // every byte of this tile has been written to the owner's staging buffer
+          fence_proxy_async_all();
+          __threadfence_system();
+          gate.tile_done(m_blk);        // red.release.sys on the owner's arrival counter
+        }
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-    if constexpr (OUT != OUT_BF16_PEER) {
-      if (issuer) tma_store_wait<0>();
-    }
+    if (issuer) tma_store_wait<0>();
   }
 
   tcgen05_fence_before();

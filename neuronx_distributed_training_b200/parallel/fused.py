@@ -45,7 +45,7 @@ class FusedTP:
         self.rank = dist.get_rank(self.group)
         assert 2 <= self.tp <= 8, "fused TP kernels support 2..8 ranks per group"
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.num_comm_ctas = int(num_comm_ctas or os.environ.get("NXDT_AG_COMM_CTAS", 0)) or (8 if self.tp >= 4 else 4)
+        self.num_comm_ctas = int(num_comm_ctas or os.environ.get("NXDT_AG_COMM_CTAS", 0)) or (12 if self.tp >= 4 else 8)
         self.max_shard_bytes = _align(max_shard_bytes)
         self.max_stage_bytes = _align(max_stage_bytes)
         self.x_off = [_DATA_OFF, _DATA_OFF + self.max_shard_bytes]
@@ -82,6 +82,13 @@ class FusedTP:
         dst.copy_(x2d)
         return [p + self.x_off[parity] for p in self.base_ptrs]
 
+    def _new_gather_buffer(self, x2d: torch.Tensor) -> torch.Tensor:
+        """gathered buffer with my own shard already in place (the kernel only pulls the peers' shards)"""
+        m, K = x2d.shape
+        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        xg[self.rank * m:(self.rank + 1) * m].copy_(x2d)
+        return xg
+
     def supports(self, rows_local: int, *dims: int) -> bool:
         return rows_local % 128 == 0 and all(d % 8 == 0 for d in dims)
 
@@ -92,7 +99,7 @@ class FusedTP:
         N = w.shape[0] if trans_b else w.shape[1]
         epoch, par = self._next_epoch()
         peer_x = self._stage_shard(x2d.contiguous(), par)
-        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        xg = self._new_gather_buffer(x2d)
         out = torch.empty(m * self.tp, N, dtype=x2d.dtype, device=x2d.device)
         hs_local, hs_peer = self._hs()
         ops._count()
@@ -105,7 +112,7 @@ class FusedTP:
         m, K = x2d.shape
         epoch, par = self._next_epoch()
         peer_x = self._stage_shard(x2d.contiguous(), par)
-        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        xg = self._new_gather_buffer(x2d)
         hs_local, hs_peer = self._hs()
         ops._count()
         ops.C().ag_gemm(xg, xg, out, dy2d.contiguous(), peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank,
@@ -116,7 +123,7 @@ class FusedTP:
         m, K = x2d.shape
         epoch, par = self._next_epoch()
         peer_x = self._stage_shard(x2d.contiguous(), par)
-        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        xg = self._new_gather_buffer(x2d)
         hs_local, hs_peer = self._hs()
         ops._count()
         ops.C().ag_only(xg, peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank, self.tp, self.num_comm_ctas * 2)
