@@ -35,3 +35,8 @@ def test_zero1_matches_adamw():
 @pytest.mark.parametrize("pp,vpp,tp,nmb", [(2, 1, 1, 4), (4, 1, 1, 6), (2, 2, 1, 4), (2, 1, 2, 3), (4, 2, 1, 8)])
 def test_pipeline_matches_unpipelined(pp, vpp, tp, nmb):
     run_dist("pipeline.py", pp * tp, {"PP": str(pp), "VPP": str(vpp), "TP": str(tp), "NMB": str(nmb)})
+
+
+@pytest.mark.parametrize("tp,pp,nproc,async_", [(1, 1, 2, "0"), (2, 1, 2, "0"), (1, 2, 2, "0"), (1, 1, 2, "1")])
+def test_checkpoint_resume_bit_exact(tmp_path, tp, pp, nproc, async_):
+    run_dist("ckpt_resume.py", nproc, {"TP": str(tp), "PP": str(pp), "WORKDIR": str(tmp_path), "ASYNC": async_})
