@@ -45,7 +45,8 @@ class FusedTP:
         self.rank = dist.get_rank(self.group)
         assert 2 <= self.tp <= 8, "fused TP kernels support 2..8 ranks per group"
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.num_comm_ctas = int(num_comm_ctas or os.environ.get("NXDT_AG_COMM_CTAS", 0)) or (12 if self.tp >= 4 else 8)
+        self.num_comm_ctas_fixed = int(num_comm_ctas or os.environ.get("NXDT_AG_COMM_CTAS", 0))
+        self.num_comm_ctas = self.num_comm_ctas_fixed or (12 if self.tp >= 4 else 8)
         self.max_shard_bytes = _align(max_shard_bytes)
         self.max_stage_bytes = _align(max_stage_bytes)
         self.x_off = [_DATA_OFF, _DATA_OFF + self.max_shard_bytes]
@@ -92,6 +93,36 @@ class FusedTP:
     def supports(self, rows_local: int, *dims: int) -> bool:
         return rows_local % 128 == 0 and all(d % 8 == 0 for d in dims)
 
+    # ---- when does fusing pay?  (measured on B200: the fused kernels give up a few SMs to the transfer and run a
+    # peer handshake, so they win when the NVLink time is a sizeable fraction of the GEMM time) -----------------
+    GEMM_FLOPS = 1.35e15          # sustained tcgen05 bf16 rate of gemm_sm100 on Llama shapes
+    LINK_BPS = 6.0e11             # ~600 GB/s effective inbound/outbound per GPU
+    PER_CTA_BPS = 7.5e10          # one comm CTA keeps 7 x 32 KB in flight over a ~2.5 us NVLink round trip
+
+    def _ratio(self, m_total: int, n: int, k: int, bytes_moved: float) -> float:
+        return (bytes_moved / self.LINK_BPS) / max(2.0 * m_total * n * k / self.GEMM_FLOPS, 1e-9)
+
+    def prefer_ag_gemm(self, rows_local: int, k: int, n: int) -> bool:
+        thr = float(os.environ.get("NXDT_FUSE_THRESHOLD", "0.30"))
+        return self._ratio(rows_local * self.tp, n, k, rows_local * (self.tp - 1) * k * 2) >= thr
+
+    def prefer_ag_wgrad(self, rows_local: int, k: int, n: int) -> bool:
+        thr = float(os.environ.get("NXDT_FUSE_THRESHOLD", "0.30"))
+        return self._ratio(rows_local * self.tp, n, k, rows_local * (self.tp - 1) * k * 2) >= thr
+
+    def prefer_gemm_rs(self, rows_total: int, k: int, n: int) -> bool:
+        thr = float(os.environ.get("NXDT_FUSE_THRESHOLD", "0.30"))
+        return self._ratio(rows_total, n, k, rows_total * n * 2 * (self.tp - 1) / self.tp) >= thr
+
+    def _comm_ctas(self, m_total: int, n: int, k: int, bytes_in: float) -> int:
+        """enough comm CTAs to finish the gather in ~half the GEMM time, bounded by what the link can take"""
+        if self.num_comm_ctas_fixed:
+            return self.num_comm_ctas_fixed
+        t_gemm = 2.0 * m_total * n * k / self.GEMM_FLOPS
+        need = bytes_in / self.PER_CTA_BPS / max(0.5 * t_gemm, 1e-9)
+        cap = int(self.LINK_BPS * 1.5 / self.PER_CTA_BPS)
+        return int(max(2, min(cap, round(need + 0.5))))
+
     # ---- ops ---------------------------------------------------------------------------------------
     def all_gather_gemm(self, x2d: torch.Tensor, w: torch.Tensor, trans_b: bool = True, return_gathered: bool = False):
         """``AG_rows(x2d) @ (w.T if trans_b else w)``; x2d [m, K] bf16 local shard."""
@@ -103,8 +134,9 @@ class FusedTP:
         out = torch.empty(m * self.tp, N, dtype=x2d.dtype, device=x2d.device)
         hs_local, hs_peer = self._hs()
         ops._count()
+        nc = self._comm_ctas(m * self.tp, N, K, m * (self.tp - 1) * K * 2)
         ops.C().ag_gemm(xg, w, out, out, peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank, self.tp,
-                        0, trans_b, False, self.num_comm_ctas)
+                        0, trans_b, False, nc)
         return (out, xg) if return_gathered else out
 
     def all_gather_wgrad(self, dy2d: torch.Tensor, x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
@@ -115,8 +147,9 @@ class FusedTP:
         xg = self._new_gather_buffer(x2d)
         hs_local, hs_peer = self._hs()
         ops._count()
+        nc = self._comm_ctas(dy2d.shape[1], K, m * self.tp, m * (self.tp - 1) * K * 2)
         ops.C().ag_gemm(xg, xg, out, dy2d.contiguous(), peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank,
-                        self.tp, 1, True, accumulate, self.num_comm_ctas)
+                        self.tp, 1, True, accumulate, nc)
         return out
 
     def all_gather(self, x2d: torch.Tensor) -> torch.Tensor:
@@ -155,6 +188,15 @@ class _FusedLayerAdapter:
 
     def ok(self, rows_local: int, *dims: int) -> bool:
         return self.ftp.supports(rows_local, *dims)
+
+    def prefer_ag_gemm(self, rows_local, k, n):
+        return self.ftp.prefer_ag_gemm(rows_local, k, n)
+
+    def prefer_ag_wgrad(self, rows_local, k, n):
+        return self.ftp.prefer_ag_wgrad(rows_local, k, n)
+
+    def prefer_gemm_rs(self, rows_total, k, n):
+        return self.ftp.prefer_gemm_rs(rows_total, k, n)
 
     def all_gather_gemm(self, x2d, w, trans_b=True, return_gathered=False):
         return self.ftp.all_gather_gemm(x2d, w, trans_b, return_gathered)

@@ -133,9 +133,10 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         ctx.x_shape = x.shape
         tp = ps.group_size(group)
         x2d = x.reshape(-1, x.shape[-1])
-        use_fused = fused is not None and sequence_parallel and tp > 1 and x2d.dtype == torch.bfloat16 and \
+        can_fuse = fused is not None and sequence_parallel and tp > 1 and x2d.dtype == torch.bfloat16 and \
             fused.ok(x2d.shape[0], x2d.shape[1], weight.shape[0])
-        ctx.use_fused = use_fused
+        ctx.can_fuse = can_fuse
+        use_fused = can_fuse and fused.prefer_ag_gemm(x2d.shape[0], x2d.shape[1], weight.shape[0])
         if sequence_parallel and tp > 1:
             if use_fused:
                 y2d = fused.all_gather_gemm(x2d, weight)
@@ -162,7 +163,7 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         need_dw = ctx.needs_input_grad[1]
         handle = None
         total_x = x2d
-        fused_wgrad = ctx.use_fused and need_dw
+        fused_wgrad = ctx.can_fuse and need_dw and ctx.fused.prefer_ag_wgrad(x2d.shape[0], x2d.shape[1], dy2d.shape[1])
         if ctx.sp and tp > 1 and need_dw:
             if fused_wgrad:
                 pass   # the gather is fused into the K loop of the wgrad GEMM below
@@ -174,7 +175,7 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         rs_handle = None
         if need_dx:
             if ctx.sp and tp > 1:
-                if ctx.use_fused:
+                if ctx.can_fuse and ctx.fused.prefer_gemm_rs(dy2d.shape[0], dy2d.shape[1], weight.shape[1]):
                     dx = ctx.fused.gemm_reduce_scatter(dy2d, weight, trans_b=False)
                 else:
                     dx_total = ops.gemm_nn(dy2d, weight)
@@ -211,9 +212,10 @@ class _RowParallelLinearFn(torch.autograd.Function):
         ctx.x_shape = x.shape
         tp = ps.group_size(group)
         x2d = x.reshape(-1, x.shape[-1])
-        use_fused = fused is not None and sequence_parallel and tp > 1 and x2d.dtype == torch.bfloat16 and \
+        can_fuse = fused is not None and sequence_parallel and tp > 1 and x2d.dtype == torch.bfloat16 and \
             fused.ok(x2d.shape[0] // tp, x2d.shape[1], weight.shape[0]) and x2d.shape[0] % tp == 0
-        ctx.use_fused = use_fused
+        ctx.can_fuse = can_fuse
+        use_fused = can_fuse and fused.prefer_gemm_rs(x2d.shape[0], x2d.shape[1], weight.shape[0])
         if tp > 1 and sequence_parallel:
             if use_fused:
                 y2d = fused.gemm_reduce_scatter(x2d, weight, trans_b=True)
@@ -236,7 +238,7 @@ class _RowParallelLinearFn(torch.autograd.Function):
         x2d = x.reshape(-1, x.shape[-1])
         dx = dw = None
         if ctx.sp and tp > 1:
-            if ctx.use_fused:
+            if ctx.can_fuse and ctx.fused.prefer_ag_gemm(dy2d.shape[0], dy2d.shape[1], weight.shape[1]):
                 # one fused kernel gathers dZ and multiplies; the gathered dZ is kept for wgrad
                 dx, dy_total = ctx.fused.all_gather_gemm(dy2d, weight, trans_b=False, return_gathered=True)
             else:

@@ -1,0 +1,152 @@
+"""Context-parallel ring attention.
+
+Capability parity: ``nki_ring_attn_func(q, k, v, rank, src_tgt_pairs)`` as used by the reference for CP
+(reference modeling_llama.py:483-484): the sequence is split contiguously over the CP group,
+every rank keeps its queries and the K/V blocks travel around the ring (rank i -> i+1); each step is a blockwise
+attention whose result is merged with an online-softmax (log-sum-exp) accumulator.  Causality: a block coming from
+a lower rank is fully visible, the own block is causal, blocks from higher ranks are skipped.
+
+Backward walks the ring again: dK/dV accumulators travel together with their K/V block and arrive home after CP
+steps; dQ accumulates locally.  Block math uses the global LSE saved by the forward, so it is exact.
+NVSwitch note: bandwidth is uniform, so ring order is only a scheduling choice (a direct all-to-all fetch is
+equivalent); K/V transfers are issued before the block math so they overlap with it.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import state as ps
+
+_Q_CHUNK = 1024
+
+
+def _block_fwd(q, k, v, scale: float, causal: bool):
+    """q [B,Sq,H,D], k/v [B,Sk,Hk,D] -> out [B,Sq,H,D] fp32, lse [B,H,Sq] fp32."""
+    B, Sq, H, D = q.shape
+    Hk = k.shape[2]
+    rep = H // Hk
+    kf = k.float().permute(0, 2, 3, 1)                          # [B,Hk,D,Sk]
+    vf = v.float().permute(0, 2, 1, 3)                          # [B,Hk,Sk,D]
+    outs, lses = [], []
+    for s in range(0, Sq, _Q_CHUNK):
+        e = min(Sq, s + _Q_CHUNK)
+        qf = q[:, s:e].float().permute(0, 2, 1, 3).reshape(B, Hk, rep, e - s, D)
+        sc = torch.matmul(qf, kf.unsqueeze(2)) * scale          # [B,Hk,rep,sq,Sk]
+        if causal:
+            qi = torch.arange(s, e, device=q.device).view(-1, 1)
+            ki = torch.arange(k.shape[1], device=q.device).view(1, -1)
+            sc = sc.masked_fill(ki > qi, float("-inf"))
+        lse = torch.logsumexp(sc, dim=-1)                       # [B,Hk,rep,sq]
+        p = torch.exp(sc - lse.unsqueeze(-1))
+        o = torch.matmul(p, vf.unsqueeze(2))                    # [B,Hk,rep,sq,D]
+        outs.append(o.reshape(B, H, e - s, D).permute(0, 2, 1, 3))
+        lses.append(lse.reshape(B, H, e - s))
+    return torch.cat(outs, 1), torch.cat(lses, 2)
+
+
+def _block_bwd(do, q, k, v, lse, delta, scale: float, causal: bool):
+    """Gradients of one block given the GLOBAL lse [B,H,Sq] and delta = rowsum(dO*O) [B,H,Sq]."""
+    B, Sq, H, D = q.shape
+    Hk = k.shape[2]
+    rep = H // Hk
+    kf = k.float().permute(0, 2, 1, 3)                          # [B,Hk,Sk,D]
+    vf = v.float().permute(0, 2, 1, 3)
+    dq = torch.zeros(B, Sq, H, D, dtype=torch.float32, device=q.device)
+    dk = torch.zeros_like(kf)
+    dv = torch.zeros_like(vf)
+    for s in range(0, Sq, _Q_CHUNK):
+        e = min(Sq, s + _Q_CHUNK)
+        qf = q[:, s:e].float().permute(0, 2, 1, 3).reshape(B, Hk, rep, e - s, D)
+        dof = do[:, s:e].float().permute(0, 2, 1, 3).reshape(B, Hk, rep, e - s, D)
+        sc = torch.matmul(qf, kf.transpose(-1, -2).unsqueeze(2)) * scale
+        if causal:
+            qi = torch.arange(s, e, device=q.device).view(-1, 1)
+            ki = torch.arange(k.shape[1], device=q.device).view(1, -1)
+            sc = sc.masked_fill(ki > qi, float("-inf"))
+        p = torch.exp(sc - lse[:, :, s:e].reshape(B, Hk, rep, e - s, 1))
+        dv += torch.matmul(p.transpose(-1, -2), dof).sum(2)
+        dp = torch.matmul(dof, vf.transpose(-1, -2).unsqueeze(2))
+        ds = p * (dp - delta[:, :, s:e].reshape(B, Hk, rep, e - s, 1)) * scale
+        dq[:, s:e] = torch.matmul(ds, kf.unsqueeze(2)).reshape(B, H, e - s, D).permute(0, 2, 1, 3)
+        dk += torch.matmul(ds.transpose(-1, -2), qf).sum(2)
+    return dq, dk.permute(0, 2, 1, 3), dv.permute(0, 2, 1, 3)
+
+
+def _ring_exchange(tensors: List[torch.Tensor], group, send_to: int, recv_from: int) -> List[torch.Tensor]:
+    outs = [torch.empty(t.shape, dtype=t.dtype, device=t.device) for t in tensors]
+    ops = []
+    for t, o in zip(tensors, outs):
+        ops.append(dist.P2POp(dist.isend, t.contiguous(), send_to, group))
+        ops.append(dist.P2POp(dist.irecv, o, recv_from, group))
+    return outs, dist.batch_isend_irecv(ops)
+
+
+class _RingAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, scale, group, ranks, my_idx):
+        cp = len(ranks)
+        nxt, prv = ranks[(my_idx + 1) % cp], ranks[(my_idx - 1) % cp]
+        B, S, H, D = q.shape
+        out = torch.zeros(B, S, H, D, dtype=torch.float32, device=q.device)
+        lse = torch.full((B, H, S), float("-inf"), dtype=torch.float32, device=q.device)
+        kb, vb = k, v
+        for step in range(cp):
+            src = (my_idx - step) % cp
+            reqs = None
+            if step < cp - 1:
+                (kn, vn), reqs = _ring_exchange([kb, vb], group, nxt, prv)
+            if src <= my_idx:
+                o_s, lse_s = _block_fwd(q, kb, vb, scale, causal=(src == my_idx))
+                new = torch.logaddexp(lse, lse_s)
+                w_old = torch.exp(lse - new).permute(0, 2, 1).unsqueeze(-1)
+                w_new = torch.exp(lse_s - new).permute(0, 2, 1).unsqueeze(-1)
+                out = out * torch.nan_to_num(w_old) + o_s * w_new
+                lse = new
+            if reqs is not None:
+                for r in reqs:
+                    r.wait()
+                kb, vb = kn, vn
+        ctx.save_for_backward(q, k, v, out.to(q.dtype), lse)
+        ctx.scale, ctx.group, ctx.ranks, ctx.my_idx = scale, group, ranks, my_idx
+        return out.to(q.dtype)
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, out, lse = ctx.saved_tensors
+        scale, group, ranks, my_idx = ctx.scale, ctx.group, ctx.ranks, ctx.my_idx
+        cp = len(ranks)
+        nxt, prv = ranks[(my_idx + 1) % cp], ranks[(my_idx - 1) % cp]
+        delta = (do.float() * out.float()).sum(-1).permute(0, 2, 1)          # [B,H,S]
+        dq = torch.zeros_like(q, dtype=torch.float32)
+        kb, vb = k, v
+        dkb = torch.zeros_like(k, dtype=torch.float32)
+        dvb = torch.zeros_like(v, dtype=torch.float32)
+        for step in range(cp):
+            src = (my_idx - step) % cp
+            if src <= my_idx:
+                dq_s, dk_s, dv_s = _block_bwd(do, q, kb, vb, lse, delta, scale, causal=(src == my_idx))
+                dq += dq_s
+                dkb += dk_s
+                dvb += dv_s
+            # pass the block (and its gradient accumulators) on; after cp hops everything is home again
+            (kb, vb, dkb, dvb), reqs = _ring_exchange([kb, vb, dkb, dvb], group, nxt, prv)
+            for r in reqs:
+                r.wait()
+        return dq.to(q.dtype), dkb.to(k.dtype), dvb.to(v.dtype), None, None, None, None
+
+
+def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None, group=None,
+                   ranks: Optional[List[int]] = None) -> torch.Tensor:
+    """q [B,S_local,H,D], k/v [B,S_local,Hkv,D] (this rank's contiguous sequence chunk) -> [B,S_local,H,D]."""
+    group = group if group is not None else ps.get_context_model_parallel_group()
+    ranks = ranks if ranks is not None else ps.get_context_model_parallel_ranks()
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    if len(ranks) == 1:
+        from .. import ops
+        return ops.flash_attention(q, k, v, causal=True, scale=scale)
+    my_idx = ranks.index(dist.get_rank())
+    return _RingAttention.apply(q, k, v, scale, group, ranks, my_idx)

@@ -40,3 +40,8 @@ def test_pipeline_matches_unpipelined(pp, vpp, tp, nmb):
 @pytest.mark.parametrize("tp,pp,nproc,async_", [(1, 1, 2, "0"), (2, 1, 2, "0"), (1, 2, 2, "0"), (1, 1, 2, "1")])
 def test_checkpoint_resume_bit_exact(tmp_path, tp, pp, nproc, async_):
     run_dist("ckpt_resume.py", nproc, {"TP": str(tp), "PP": str(pp), "WORKDIR": str(tmp_path), "ASYNC": async_})
+
+
+@pytest.mark.parametrize("cp", [2, 4])
+def test_ring_attention_context_parallel(cp):
+    run_dist("ring_attention.py", cp, {"CP": str(cp)})
