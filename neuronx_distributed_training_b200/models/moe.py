@@ -125,7 +125,7 @@ class ExpertMLPs(nn.Module):
         for p in (self.mlp_op.gate_up_proj, self.mlp_op.down_proj):
             p.expert_parallel = ep > 1
         with torch.no_grad():
-            if use_cpu_initialization and tp > 1:
+            if use_cpu_initialization and (tp > 1 or ep > 1):
                 g = torch.empty(num_experts, hidden_size, mult * intermediate_size).normal_(0, init_std)
                 d = torch.empty(num_experts, intermediate_size, hidden_size).normal_(0, init_std)
                 g = g[epr * self.E_local:(epr + 1) * self.E_local]

@@ -56,7 +56,7 @@ class DistributedOptimizer:
                  zero1: bool = True, master_weights: bool = True, fp32_grad_acc: bool = True,
                  max_grad_norm: Optional[float] = 1.0, stochastic_rounding: bool = False,
                  state_dtype: torch.dtype = torch.float32, dp_group=None, grad_sync_groups: Optional[dict] = None,
-                 average_over_dp: bool = True, **unused):
+                 average_over_dp: bool = True, extra_grad_scale: float = 1.0, **unused):
         self.algorithm = algorithm.lower()
         self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, momentum=momentum)
         self.param_groups: List[Dict[str, Any]] = []
@@ -66,7 +66,10 @@ class DistributedOptimizer:
             for k, v in self.defaults.items():
                 g.setdefault(k, v)
             self.param_groups.append(g)
-        self.dp_group = dp_group if dp_group is not None else ps.get_data_context_parallel_group()
+        if isinstance(dp_group, str) and dp_group == "self":
+            self.dp_group = None            # explicitly no data-parallel reduction (e.g. experts with EP == DP)
+        else:
+            self.dp_group = dp_group if dp_group is not None else ps.get_data_context_parallel_group()
         self.dp_size = ps.group_size(self.dp_group)
         self.dp_rank = ps.group_rank(self.dp_group)
         self.zero1 = bool(zero1) and self.dp_size > 1
@@ -77,6 +80,7 @@ class DistributedOptimizer:
         self.stochastic_rounding = stochastic_rounding
         self.state_dtype = state_dtype
         self.average_over_dp = average_over_dp
+        self.extra_grad_scale = float(extra_grad_scale)   # e.g. 1/EP for expert-parallel parameters
         self.step_count = 0
         self.grad_norm: Optional[torch.Tensor] = None
         self._hooks = []
@@ -171,6 +175,8 @@ class DistributedOptimizer:
 
     def _reduce_over_dp(self) -> torch.Tensor:
         """Returns this rank's gradient shard (view) after the DP reduction."""
+        if self.extra_grad_scale != 1.0:
+            self.grad_buffer.mul_(self.extra_grad_scale)
         if self.dp_size == 1:
             return self.grad_buffer
         if self.average_over_dp:
@@ -209,26 +215,39 @@ class DistributedOptimizer:
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
-        self.step_count += 1
-        self.state["step"] = self.step_count
         if self._fused_zero1 is not None:
+            self.step_count += 1
+            self.state["step"] = self.step_count
             self._fused_zero1.step(self)
             return loss
+        sq = self.prepare_step()
+        self.apply_step(sq.sqrt())
+        return loss
+
+    def prepare_step(self, extra_norm_groups=()) -> torch.Tensor:
+        """Phase 1: SP grad sync + DP reduction; returns the squared global grad norm of THIS optimizer's params."""
+        self.step_count += 1
+        self.state["step"] = self.step_count
         self._sync_sequence_parallel_grads()
-        gshard = self._reduce_over_dp()
-        norm = self._global_grad_norm(gshard)
+        self._gshard = self._reduce_over_dp()
+        sq = self._global_grad_norm(self._gshard) ** 2
+        for grp in extra_norm_groups:
+            if ps.group_size(grp) > 1:
+                dist.all_reduce(sq, group=grp)
+        return sq
+
+    def apply_step(self, norm: torch.Tensor) -> None:
+        """Phase 2: clip with the (possibly combined) global norm, update the shard, all-gather params."""
         self.grad_norm = norm
-        if self.max_grad_norm is not None:
-            clip = torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0)
-        else:
-            clip = None
+        clip = torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0) if self.max_grad_norm is not None else None
+        gshard = self._gshard
         pshard = self.param_buffer[self.shard_lo:self.shard_hi]
         for s, lo, hi in self._seg_ranges():
             g = self.param_groups[s.group_idx]
             self._update(pshard[lo:hi], gshard[lo:hi], lo, hi, g, clip)
         if self.zero1:
             dist.all_gather_into_tensor(self.param_buffer, pshard, group=self.dp_group)
-        return loss
+        self._gshard = None
 
     def _update(self, p, g, lo, hi, group, clip):
         lr, wd = float(group["lr"]), float(group["weight_decay"])
@@ -305,3 +324,60 @@ class DistributedOptimizer:
             return 0 if t is None else t.numel() * t.element_size()
         return {"params": nb(self.param_buffer), "grads": nb(self.grad_buffer), "master": nb(self.master),
                 "exp_avg": nb(self.exp_avg), "exp_avg_sq": nb(self.exp_avg_sq)}
+
+
+class ChainedOptimizer:
+    """Several flat optimizers stepped as one (dense params reduced over the DP group, expert-parallel params over
+    the expert-data-parallel group) with ONE global grad-norm / clip coefficient."""
+
+    def __init__(self, optimizers, extra_norm_groups=None):
+        self.optimizers = list(optimizers)
+        self.extra_norm_groups = extra_norm_groups or [() for _ in self.optimizers]
+        self.grad_norm = None
+
+    @property
+    def param_groups(self):
+        return [g for o in self.optimizers for g in o.param_groups]
+
+    @property
+    def zero1(self):
+        return any(o.zero1 for o in self.optimizers)
+
+    @property
+    def master(self):
+        return self.optimizers[0].master
+
+    def zero_grad(self, set_to_none: bool = True):
+        for o in self.optimizers:
+            o.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        sq = None
+        for o, extra in zip(self.optimizers, self.extra_norm_groups):
+            s = o.prepare_step(extra)
+            sq = s if sq is None else sq + s
+        norm = sq.sqrt()
+        for o in self.optimizers:
+            o.apply_step(norm)
+        self.grad_norm = norm
+        return loss
+
+    def state_dict(self):
+        return {"chained": [o.state_dict() for o in self.optimizers]}
+
+    def load_state_dict(self, sd):
+        for o, s in zip(self.optimizers, sd["chained"]):
+            o.load_state_dict(s)
+
+    def sync_master_from_params(self):
+        for o in self.optimizers:
+            o.sync_master_from_params()
+
+    def memory_bytes(self):
+        out = {}
+        for o in self.optimizers:
+            for k, v in o.memory_bytes().items():
+                out[k] = out.get(k, 0) + v
+        return out

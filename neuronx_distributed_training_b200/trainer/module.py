@@ -110,12 +110,28 @@ class BaseModelModule:
         groups = self.setup_optimizer_param_groups()
         clip = self.cfg.trainer.get("gradient_clip_val", None)
         pol = self.precision
-        self.optimizer = DistributedOptimizer(
-            groups, lr=float(ocfg.get("lr", 1e-4)), betas=tuple(ocfg.get("betas", (0.9, 0.999))),
-            eps=float(ocfg.get("eps", 1e-8)), weight_decay=float(ocfg.get("weight_decay", 0.01)),
-            algorithm=algo, momentum=float(ocfg.get("momentum", 0.0)), zero1=self.zero1,
-            master_weights=pol.master_weights, fp32_grad_acc=pol.fp32_grad_acc, max_grad_norm=clip,
-            stochastic_rounding=pol.stochastic_rounding, state_dtype=pol.optimizer_state_dtype)
+        common = dict(lr=float(ocfg.get("lr", 1e-4)), betas=tuple(ocfg.get("betas", (0.9, 0.999))),
+                      eps=float(ocfg.get("eps", 1e-8)), weight_decay=float(ocfg.get("weight_decay", 0.01)),
+                      algorithm=algo, momentum=float(ocfg.get("momentum", 0.0)), zero1=self.zero1,
+                      master_weights=pol.master_weights, fp32_grad_acc=pol.fp32_grad_acc, max_grad_norm=clip,
+                      stochastic_rounding=pol.stochastic_rounding, state_dtype=pol.optimizer_state_dtype)
+        is_expert = lambda p: bool(getattr(p, "expert_parallel", False))
+        if self.dims.ep > 1 and any(is_expert(p) for g in groups for p in g["params"]):
+            # expert-parallel parameters differ across the EP group: reduce them over the expert-data-parallel group
+            # only, and add their norm over the EP group; everything else reduces over the full DP(xCP) group.
+            from ..optim.distributed import ChainedOptimizer
+            dense = [dict(g, params=[p for p in g["params"] if not is_expert(p)]) for g in groups]
+            expert = [dict(g, params=[p for p in g["params"] if is_expert(p)]) for g in groups]
+            dense = [g for g in dense if g["params"]]
+            expert = [g for g in expert if g["params"]]
+            o_dense = DistributedOptimizer(dense, **common)
+            # tokens of every EP rank reach an expert, each carrying d(loss_rank): scale by 1/EP so that together with the
+            # mean over the expert-data-parallel group the gradient is the mean over the whole data-parallel batch
+            o_exp = DistributedOptimizer(expert, dp_group=ps.get_expert_data_parallel_group() or "self",
+                                         extra_grad_scale=1.0 / self.dims.ep, **common)
+            self.optimizer = ChainedOptimizer([o_dense, o_exp], [(), (ps.get_expert_model_parallel_group(),)])
+        else:
+            self.optimizer = DistributedOptimizer(groups, **common)
         sched = ocfg.get("sched", None)
         self.lr_scheduler = prepare_lr_scheduler(self.optimizer, sched, max_steps) if sched is not None else None
         return self.optimizer, self.lr_scheduler
