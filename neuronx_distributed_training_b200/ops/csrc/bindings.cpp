@@ -12,11 +12,13 @@ void adamw_flat(at::Tensor master, at::Tensor param, const at::Tensor& grad, at:
                 const at::Tensor& decay_mask, double lr, double b1, double b2, double eps, double wd, double bc1,
                 double bc2, const at::Tensor& grad_scale, bool sr, int64_t seed);
 at::Tensor sq_norm(const at::Tensor& x);
-void ag_gemm(at::Tensor xg, const at::Tensor& b, at::Tensor out, const at::Tensor& other, std::vector<int64_t> peer_x,
-             int64_t flags_ptr, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank,
-             int64_t tp, int64_t mode, bool b_kmajor, bool accumulate, int64_t num_comm_ctas);
-void ag_only(at::Tensor xg, std::vector<int64_t> peer_x, int64_t flags_ptr, int64_t hs_local_ptr,
-             std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t num_comm_ctas);
+void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
+             std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
+             std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
+             bool accumulate, int64_t num_comm_ctas);
+void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer,
+             int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp,
+             int64_t num_comm_ctas);
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
              int64_t rank, int64_t tp, bool b_kmajor);

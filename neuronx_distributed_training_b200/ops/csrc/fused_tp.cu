@@ -37,11 +37,12 @@ constexpr int RING_SLOTS = 7;
 constexpr int PIECE_BYTES = 32 * 1024;
 
 struct CommArgs {
-  const uint8_t* peer_x[MAX_TP];   // every rank's input shard (symmetric buffer, this call's parity)
+  const uint8_t* x_local;          // my input shard [rows_per_rank, row_bytes] (ordinary device memory)
+  uint8_t* xg_peer[MAX_TP];        // every rank's gathered buffer [tp * rows_per_rank, row_bytes] (symmetric, this parity)
+  uint32_t* flags_peer[MAX_TP];    // every rank's ready flags, one per 128-row block of its gathered buffer
   uint32_t* hs_peer[MAX_TP];       // every rank's handshake array
   uint32_t* hs_local;              // my handshake array [tp]
-  uint8_t* xg;                     // local gathered buffer [tp * rows_per_rank, row_bytes]
-  uint32_t* flags;                 // local ready flags, one per 128-row block of xg
+  uint32_t* flags;                 // my ready flags (== flags_peer[rank])
   uint32_t epoch;
   int rank, tp, rows_per_rank, row_bytes, num_comm_ctas;
 };
@@ -53,7 +54,7 @@ struct AgGate {
   int local_lo, local_hi;   // row-blocks of my own shard: already in place, never waited on
   __device__ __forceinline__ void wait_flag(int blk) const {
     if (blk >= local_lo && blk < local_hi) return;
-    while (ld_acquire_gpu(flags + blk) != epoch) __nanosleep(64);
+    while (ld_acquire_sys(flags + blk) != epoch) __nanosleep(64);
     fence_proxy_async_all();   // generic-proxy acquire -> subsequent async-proxy (TMA) reads
   }
   __device__ __forceinline__ void wait_m(int m_blk) const {
@@ -72,7 +73,10 @@ __device__ __forceinline__ void send_handshake(uint32_t* const* hs_peer, int ran
   for (int p = 0; p < tp; ++p) st_release_sys(hs_peer[p] + rank, epoch);
 }
 
-// One thread per comm CTA drives: peer/global --bulk--> smem ring --bulk--> local gathered buffer.
+// PUSH-mode all-gather.  One thread per comm CTA drives: my shard --bulk--> smem ring --bulk--> every peer's gathered
+// buffer.  Remote *stores* are posted (fire and forget), so the transfer runs at link rate instead of being bound by
+// NVLink round-trip latency x bytes in flight as a pull (remote loads) would be.  After a 128-row block has been
+// written everywhere, its ready flag is released (st.release.sys) on every peer.
 __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING_SLOTS * PIECE_BYTES);
@@ -80,24 +84,20 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
   if (blockIdx.x == 0) send_handshake(a.hs_peer, a.rank, a.tp, a.epoch);
   for (int i = 0; i < RING_SLOTS; ++i) mbar_init(&full[i], 1);
   fence_barrier_init();
+  // a peer's gathered buffer of this parity was last read by its call (epoch - 2): it is free once that peer has
+  // entered call (epoch - 1)
+  for (int p = 0; p < a.tp; ++p) {
+    if (p == a.rank) continue;
+    while ((int)ld_acquire_sys(a.hs_local + p) < (int)a.epoch - 1) __nanosleep(100);
+  }
   const int blocks_per_rank = a.rows_per_rank / 128;
-  const int total_blocks = blocks_per_rank * a.tp;
   const size_t block_bytes = (size_t)128 * a.row_bytes;
   const int pieces = (int)((block_bytes + PIECE_BYTES - 1) / PIECE_BYTES);
   uint32_t slot_phase = 0;   // bit i = phase parity of ring slot i
-  int waited_rank_mask = 0;
-  for (int idx = blockIdx.x; idx < total_blocks; idx += a.num_comm_ctas) {
-    int blk = idx + a.rank * blocks_per_rank;
-    if (blk >= total_blocks) blk -= total_blocks;
-    const int src_rank = blk / blocks_per_rank;
-    if (src_rank == a.rank) continue;     // my own shard was placed into xg by the host-side copy
-    if (!((waited_rank_mask >> src_rank) & 1)) {
-      // the peer's shard for this epoch is in place (and it is done with the previous use of my buffers)
-      while (ld_acquire_sys(a.hs_local + src_rank) < a.epoch) __nanosleep(100);
-      waited_rank_mask |= 1 << src_rank;
-    }
-    const uint8_t* src = a.peer_x[src_rank] + (size_t)(blk - src_rank * blocks_per_rank) * block_bytes;
-    uint8_t* dst = a.xg + (size_t)blk * block_bytes;
+  for (int lb = blockIdx.x; lb < blocks_per_rank; lb += a.num_comm_ctas) {
+    const int blk = a.rank * blocks_per_rank + lb;
+    const uint8_t* src = a.x_local + (size_t)lb * block_bytes;
+    const size_t dst_off = (size_t)blk * block_bytes;
     auto piece_bytes = [&](int p) -> uint32_t {
       const size_t off = (size_t)p * PIECE_BYTES;
       return (uint32_t)min((size_t)PIECE_BYTES, block_bytes - off);
@@ -111,19 +111,28 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
       const int s = p % RING_SLOTS;
       mbar_wait(&full[s], (slot_phase >> s) & 1);
       slot_phase ^= 1u << s;
-      bulk_s2g(dst + (size_t)p * PIECE_BYTES, ring + s * PIECE_BYTES, piece_bytes(p));
+      // the rank right below me consumes my rows first (its tile order walks rank+1, rank+2, ...)
+      for (int d = 1; d < a.tp; ++d) {
+        int peer = a.rank - d;
+        if (peer < 0) peer += a.tp;
+        bulk_s2g(a.xg_peer[peer] + dst_off + (size_t)p * PIECE_BYTES, ring + s * PIECE_BYTES, piece_bytes(p));
+      }
       tma_store_commit();
       const int np = p + RING_SLOTS;
       if (np < pieces) {
-        tma_store_wait_read<0>();   // smem slot drained by the store before the next load lands in it
+        tma_store_wait_read<0>();   // smem slot drained by the stores before the next load lands in it
         mbar_expect_tx(&full[s], piece_bytes(np));
         bulk_g2s(ring + s * PIECE_BYTES, src + (size_t)np * PIECE_BYTES, piece_bytes(np), &full[s]);
       }
     }
-    tma_store_wait<0>();           // all bytes of this row-block are written
+    tma_store_wait<0>();           // every byte of this row-block has been written to every peer
     fence_proxy_async_all();
-    __threadfence();
-    st_release_gpu(a.flags + blk, a.epoch);
+    __threadfence_system();
+    for (int d = 1; d < a.tp; ++d) {
+      int peer = a.rank - d;
+      if (peer < 0) peer += a.tp;
+      st_release_sys(a.flags_peer[peer] + blk, a.epoch);
+    }
   }
 }
 
@@ -146,6 +155,12 @@ ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 __global__ void __launch_bounds__(NUM_THREADS, 1) ag_only_kernel(const CommArgs comm) {
   extern __shared__ uint8_t smem_raw[];
   comm_cta(comm, smem_raw);
+  // the kernel completes only when every peer's rows have landed in my gathered buffer
+  const int bpr = comm.rows_per_rank / 128;
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < bpr * comm.tp; blk += gridDim.x * blockDim.x) {
+    if (blk / bpr == comm.rank) continue;
+    while (ld_acquire_sys(comm.flags + blk) != comm.epoch) __nanosleep(200);
+  }
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -257,9 +272,10 @@ static void fill_ptrs(const std::vector<int64_t>& v, int tp, void** dst) {
 // mode 0: out[M_total,N] = xg[M_total,K] * op(b)            (b: [N,K] if b_kmajor else [K,N])
 // mode 1: out[N',K'] (+)= other[M_total,N']^T * xg[M_total,K']   (wgrad; `b` unused)
 // xg is filled inside the kernel from the peers' shards `peer_x` ([rows_per_rank, K] each).
-void ag_gemm(at::Tensor xg, const at::Tensor& b, at::Tensor out, const at::Tensor& other, std::vector<int64_t> peer_x,
-             int64_t flags_ptr, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank,
-             int64_t tp, int64_t mode, bool b_kmajor, bool accumulate, int64_t num_comm_ctas) {
+void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
+             std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
+             std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
+             bool accumulate, int64_t num_comm_ctas) {
   using namespace fused;
   TORCH_CHECK(xg.is_cuda() && xg.is_contiguous() && xg.scalar_type() == at::kBFloat16 && xg.dim() == 2);
   TORCH_CHECK(tp >= 2 && tp <= MAX_TP);
@@ -269,13 +285,18 @@ void ag_gemm(at::Tensor xg, const at::Tensor& b, at::Tensor out, const at::Tenso
   c10::cuda::CUDAGuard guard(xg.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   CommArgs comm;
-  fill_ptrs(peer_x, tp, (void**)comm.peer_x);
+  TORCH_CHECK(x_local.is_cuda() && x_local.is_contiguous() && x_local.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x_local.size(0) * tp == xg.size(0) && x_local.size(1) == xg.size(1), "shard / gathered shape mismatch");
+  comm.x_local = reinterpret_cast<const uint8_t*>(x_local.data_ptr());
+  fill_ptrs(xg_peer, tp, (void**)comm.xg_peer);
+  fill_ptrs(flags_peer, tp, (void**)comm.flags_peer);
   fill_ptrs(hs_peer, tp, (void**)comm.hs_peer);
   comm.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
-  comm.xg = reinterpret_cast<uint8_t*>(xg.data_ptr());
-  comm.flags = reinterpret_cast<uint32_t*>(flags_ptr);
+  comm.flags = comm.flags_peer[rank];
+  TORCH_CHECK(reinterpret_cast<uint8_t*>(xg.data_ptr()) == comm.xg_peer[rank], "xg must be my symmetric gathered buffer");
   comm.epoch = (uint32_t)epoch;
   comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
+  num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, rows_per_rank / 128));
   comm.num_comm_ctas = num_comm_ctas;
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   TORCH_CHECK(num_comm_ctas >= 1 && num_comm_ctas < sms);
@@ -316,21 +337,27 @@ void ag_gemm(at::Tensor xg, const at::Tensor& b, at::Tensor out, const at::Tenso
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
-void ag_only(at::Tensor xg, std::vector<int64_t> peer_x, int64_t flags_ptr, int64_t hs_local_ptr,
-             std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t num_comm_ctas) {
+void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer,
+             int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp,
+             int64_t num_comm_ctas) {
   using namespace fused;
   const int M_total = xg.size(0), Kx = xg.size(1);
   const int rows_per_rank = M_total / tp;
   TORCH_CHECK(rows_per_rank % 128 == 0);
   c10::cuda::CUDAGuard guard(xg.device());
   CommArgs comm;
-  fill_ptrs(peer_x, tp, (void**)comm.peer_x);
+  TORCH_CHECK(x_local.is_cuda() && x_local.is_contiguous() && x_local.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x_local.size(0) * tp == xg.size(0) && x_local.size(1) == xg.size(1), "shard / gathered shape mismatch");
+  comm.x_local = reinterpret_cast<const uint8_t*>(x_local.data_ptr());
+  fill_ptrs(xg_peer, tp, (void**)comm.xg_peer);
+  fill_ptrs(flags_peer, tp, (void**)comm.flags_peer);
   fill_ptrs(hs_peer, tp, (void**)comm.hs_peer);
   comm.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
-  comm.xg = reinterpret_cast<uint8_t*>(xg.data_ptr());
-  comm.flags = reinterpret_cast<uint32_t*>(flags_ptr);
+  comm.flags = comm.flags_peer[rank];
+  TORCH_CHECK(reinterpret_cast<uint8_t*>(xg.data_ptr()) == comm.xg_peer[rank], "xg must be my symmetric gathered buffer");
   comm.epoch = (uint32_t)epoch;
   comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
+  num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, rows_per_rank / 128));
   comm.num_comm_ctas = num_comm_ctas;
   set_smem(ag_only_kernel);
   ag_only_kernel<<<num_comm_ctas, NUM_THREADS, SMEM_BYTES, at::cuda::getCurrentCUDAStream()>>>(comm);

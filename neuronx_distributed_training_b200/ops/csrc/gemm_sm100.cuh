@@ -190,6 +190,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
     constexpr int NCHUNK = BLOCK_N / COLS_PER_CHUNK;
     uint32_t acc = 0, acc_phase = 0, cbuf = 0;
     bool first_store = true;
+    int prev_tile_m = -1;
     for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
       int m_blk, n_blk;
       tile_coords(p, t, m_blk, n_blk);
@@ -265,15 +266,29 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
       }
       if constexpr (OUT == OUT_BF16_PEER) {
         if (issuer) {
-          tma_store_wait<0>();          // every byte of this tile has been written to the owner's staging buffer
-          fence_proxy_async_all();
-          __threadfence_system();
-          gate.tile_done(m_blk);        // red.release.sys on the owner's arrival counter
+          // completion of the PREVIOUS tile's stores is awaited while this tile's are in flight (NCHUNK groups),
+          // so the NVLink write latency hides behind the next tile's math
+          if (prev_tile_m >= 0) {
+            tma_store_wait<NCHUNK>();
+            fence_proxy_async_all();
+            __threadfence_system();
+            gate.tile_done(prev_tile_m);    // red.release.sys on the owner's arrival counter
+          }
+          prev_tile_m = m_blk;
         }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
-    if (issuer) tma_store_wait<0>();
+    if (issuer) {
+      tma_store_wait<0>();
+      if constexpr (OUT == OUT_BF16_PEER) {
+        if (prev_tile_m >= 0) {
+          fence_proxy_async_all();
+          __threadfence_system();
+          gate.tile_done(prev_tile_m);
+        }
+      }
+    }
   }
 
   tcgen05_fence_before();

@@ -3,7 +3,7 @@
 One ``FusedTP`` object per tensor-parallel group owns a *symmetric* workspace (same layout on every rank,
 peer-mapped over NVLink through ``torch.distributed._symmetric_memory``):
 
-    [ handshake slots | RS arrival counters x2 | input-shard buffers x2 | RS staging slabs x2 ]
+    [ handshake slots | RS arrival counters x2 | AG ready flags | gathered buffers x2 | RS staging slabs x2 ]
 
 and a monotonically increasing ``epoch`` (every fused call on every rank of the group advances it in
 lock-step, which is what makes the double-buffer parity protocol safe - see the kernel file).
@@ -29,7 +29,9 @@ from . import state as ps
 _HS_OFF = 0
 _CNT_OFF = 4096
 _CNT_BYTES = 4096            # per parity: up to 1024 row-blocks of 128 rows
-_DATA_OFF = _CNT_OFF + 2 * _CNT_BYTES
+_FLAG_OFF = _CNT_OFF + 2 * _CNT_BYTES
+_FLAG_BYTES = 16384          # ready flags of the gathered buffer (one uint32 per 128-row block), written by the peers
+_DATA_OFF = _FLAG_OFF + _FLAG_BYTES
 
 
 def _align(n: int, a: int = 4096) -> int:
@@ -48,9 +50,10 @@ class FusedTP:
         self.num_comm_ctas_fixed = int(num_comm_ctas or os.environ.get("NXDT_AG_COMM_CTAS", 0))
         self.num_comm_ctas = self.num_comm_ctas_fixed or (12 if self.tp >= 4 else 8)
         self.max_shard_bytes = _align(max_shard_bytes)
+        self.max_gather_bytes = self.max_shard_bytes * self.tp
         self.max_stage_bytes = _align(max_stage_bytes)
-        self.x_off = [_DATA_OFF, _DATA_OFF + self.max_shard_bytes]
-        self.stage_off = [_DATA_OFF + 2 * self.max_shard_bytes, _DATA_OFF + 2 * self.max_shard_bytes + self.max_stage_bytes]
+        self.xg_off = [_DATA_OFF, _DATA_OFF + self.max_gather_bytes]
+        self.stage_off = [_DATA_OFF + 2 * self.max_gather_bytes, _DATA_OFF + 2 * self.max_gather_bytes + self.max_stage_bytes]
         total = self.stage_off[1] + self.max_stage_bytes
         try:
             symm_mem.enable_symm_mem_for_group(self.group.group_name)
@@ -61,7 +64,6 @@ class FusedTP:
         self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
         self.base_ptrs: List[int] = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(self.base_ptrs) == self.tp
-        self.flags = torch.zeros(4096, dtype=torch.int32, device=self.device)
         self.epoch = 0
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
@@ -74,21 +76,17 @@ class FusedTP:
     def _hs(self) -> Tuple[int, List[int]]:
         return self.base_ptrs[self.rank] + _HS_OFF, [p + _HS_OFF for p in self.base_ptrs]
 
-    def _stage_shard(self, x2d: torch.Tensor, parity: int) -> List[int]:
-        nbytes = x2d.numel() * x2d.element_size()
-        if nbytes > self.max_shard_bytes:
-            raise ValueError(f"shard of {nbytes} bytes exceeds the fused-TP workspace ({self.max_shard_bytes}); "
-                             "raise max_shard_bytes")
-        dst = self.buf[self.x_off[parity]: self.x_off[parity] + nbytes].view(torch.bfloat16).view(x2d.shape)
-        dst.copy_(x2d)
-        return [p + self.x_off[parity] for p in self.base_ptrs]
-
-    def _new_gather_buffer(self, x2d: torch.Tensor) -> torch.Tensor:
-        """gathered buffer with my own shard already in place (the kernel only pulls the peers' shards)"""
+    def _gather_buffer(self, x2d: torch.Tensor, parity: int):
+        """My symmetric gathered buffer for this call (peers push their shards into it) with my own shard copied
+        in; returns (view [tp*m, K], per-rank base pointers of the same buffer, per-rank flag pointers)."""
         m, K = x2d.shape
-        xg = torch.empty(m * self.tp, K, dtype=x2d.dtype, device=x2d.device)
+        nbytes = m * self.tp * K * x2d.element_size()
+        if nbytes > self.max_gather_bytes:
+            raise ValueError(f"gathered tensor of {nbytes} bytes exceeds the fused-TP workspace ({self.max_gather_bytes})")
+        off = self.xg_off[parity]
+        xg = self.buf[off: off + nbytes].view(torch.bfloat16).view(m * self.tp, K)
         xg[self.rank * m:(self.rank + 1) * m].copy_(x2d)
-        return xg
+        return xg, [p + off for p in self.base_ptrs], [p + _FLAG_OFF for p in self.base_ptrs]
 
     def supports(self, rows_local: int, *dims: int) -> bool:
         return rows_local % 128 == 0 and all(d % 8 == 0 for d in dims)
@@ -97,7 +95,7 @@ class FusedTP:
     # peer handshake, so they win when the NVLink time is a sizeable fraction of the GEMM time) -----------------
     GEMM_FLOPS = 1.35e15          # sustained tcgen05 bf16 rate of gemm_sm100 on Llama shapes
     LINK_BPS = 6.0e11             # ~600 GB/s effective inbound/outbound per GPU
-    PER_CTA_BPS = 7.5e10          # one comm CTA keeps 7 x 32 KB in flight over a ~2.5 us NVLink round trip
+    PER_CTA_BPS = 1.5e11          # one comm CTA: local bulk loads + posted remote bulk stores
 
     def _ratio(self, m_total: int, n: int, k: int, bytes_moved: float) -> float:
         return (bytes_moved / self.LINK_BPS) / max(2.0 * m_total * n * k / self.GEMM_FLOPS, 1e-9)
@@ -129,38 +127,39 @@ class FusedTP:
         m, K = x2d.shape
         N = w.shape[0] if trans_b else w.shape[1]
         epoch, par = self._next_epoch()
-        peer_x = self._stage_shard(x2d.contiguous(), par)
-        xg = self._new_gather_buffer(x2d)
+        x2d = x2d.contiguous()
+        xg, xg_peer, flags_peer = self._gather_buffer(x2d, par)
         out = torch.empty(m * self.tp, N, dtype=x2d.dtype, device=x2d.device)
         hs_local, hs_peer = self._hs()
         ops._count()
         nc = self._comm_ctas(m * self.tp, N, K, m * (self.tp - 1) * K * 2)
-        ops.C().ag_gemm(xg, w, out, out, peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank, self.tp,
+        ops.C().ag_gemm(xg, x2d, w, out, out, xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank, self.tp,
                         0, trans_b, False, nc)
+        # NOTE: the gathered view lives in the double-buffered workspace: consume it before the second next fused call
         return (out, xg) if return_gathered else out
 
     def all_gather_wgrad(self, dy2d: torch.Tensor, x2d: torch.Tensor, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
         """``out (+)= dy2d^T @ AG_rows(x2d)``; dy2d [M_total, N'], x2d [m, K'] local shard, out [N', K']."""
         m, K = x2d.shape
         epoch, par = self._next_epoch()
-        peer_x = self._stage_shard(x2d.contiguous(), par)
-        xg = self._new_gather_buffer(x2d)
+        x2d = x2d.contiguous()
+        xg, xg_peer, flags_peer = self._gather_buffer(x2d, par)
         hs_local, hs_peer = self._hs()
         ops._count()
         nc = self._comm_ctas(dy2d.shape[1], K, m * self.tp, m * (self.tp - 1) * K * 2)
-        ops.C().ag_gemm(xg, xg, out, dy2d.contiguous(), peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank,
+        ops.C().ag_gemm(xg, x2d, xg, out, dy2d.contiguous(), xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank,
                         self.tp, 1, True, accumulate, nc)
         return out
 
     def all_gather(self, x2d: torch.Tensor) -> torch.Tensor:
         m, K = x2d.shape
         epoch, par = self._next_epoch()
-        peer_x = self._stage_shard(x2d.contiguous(), par)
-        xg = self._new_gather_buffer(x2d)
+        x2d = x2d.contiguous()
+        xg, xg_peer, flags_peer = self._gather_buffer(x2d, par)
         hs_local, hs_peer = self._hs()
         ops._count()
-        ops.C().ag_only(xg, peer_x, self.flags.data_ptr(), hs_local, hs_peer, epoch, self.rank, self.tp, self.num_comm_ctas * 2)
-        return xg
+        ops.C().ag_only(xg, x2d, xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank, self.tp, self.num_comm_ctas)
+        return xg.clone()
 
     def gemm_reduce_scatter(self, a2d: torch.Tensor, w: torch.Tensor, trans_b: bool = True) -> torch.Tensor:
         """``RS_rows(a2d @ (w.T if trans_b else w))``; a2d [M_total, K_local]."""
