@@ -1,0 +1,103 @@
+import glob
+import json
+import os
+
+import pytest
+import torch
+
+from neuronx_distributed_training_b200.config import from_dict, process_config
+from neuronx_distributed_training_b200.parallel import state as ps
+
+
+def _cfg(log_dir, max_steps=4, **model_kw):
+    model = {"model_config": "llama_125m", "encoder_seq_length": 32, "num_layers": 2, "hidden_size": 64, "intermediate_size": 128,
+             "num_attention_heads": 4, "num_kv_heads": 2, "vocab_size": 128, "fusions": {"flash_attention": False},
+             "optim": {"name": "adamw_fp32OptState", "lr": 1e-2, "weight_decay": 0.01, "betas": [0.9, 0.95],
+                       "sched": {"name": "LinearAnnealingWithWarmUp", "warmup_steps": 1, "max_steps": 10}}}
+    model.update(model_kw)
+    return from_dict({
+        "name": "t", "model_source": "hf", "seed": 3,
+        "trainer": {"devices": 1, "num_nodes": 1, "max_steps": max_steps, "log_every_n_steps": 1, "val_check_interval": 2,
+                    "limit_val_batches": 2, "gradient_clip_val": 1.0},
+        "exp_manager": {"explicit_log_dir": log_dir, "create_tensorboard_logger": False, "create_checkpoint_callback": True,
+                        "resume_if_exists": True, "resume_ignore_no_checkpoint": True, "log_parameter_norm": True, "log_gradient_norm": True,
+                        "checkpoint_callback_params": {"save_top_k": 1, "every_n_train_steps": 2, "filename": "t--{step}-{consumed_samples}"}},
+        "distributed_strategy": {"tensor_model_parallel_size": 1, "zero1": True},
+        "data": {"micro_batch_size": 1, "global_batch_size": 2, "synthetic": True},
+        "model": model, "precision": {"type": "fp32"},
+    })
+
+
+@pytest.fixture(autouse=True)
+def _mp():
+    ps.initialize_model_parallel(1, 1, 1)
+    yield
+    ps.destroy_model_parallel()
+    import logging
+    lg = logging.getLogger("nxdt")
+    for h in list(lg.handlers):
+        lg.removeHandler(h)
+
+
+def _fit(cfg):
+    from neuronx_distributed_training_b200.trainer import Trainer
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    from neuronx_distributed_training_b200.data import SyntheticDataModule
+    from neuronx_distributed_training_b200.utils.exp_manager import exp_manager
+    process_config(cfg, 1)
+    tr = Trainer(**cfg.trainer.to_dict())
+    em = exp_manager(tr, cfg.exp_manager)
+    mod = HFLlamaModule(cfg, tr)
+    tr.fit(mod, SyntheticDataModule(cfg, tr), ckpt_path=em.resume_from_checkpoint)
+    return tr, mod
+
+
+def test_fit_logs_validates_and_checkpoints(tmp_path):
+    tr, mod = _fit(_cfg(str(tmp_path / "run")))
+    assert tr.global_step == 4
+    m = tr.logged_metrics
+    for k in ("reduced_train_loss", "lr", "gradient_norm", "parameter_norm", "consumed_samples", "throughput", "throughput_peak"):
+        assert k in m, k
+    assert m["consumed_samples"] == 8 and "val_loss" in tr.callback_metrics
+    files = os.listdir(tmp_path / "run")
+    assert "cmd-args.log" in files and "metrics.jsonl" in files and any(f.startswith("nemo_log_globalrank-0") for f in files)
+    ck = glob.glob(str(tmp_path / "run" / "checkpoints" / "*.ckpt"))
+    assert len(ck) == 1 and "step=4-consumed_samples=8.0" in ck[0]          # save_top_k=1 kept the newest
+    lines = [json.loads(l) for l in open(tmp_path / "run" / "metrics.jsonl")]
+    assert any("val_loss" in l for l in lines) and sum("reduced_train_loss" in l for l in lines) == 4
+
+
+def test_trainer_rejects_unsupported_options():
+    from neuronx_distributed_training_b200.trainer import Trainer
+    with pytest.raises(ValueError):
+        Trainer(accumulate_grad_batches=2)
+    with pytest.raises(ValueError):
+        Trainer(gradient_clip_algorithm="value")
+    t = Trainer(max_time="00:00:01:30", lnc=2, sequential_move_factor=11)    # Neuron-only knobs are accepted
+    assert t.max_time == 90.0
+
+
+@pytest.mark.parametrize("gran,rec", [("selective", ["LlamaMLP", "CoreAttention"]), ("full", None)])
+def test_activation_checkpointing_is_exact(tmp_path, gran, rec):
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    losses = {}
+    for tag, kw in (("none", {}), ("ckpt", {"activations_checkpoint_granularity": gran, "activations_checkpoint_recompute": rec})):
+        cfg = process_config(_cfg(str(tmp_path / tag), **kw), 1)
+        mod = HFLlamaModule(cfg, None); mod.setup(); mod.configure_optimizers(10)
+        ids = torch.randint(0, 128, (2, 32), generator=torch.Generator().manual_seed(0))
+        ls = [float(mod.training_step({"input_ids": ids, "labels": ids.clone()})) for _ in range(3)]
+        losses[tag] = ls
+        if tag == "ckpt":
+            n = sum(1 for m in mod.model.modules() if getattr(m, "_activation_checkpointed", False))
+            assert n == (4 if gran == "selective" else 2)
+    assert losses["none"] == pytest.approx(losses["ckpt"], abs=1e-6)
+
+
+def test_unknown_recompute_class_and_exp_manager_keys(tmp_path):
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    from neuronx_distributed_training_b200.utils.exp_manager import ExpManagerConfig
+    cfg = process_config(_cfg(str(tmp_path / "x"), activations_checkpoint_granularity="selective", activations_checkpoint_recompute=["Nope"]), 1)
+    with pytest.raises(ValueError):
+        HFLlamaModule(cfg, None).setup()
+    with pytest.raises(ValueError):
+        ExpManagerConfig.from_config(from_dict({"not_a_key": 1}))
