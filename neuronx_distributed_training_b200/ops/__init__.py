@@ -335,9 +335,14 @@ def _sdpa(q, k, v, causal, scale):
 
 def flash_attention(q, k, v, causal: bool = True, window: Optional[int] = None, scale: Optional[float] = None):
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
-    if _use_native(q) and q.dtype == torch.bfloat16 and q.shape[-1] in (64, 128) and hasattr(C(), "flash_attn_fwd"):
+    native_ok = (_use_native(q) and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and causal and q.shape[1] % 128 == 0
+                 and q.shape[1] == k.shape[1] and hasattr(C(), "flash_attn_fwd"))
+    if native_ok and hasattr(C(), "flash_attn_bwd"):
         return _FlashAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal,
                                   int(window or 0), float(scale))
+    if native_ok and not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)):
+        _count()
+        return C().flash_attn_fwd(q.contiguous(), k.contiguous(), v.contiguous(), True, int(window or 0), float(scale))[0]
     if q.is_cuda and (window is None or window <= 0):
         return _sdpa(q, k, v, causal, scale)   # baseline arm: library flash attention through SDPA
     return attention_ref(q, k, v, causal, window, scale)

@@ -12,6 +12,8 @@ void adamw_flat(at::Tensor master, at::Tensor param, const at::Tensor& grad, at:
                 const at::Tensor& decay_mask, double lr, double b1, double b2, double eps, double wd, double bc1,
                 double bc2, const at::Tensor& grad_scale, bool sr, int64_t seed);
 at::Tensor sq_norm(const at::Tensor& x);
+std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
+                                       int64_t window, double scale);
 void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
              std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
              std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
@@ -32,6 +34,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("adamw_flat", &adamw_flat);
   m.def("sq_norm", &sq_norm);
+  m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 causal flash attention forward (head_dim 128)");
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");
   m.def("ag_only", &ag_only);
   m.def("gemm_rs", &gemm_rs, "fused tcgen05 GEMM -> reduce-scatter over peer memory");

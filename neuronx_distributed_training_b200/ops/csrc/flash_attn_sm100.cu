@@ -1,0 +1,324 @@
+// Causal flash attention forward for sm_100a (head_dim 128, GQA-native, optional sliding window).
+//
+// One CTA = 128 query rows of one (batch, head).  192 threads:
+//   warp 0      TMA producer: Q once, then K_j / V_j tiles (128 keys each) through 2-stage rings
+//   warp 1      tcgen05 issuer:  S_j = Q K_j^T  (128x128x128, accumulator in TMEM, double buffered)
+//                                O  += P_j V_j   (A = P from shared memory, B = V tile as an MN-major operand)
+//               QK_{j+1} is issued BEFORE PV_j so the tensor core computes the next scores while the softmax
+//               warps are still busy with block j.
+//   warps 2..5  softmax + epilogue: thread t owns query row t (TMEM lane t): tcgen05.ld the score row, online
+//               softmax in the exp2 domain with LAZY rescaling (O in TMEM is only rescaled when a row maximum
+//               grows by more than 2^8; otherwise the stale maximum is kept, which is exact after the final 1/l
+//               normalisation), P written as bf16 into the 128B-swizzled K-major layout the PV MMA reads.
+// TMEM columns: [0,128) S even, [128,256) S odd, [256,384) O.
+// Output: O [B,S,Hq,D] bf16 and LSE [B,Hq,S] fp32 (natural log), which the backward kernels consume.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "sm100_ptx.cuh"
+#include "tma_utils.h"
+
+namespace fa100 {
+
+using namespace sm100;
+
+constexpr int BM = 128;          // query rows per CTA
+constexpr int BN = 128;          // keys per block
+constexpr int D = 128;           // head dim
+constexpr int TILE_BYTES = 128 * 128 * 2;     // one [128 x 128] bf16 tile = two 16 KB swizzle chunks
+constexpr int CHUNK_BYTES = 128 * 64 * 2;     // [128 rows x 64 cols] bf16
+constexpr int KV_STAGES = 2;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = TILE_BYTES /*Q / O staging*/ + 2 * KV_STAGES * TILE_BYTES /*K,V*/ + TILE_BYTES /*P*/ + 1024 + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;
+
+struct Params {
+  int B, S, Hq, Hk;
+  int num_q_blocks;
+  int window;            // 0 = none; otherwise keys with k <= q - window are masked
+  float scale_log2;      // softmax scale * log2(e)
+  float* lse;            // [B, Hq, S]
+};
+
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kk) {
+  // K-major [128 rows x 128 cols] tile stored as two [128 x 64] swizzle chunks; kk = 16-column step (0..7)
+  return make_smem_desc_sw128(tile_addr + (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kk) {
+  // the same physical tile read as an MN-major operand: rows are the K index, the two 64-column chunks are N groups
+  return make_smem_desc_sw128(tile_addr + kk * (16 * 128), CHUNK_BYTES, 1024);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                 const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;
+  uint8_t* sP = sV + KV_STAGES * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE_BYTES);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // [2]
+  uint64_t* k_empty = bars + 3;            // [2]
+  uint64_t* v_full = bars + 5;             // [2]
+  uint64_t* v_empty = bars + 7;            // [2]
+  uint64_t* s_full = bars + 9;             // [2]
+  uint64_t* s_empty = bars + 11;           // [2]
+  uint64_t* p_full = bars + 13;            // 1
+  uint64_t* pv_done = bars + 14;           // 1
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+
+  // heavy (late) query blocks first: better tail behaviour under causal masking
+  const int q_blk = p.num_q_blocks - 1 - (int)blockIdx.x;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int kv_head = head / (p.Hq / p.Hk);
+  const int q0 = q_blk * BM;
+  int j_lo = 0;
+  if (p.window > 0) j_lo = max(0, (q0 - p.window + 1) / BN);
+  const int j_hi = q_blk;                                  // inclusive (diagonal block)
+  const int n_blocks = j_hi - j_lo + 1;
+  const int row_base = batch * p.S;                        // row of token 0 of this batch in the [B*S, H*D] views
+
+  if (warp_idx == 0 && elect_one()) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_o);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+    }
+    mbar_init(p_full, 1);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc<1>(tmem_ptr, 512);
+    tmem_relinquish<1>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp_idx == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tma_q, q_full, head * D, row_base + q0);
+      tma_load_2d(sQ + CHUNK_BYTES, &tma_q, q_full, head * D + 64, row_base + q0);
+      for (int i = 0; i < n_blocks; ++i) {
+        const int j = j_lo + i, st = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_2d(sK + st * TILE_BYTES, &tma_k, &k_full[st], kv_head * D, row_base + j * BN);
+        tma_load_2d(sK + st * TILE_BYTES + CHUNK_BYTES, &tma_k, &k_full[st], kv_head * D + 64, row_base + j * BN);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        tma_load_2d(sV + st * TILE_BYTES, &tma_v, &v_full[st], kv_head * D, row_base + j * BN);
+        tma_load_2d(sV + st * TILE_BYTES + CHUNK_BYTES, &tma_v, &v_full[st], kv_head * D + 64, row_base + j * BN);
+      }
+    }
+  } else if (warp_idx == 1) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BN, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, false, true);
+    const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+    auto issue_qk = [&](int i) {
+      const int st = i & 1;
+      mbar_wait(&k_full[st], (i >> 1) & 1);
+      mbar_wait(&s_empty[st], ((i >> 1) & 1) ^ 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t k_addr = smem_u32(sK + st * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16<1>(tmem_base + st * BN, desc_kmajor(q_addr, kk), desc_kmajor(k_addr, kk), idesc_qk, kk != 0);
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int i = 0; i < n_blocks; ++i) {
+      if (i + 1 < n_blocks) issue_qk(i + 1);
+      const int st = i & 1;
+      mbar_wait(p_full, i & 1);
+      mbar_wait(&v_full[st], (i >> 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t v_addr = smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk)
+          umma_f16<1>(tmem_o, desc_kmajor(p_addr, kk), desc_mnmajor(v_addr, kk), idesc_pv, (i | kk) != 0);
+        umma_commit(pv_done);
+        umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const uint32_t q = warp_idx & 3;
+    const uint32_t row = q * 32 + lane;
+    const uint32_t lane_off = (q * 32u) << 16;
+    const int q_pos = q0 + (int)row;
+    float m_used = -INFINITY, l = 0.f;
+    for (int i = 0; i < n_blocks; ++i) {
+      const int j = j_lo + i, st = i & 1;
+      mbar_wait(&s_full[st], (i >> 1) & 1);
+      tcgen05_fence_after();
+      float s[BN];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + st * BN + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) sr[c * 32 + t] = v[t];
+        }
+      }
+      // the score buffer may now be overwritten by QK_{i+2}
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      const int k0 = j * BN;
+      const bool need_mask = (j == j_hi) || (p.window > 0 && k0 <= q_pos - p.window);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < BN; ++t) {
+        float v = s[t] * p.scale_log2;
+        if (need_mask) {
+          const int kpos = k0 + t;
+          if (kpos > q_pos || (p.window > 0 && kpos <= q_pos - p.window)) v = -INFINITY;
+        }
+        s[t] = v;
+        mx = fmaxf(mx, v);
+      }
+      const float m_new = fmaxf(m_used, mx);
+      // PV_{i-1} must have retired before P is overwritten / O is touched
+      if (i > 0) mbar_wait(pv_done, (i - 1) & 1);
+      const bool grow = (m_new - m_used) > RESCALE_THRESHOLD;     // also true on the first block (m_used = -inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        const float alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
+        l *= alpha;
+        m_used = m_new;
+        if (i > 0) {
+          tcgen05_fence_after();
+#pragma unroll
+          for (int c = 0; c < D / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_off + c * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * alpha);
+            tmem_st_32x32b_x16(tmem_o + lane_off + c * 16, v);
+          }
+          tmem_st_wait();
+          tcgen05_fence_before();
+        }
+      }
+      float rs = 0.f;
+      uint8_t* prow = sP + row * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < BN / 8; ++c16) {
+        float e[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          e[t] = exp2f(s[c16 * 8 + t] - m_used);
+          rs += e[t];
+        }
+        uint4 o;
+        o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+        o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+        const int chunk = c16 >> 3, j16 = c16 & 7;
+        *reinterpret_cast<uint4*>(prow + chunk * CHUNK_BYTES + ((j16 ^ (row & 7)) * 16)) = o;
+      }
+      l += rs;
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) mbar_arrive(p_full);
+    }
+    // ---------------- epilogue: O / l -> bf16 -> smem (Q buffer is free now) -> TMA store; LSE ----------------
+    mbar_wait(pv_done, (n_blocks - 1) & 1);
+    tcgen05_fence_after();
+    const float inv_l = 1.f / l;
+    uint8_t* orow = sQ + row * 128;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t8 = 0; t8 < 4; ++t8) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[t8 * 8 + 0]) * inv_l, __uint_as_float(v[t8 * 8 + 1]) * inv_l);
+        o.y = pack_bf16x2(__uint_as_float(v[t8 * 8 + 2]) * inv_l, __uint_as_float(v[t8 * 8 + 3]) * inv_l);
+        o.z = pack_bf16x2(__uint_as_float(v[t8 * 8 + 4]) * inv_l, __uint_as_float(v[t8 * 8 + 5]) * inv_l);
+        o.w = pack_bf16x2(__uint_as_float(v[t8 * 8 + 6]) * inv_l, __uint_as_float(v[t8 * 8 + 7]) * inv_l);
+        const int c16 = c * 4 + t8;                       // 16-byte column group 0..15
+        const int chunk = c16 >> 3, j16 = c16 & 7;
+        *reinterpret_cast<uint4*>(orow + chunk * CHUNK_BYTES + ((j16 ^ (row & 7)) * 16)) = o;
+      }
+    }
+    p.lse[((size_t)batch * p.Hq + head) * p.S + q_pos] = (m_used + log2f(l)) * 0.6931471805599453f;
+    tcgen05_fence_before();
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      tma_store_2d(&tma_o, sQ, head * D, row_base + q0);
+      tma_store_2d(&tma_o, sQ + CHUNK_BYTES, head * D + 64, row_base + q0);
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace fa100
+
+// q [B,S,Hq,128], k/v [B,S,Hk,128] bf16 with a contiguous last dim and row (token) pitch given by stride(1);
+// returns (out [B,S,Hq,128] bf16, lse [B,Hq,S] fp32)
+std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
+                                       int64_t window, double scale) {
+  using namespace fa100;
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.size(3) == D && k.size(3) == D && v.size(3) == D,
+              "flash_attn_fwd: head_dim must be 128");
+  TORCH_CHECK(causal, "flash_attn_fwd: only causal attention is implemented");
+  TORCH_CHECK(q.is_contiguous() && k.is_contiguous() && v.is_contiguous(), "flash_attn_fwd: contiguous [B,S,H,D] inputs required");
+  const int B = q.size(0), S = q.size(1), Hq = q.size(2), Hk = k.size(2);
+  TORCH_CHECK(k.size(1) == S && v.size(1) == S && v.size(2) == Hk && Hq % Hk == 0);
+  TORCH_CHECK(S % BM == 0, "flash_attn_fwd: sequence length must be a multiple of 128");
+  c10::cuda::CUDAGuard guard(q.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  auto out = at::empty_like(q);
+  auto lse = at::empty({B, Hq, S}, q.options().dtype(at::kFloat));
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tq = tma::make_2d(q.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, 128, 64);
+  CUtensorMap tk = tma::make_2d(k.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap to = tma::make_2d(out.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, 128, 64);
+  Params p;
+  p.B = B; p.S = S; p.Hq = Hq; p.Hk = Hk; p.num_q_blocks = S / BM; p.window = (int)window;
+  p.scale_log2 = (float)(scale * 1.4426950408889634);
+  p.lse = lse.data_ptr<float>();
+  static bool once = false;
+  if (!once) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    once = true;
+  }
+  dim3 grid(p.num_q_blocks, Hq, B);
+  flash_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {out, lse};
+}

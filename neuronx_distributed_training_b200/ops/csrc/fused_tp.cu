@@ -35,6 +35,7 @@ using namespace gemm100;
 constexpr int MAX_TP = 8;
 constexpr int RING_SLOTS = 7;
 constexpr int PIECE_BYTES = 32 * 1024;
+constexpr int STORE_LAG = 3;
 
 struct CommArgs {
   const uint8_t* x_local;          // my input shard [rows_per_rank, row_bytes] (ordinary device memory)
@@ -118,11 +119,14 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
         bulk_s2g(a.xg_peer[peer] + dst_off + (size_t)p * PIECE_BYTES, ring + s * PIECE_BYTES, piece_bytes(p));
       }
       tma_store_commit();
-      const int np = p + RING_SLOTS;
-      if (np < pieces) {
-        tma_store_wait_read<0>();   // smem slot drained by the stores before the next load lands in it
-        mbar_expect_tx(&full[s], piece_bytes(np));
-        bulk_g2s(ring + s * PIECE_BYTES, src + (size_t)np * PIECE_BYTES, piece_bytes(np), &full[s]);
+      // refill the slot of piece (p - LAG): its stores have finished reading shared memory once at most LAG newer
+      // store groups are still pending, so LAG stores and RING_SLOTS - LAG loads stay in flight
+      const int r = p - STORE_LAG;
+      if (r >= 0 && r + RING_SLOTS < pieces) {
+        tma_store_wait_read<STORE_LAG>();
+        const int rs = r % RING_SLOTS, np = r + RING_SLOTS;
+        mbar_expect_tx(&full[rs], piece_bytes(np));
+        bulk_g2s(ring + rs * PIECE_BYTES, src + (size_t)np * PIECE_BYTES, piece_bytes(np), &full[rs]);
       }
     }
     tma_store_wait<0>();           // every byte of this row-block has been written to every peer

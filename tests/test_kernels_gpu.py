@@ -142,3 +142,21 @@ def test_sq_norm(C):
     assert abs(ops.sq_norm(xa).item() - xa.double().pow(2).sum().item()) / xa.double().pow(2).sum().item() < 1e-5
     xb = torch.randn(777_776, device="cuda").bfloat16()
     assert abs(ops.sq_norm(xb).item() - xb.double().pow(2).sum().item()) / xb.double().pow(2).sum().item() < 1e-4
+
+
+@pytest.mark.parametrize("B,S,Hq,Hk,window", [(1, 256, 4, 1, 0), (2, 1024, 8, 2, 0), (1, 2048, 4, 4, 0), (1, 1024, 4, 1, 300)])
+def test_flash_attn_fwd(C, B, S, Hq, Hk, window):
+    from neuronx_distributed_training_b200 import ops
+    if not hasattr(C, "flash_attn_fwd"):
+        pytest.skip("flash attention kernel not built")
+    torch.manual_seed(0)
+    q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16()
+    k = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
+    v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
+    scale = 1.0 / math.sqrt(128)
+    out, lse = C.flash_attn_fwd(q, k, v, True, window, scale)
+    torch.cuda.synchronize()
+    ref, lse_ref = ops.attention_ref(q, k, v, causal=True, window=window or None, scale=scale, return_lse=True)
+    assert torch.isfinite(out.float()).all()
+    assert _rel_err(out, ref) < 1e-2, _rel_err(out, ref)
+    assert (lse - lse_ref).abs().max().item() < 2e-2
