@@ -37,6 +37,18 @@ constexpr int RING_SLOTS = 7;
 constexpr int PIECE_BYTES = 32 * 1024;
 constexpr int STORE_LAG = 3;
 
+// Optional timeline capture: when `g_dbg` is non-null every CTA records globaltimer stamps
+// [cta][0]=kernel start, [1]=handshake done, [2]=main phase done, [3]=kernel end.
+__device__ unsigned long long* g_dbg = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void dbg_stamp(int slot) {
+  if (g_dbg != nullptr && (threadIdx.x == 0 || (slot == 1 && threadIdx.x == 64))) g_dbg[blockIdx.x * 4 + slot] = gtimer();
+}
+
 struct CommArgs {
   const uint8_t* x_local;          // my input shard [rows_per_rank, row_bytes] (ordinary device memory)
   uint8_t* xg_peer[MAX_TP];        // every rank's gathered buffer [tp * rows_per_rank, row_bytes] (symmetric, this parity)
@@ -82,6 +94,7 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING_SLOTS * PIECE_BYTES);
   if (threadIdx.x != 0) return;
+  dbg_stamp(0);
   if (blockIdx.x == 0) send_handshake(a.hs_peer, a.rank, a.tp, a.epoch);
   for (int i = 0; i < RING_SLOTS; ++i) mbar_init(&full[i], 1);
   fence_barrier_init();
@@ -91,6 +104,7 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
     if (p == a.rank) continue;
     while ((int)ld_acquire_sys(a.hs_local + p) < (int)a.epoch - 1) __nanosleep(100);
   }
+  dbg_stamp(1);
   const int blocks_per_rank = a.rows_per_rank / 128;
   const size_t block_bytes = (size_t)128 * a.row_bytes;
   const int pieces = (int)((block_bytes + PIECE_BYTES - 1) / PIECE_BYTES);
@@ -138,6 +152,7 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
       st_release_sys(a.flags_peer[peer] + blk, a.epoch);
     }
   }
+  dbg_stamp(3);
 }
 
 template <bool A_MN, bool B_MN, int OUT>
@@ -151,8 +166,10 @@ ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   const int bpr = comm.rows_per_rank / 128;
   AgGate gate{comm.flags, comm.epoch, mode, comm.rank * bpr, (comm.rank + 1) * bpr};
+  dbg_stamp(0);
   gemm_body<A_MN, B_MN, OUT, AgGate>(&tma_a, &tma_b, &tma_c, p, smem_raw, gate, (int)blockIdx.x - comm.num_comm_ctas,
                                      (int)gridDim.x - comm.num_comm_ctas);
+  dbg_stamp(3);
 }
 
 // pure all-gather (same comm CTAs, no GEMM): used where the gathered tensor is needed on its own
@@ -193,6 +210,7 @@ struct RsGate {
     if (threadIdx.x == 64) {
       for (int p = 0; p < a.tp; ++p)
         while (ld_acquire_sys(a.hs_local + p) < a.epoch) __nanosleep(100);
+      dbg_stamp(1);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
@@ -219,7 +237,9 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (blockIdx.x == 0 && threadIdx.x == 0) send_handshake(rs.hs_peer, rs.rank, rs.tp, rs.epoch);
   RsGate gate{rs, maps.m};
   const CUtensorMap& tma_c = maps.m[0];
+  dbg_stamp(0);
   gemm_body<false, B_MN, OUT_BF16_PEER, RsGate>(&tma_a, &tma_b, &tma_c, p, smem_raw, gate, blockIdx.x, gridDim.x);
+  dbg_stamp(2);
   // ---------------- reduce phase: sum the TP partial slabs of my rows ----------------
   const int bpr = rs.rows_per_rank / 128;
   const int n_chunks = (rs.N + 255) / 256;
@@ -255,6 +275,7 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     __syncthreads();
   }
+  dbg_stamp(3);
 }
 
 template <class K>
@@ -412,4 +433,10 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   };
   if (b_kmajor) run(gemm_rs_kernel<false>); else run(gemm_rs_kernel<true>);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// debug: point the in-kernel timeline capture at `buf` ([num_ctas, 4] int64) or disable it with an empty tensor
+void fused_tp_set_debug(at::Tensor buf) {
+  unsigned long long* p = buf.numel() ? reinterpret_cast<unsigned long long*>(buf.data_ptr()) : nullptr;
+  C10_CUDA_CHECK(cudaMemcpyToSymbol(fused::g_dbg, &p, sizeof(p)));
 }

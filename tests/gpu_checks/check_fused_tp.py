@@ -70,6 +70,27 @@ res["ag_wgrad_ms"] = {"fused": t_f, "nccl+cublas": t_b}
 if rank == 0: print(f"AG-wgrad rel_err={e:.2e} fused {t_f:.3f} ms vs nccl+cublas {t_b:.3f} ms", flush=True)
 xg = ftp.all_gather(x); torch.cuda.synchronize()
 res["ag_only_err"] = rel(xg, ag(x))
+# ---- in-kernel timelines (globaltimer stamps per CTA) ----
+if os.environ.get("FUSED_TIMELINE", "1") == "1":
+    C = ops.C()
+    dbg = torch.zeros(148, 4, dtype=torch.int64, device=dev)
+    def timeline(name, fn):
+        fn(); torch.cuda.synchronize(); dist.barrier()
+        dbg.zero_(); C.fused_tp_set_debug(dbg)
+        fn(); torch.cuda.synchronize()
+        C.fused_tp_set_debug(torch.empty(0, dtype=torch.int64, device=dev))
+        d = dbg.cpu()
+        t0 = d[:, 0][d[:, 0] > 0].min().item()
+        def stat(col):
+            v = d[:, col][d[:, col] > 0]
+            return (None if v.numel() == 0 else (round((v.min().item() - t0) / 1e3, 1), round((v.max().item() - t0) / 1e3, 1)))
+        if rank == 0:
+            print(f"TIMELINE {name}: start..{stat(0)} hs_done {stat(1)} main_done {stat(2)} end {stat(3)} (us, min/max over CTAs)", flush=True)
+    x_ = (torch.randn(m, H, device=dev) * 0.5).bfloat16(); w_ = (torch.randn(6144 // tp, H, device=dev) * 0.05).bfloat16()
+    timeline("ag_gemm_qkv", lambda: ftp.all_gather_gemm(x_, w_))
+    a_ = (torch.randn(S, 4096 // tp, device=dev) * 0.5).bfloat16(); wo_ = (torch.randn(H, 4096 // tp, device=dev) * 0.05).bfloat16()
+    timeline("gemm_rs_oproj", lambda: ftp.gemm_reduce_scatter(a_, wo_))
+    timeline("ag_wgrad", lambda: ftp.all_gather_wgrad(dy, x, mg, True))
 ok = all(v < 2e-2 for k, v in res.items() if k.endswith("_err"))
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
