@@ -232,6 +232,15 @@ class LlamaAttention(nn.Module):
 
     def forward(self, hidden: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
         # hidden: [S_local, B, H]
+        if self.qkv_mode == "gqa" and self.config.fuse_qkv and not self.use_ring and \
+                type(self.qkv_proj).__name__ == "GQAQKVColumnParallelLinear":
+            # one GEMM, then one fused kernel: split + RoPE + [S,B]->[B,S] layout, no intermediate copies
+            packed = self.qkv_proj.forward_packed(hidden)
+            S, B = packed.shape[0], packed.shape[1]
+            q, k, v = ops.qkv_rope_split(packed, cos, sin, self.local_q_heads, self.local_kv_heads, self.head_dim)
+            o = self.core_attn(q, k, v)
+            o = o.transpose(0, 1).reshape(S, B, self.local_q_heads * self.head_dim)
+            return self.o_proj(o)
         if self.qkv_mode == "gqa":
             q, k, v = self.qkv_proj(hidden)
         elif self.qkv_mode == "fused":

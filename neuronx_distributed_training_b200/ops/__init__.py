@@ -217,6 +217,39 @@ def rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor)
     return rope_ref(q, cos, sin), rope_ref(k, cos, sin)
 
 
+class _QKVRopeSplitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, cos, sin, B, S, Hq, Hk):
+        ctx.save_for_backward(cos, sin)
+        _count()
+        q, k, v = C().qkv_rope_split_fwd(packed, cos, sin, B, S, Hq, Hk)
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        cos, sin = ctx.saved_tensors
+        _count()
+        return C().qkv_rope_split_bwd(dq.contiguous(), dk.contiguous(), dv.contiguous(), cos, sin), None, None, None, None, None, None
+
+
+def qkv_rope_split(packed: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, num_q_heads: int, num_kv_heads: int,
+                   head_dim: int):
+    """packed [S, B, (Hq+2Hk)*D] (sequence first) -> rotated q [B,S,Hq,D], k [B,S,Hk,D] and v [B,S,Hk,D], contiguous.
+    One fused pass replaces split + 3x .contiguous() + RoPE + the [S,B]->[B,S] transpose."""
+    S, B = packed.shape[0], packed.shape[1]
+    if _use_native(packed) and packed.dtype == torch.bfloat16 and head_dim % 16 == 0 and cos.dim() == 2:
+        p2 = packed.reshape(S * B, -1)
+        p2 = p2 if p2.is_contiguous() else p2.contiguous()
+        return _QKVRopeSplitFn.apply(p2, cos.contiguous(), sin.contiguous(), B, S, num_q_heads, num_kv_heads)
+    qd, kd = num_q_heads * head_dim, num_kv_heads * head_dim
+    q, k, v = torch.split(packed, [qd, kd, kd], dim=-1)
+    q = q.reshape(S, B, num_q_heads, head_dim).transpose(0, 1)
+    k = k.reshape(S, B, num_kv_heads, head_dim).transpose(0, 1)
+    v = v.reshape(S, B, num_kv_heads, head_dim).transpose(0, 1)
+    q, k = rope(q, k, cos, sin)
+    return q, k, v
+
+
 # =====================================================================================================
 # SwiGLU on fused gate||up  ([..., 2I] -> [..., I])
 # =====================================================================================================
@@ -354,6 +387,35 @@ def flash_attention(q, k, v, causal: bool = True, window: Optional[int] = None, 
 def cross_entropy_ref(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
     """per-token loss [T] (0 where ignored)."""
     return F.cross_entropy(logits.float(), labels, ignore_index=ignore_index, reduction="none")
+
+
+def native_ce_available(logits: torch.Tensor) -> bool:
+    return (_use_native(logits) and logits.dtype == torch.bfloat16 and logits.dim() == 2 and logits.is_contiguous()
+            and logits.shape[1] % 8 == 0 and hasattr(C(), "ce_stats"))
+
+
+def cross_entropy_fused_(logits: torch.Tensor, labels: torch.Tensor, vocab_start: int, group, ignore_index: int = -100,
+                         want_grad: bool = True):
+    """Vocab-parallel CE on bf16 ``logits`` [T, V_local].  Returns (per-token loss [T] fp32, d(logits) or None);
+    when ``want_grad`` the logits buffer is overwritten in place with (softmax - onehot) (0 on ignored rows)."""
+    import torch.distributed as dist
+    from ..parallel import state as ps
+    _count(2 if want_grad else 1)
+    lmax, lsum, tgt = C().ce_stats(logits, labels, int(vocab_start))
+    if ps.group_size(group) > 1:
+        gmax = lmax.clone()
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+        packed = torch.stack([lsum * torch.exp(lmax - gmax), tgt])
+        dist.all_reduce(packed, group=group)
+        gsum, tgt = packed[0].contiguous(), packed[1]
+    else:
+        gmax, gsum = lmax, lsum
+    ignore = labels == ignore_index
+    loss = (gsum.log() + gmax - tgt).masked_fill(ignore, 0.0)
+    if not want_grad:
+        return loss, None
+    C().ce_grad_(logits, labels, int(vocab_start), gmax, gsum, int(ignore_index))
+    return loss, logits
 
 
 # =====================================================================================================

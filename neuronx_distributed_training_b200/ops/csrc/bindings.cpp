@@ -12,15 +12,22 @@ void adamw_flat(at::Tensor master, at::Tensor param, const at::Tensor& grad, at:
                 const at::Tensor& decay_mask, double lr, double b1, double b2, double eps, double wd, double bc1,
                 double bc2, const at::Tensor& grad_scale, bool sr, int64_t seed);
 at::Tensor sq_norm(const at::Tensor& x);
+std::vector<at::Tensor> ce_stats(const at::Tensor& logits, const at::Tensor& labels, int64_t vocab_start);
+void ce_grad_(at::Tensor logits, const at::Tensor& labels, int64_t vocab_start, const at::Tensor& gmax, const at::Tensor& gsum,
+              int64_t ignore_index);
+std::vector<at::Tensor> qkv_rope_split_fwd(const at::Tensor& packed, const at::Tensor& cos, const at::Tensor& sin,
+                                           int64_t B, int64_t S, int64_t Hq, int64_t Hk);
+at::Tensor qkv_rope_split_bwd(const at::Tensor& dq, const at::Tensor& dk, const at::Tensor& dv, const at::Tensor& cos,
+                              const at::Tensor& sin);
 std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
                                        int64_t window, double scale);
 void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
              std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
              std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
-             bool accumulate, int64_t num_comm_ctas);
+             bool accumulate, int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push);
 void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer,
              int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp,
-             int64_t num_comm_ctas);
+             int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push);
 void fused_tp_set_debug(at::Tensor buf);
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
@@ -35,6 +42,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("adamw_flat", &adamw_flat);
   m.def("sq_norm", &sq_norm);
+  m.def("ce_stats", &ce_stats);
+  m.def("ce_grad_", &ce_grad_);
+  m.def("qkv_rope_split_fwd", &qkv_rope_split_fwd);
+  m.def("qkv_rope_split_bwd", &qkv_rope_split_bwd);
   m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 causal flash attention forward (head_dim 128)");
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");
   m.def("ag_only", &ag_only);

@@ -329,6 +329,128 @@ __global__ void sq_norm_kernel(const T* __restrict__ x, size_t n, float* __restr
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused QKV split + RoPE + layout change.  Input: the packed projection output [S*B, (Hq+2Hk)*D] in sequence-first
+// token order (t = s*B + b).  Outputs: q [B,S,Hq,D], k [B,S,Hk,D] (rotated) and v [B,S,Hk,D], contiguous - exactly what
+// the attention kernel consumes, so no slicing / .contiguous() copies remain.  `conj` = backward (inverse rotation,
+// gathers dq/dk/dv back into the packed layout).
+// ------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void qkv_rope_split_kernel(__nv_bfloat16* __restrict__ packed, __nv_bfloat16* __restrict__ q,
+                                      __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v,
+                                      const float* __restrict__ cs, const float* __restrict__ sn, int B, int S, int Hq,
+                                      int Hk, int D, size_t total_units) {
+  const int half = D / 2, upb = half / 8, nheads = Hq + 2 * Hk;
+  const size_t W = (size_t)nheads * D;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < total_units; u += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(u % upb);
+    const size_t hl = u / upb;
+    const int hidx = (int)(hl % nheads);
+    const size_t t = hl / nheads;              // packed token index = s*B + b
+    const int sidx = (int)(t / B), b = (int)(t % B);
+    __nv_bfloat16* pk = packed + t * W + (size_t)hidx * D + j * 8;
+    __nv_bfloat16* dst;
+    bool rot = true;
+    const size_t tok = (size_t)b * S + sidx;
+    if (hidx < Hq) dst = q + (tok * Hq + hidx) * D + j * 8;
+    else if (hidx < Hq + Hk) dst = k + (tok * Hk + (hidx - Hq)) * D + j * 8;
+    else { dst = v + (tok * Hk + (hidx - Hq - Hk)) * D + j * 8; rot = false; }
+    float a[8], bb[8], o1[8], o2[8];
+    if (!BWD) { load8<__nv_bfloat16>(pk, a); load8<__nv_bfloat16>(pk + half, bb); }
+    else { load8<__nv_bfloat16>(dst, a); load8<__nv_bfloat16>(dst + half, bb); }
+    if (rot) {
+      float c1[8], c2[8], s1[8], s2[8];
+      load8<float>(cs + (size_t)sidx * D + j * 8, c1);
+      load8<float>(cs + (size_t)sidx * D + half + j * 8, c2);
+      load8<float>(sn + (size_t)sidx * D + j * 8, s1);
+      load8<float>(sn + (size_t)sidx * D + half + j * 8, s2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!BWD) { o1[i] = a[i] * c1[i] - bb[i] * s1[i]; o2[i] = bb[i] * c2[i] + a[i] * s2[i]; }
+        else { o1[i] = a[i] * c1[i] + bb[i] * s2[i]; o2[i] = bb[i] * c2[i] - a[i] * s1[i]; }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o1[i] = a[i]; o2[i] = bb[i]; }
+    }
+    if (!BWD) { store8<__nv_bfloat16>(dst, o1); store8<__nv_bfloat16>(dst + half, o2); }
+    else { store8<__nv_bfloat16>(pk, o1); store8<__nv_bfloat16>(pk + half, o2); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vocab-parallel cross entropy on bf16 logits, two fused passes (one CTA per token row):
+//   ce_stats : online max / sum-exp (relative to the local max) / target logit of the local vocab shard
+//   ce_grad  : logits <- (softmax - onehot) * mask, written IN PLACE as bf16 (the logits buffer becomes dlogits)
+// Between the passes the host combines the per-row statistics across the TP group (max, then sums).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ce_stats_kernel(const __nv_bfloat16* __restrict__ logits,
+                                                       const int64_t* __restrict__ labels, int T, int V,
+                                                       int64_t vocab_start, float* __restrict__ out_max,
+                                                       float* __restrict__ out_sum, float* __restrict__ out_tgt) {
+  __shared__ float sm[32];
+  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+    const __nv_bfloat16* lr = logits + (size_t)row * V;
+    float m = -INFINITY, ssum = 0.f;
+    for (int c = threadIdx.x * 8; c < V; c += 256 * 8) {
+      float f[8];
+      load8<__nv_bfloat16>(lr + c, f);
+      float cm = f[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) cm = fmaxf(cm, f[i]);
+      const float nm = fmaxf(m, cm);
+      float add = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) add += __expf(f[i] - nm);
+      ssum = ssum * __expf(m - nm) + add;
+      m = nm;
+    }
+    // block-combine (max, sum) pairs
+    float gm = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    __shared__ float smax[8];
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = gm;
+    __syncthreads();
+    gm = smax[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) gm = fmaxf(gm, smax[i]);
+    const float total = block_sum<256>(m == -INFINITY ? 0.f : ssum * __expf(m - gm), sm);
+    if (threadIdx.x == 0) {
+      out_max[row] = gm;
+      out_sum[row] = total;
+      const int64_t lab = labels[row] - vocab_start;
+      out_tgt[row] = (lab >= 0 && lab < V) ? __bfloat162float(lr[lab]) : 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) ce_grad_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                      int T, int V, int64_t vocab_start, const float* __restrict__ gmax,
+                                                      const float* __restrict__ gsum, int64_t ignore_index) {
+  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+    __nv_bfloat16* lr = logits + (size_t)row * V;
+    const int64_t lab_raw = labels[row];
+    const bool ignore = lab_raw == ignore_index;
+    const int64_t lab = lab_raw - vocab_start;
+    const float m = gmax[row], inv = 1.f / gsum[row];
+    for (int c = threadIdx.x * 8; c < V; c += 256 * 8) {
+      float f[8];
+      if (ignore) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+      } else {
+        load8<__nv_bfloat16>(lr + c, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __expf(f[i] - m) * inv;
+        if (lab >= c && lab < c + 8) f[lab - c] -= 1.f;
+      }
+      store8<__nv_bfloat16>(lr + c, f);
+    }
+  }
+}
+
 inline int grid_for(size_t units, int threads, int per_sm) {
   size_t blocks = (units + threads - 1) / threads;
   size_t cap = (size_t)at::cuda::getCurrentDeviceProperties()->multiProcessorCount * per_sm;
@@ -493,4 +615,65 @@ at::Tensor sq_norm(const at::Tensor& x) {
     TORCH_CHECK(false, "sq_norm: bf16/fp32 only");
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return out;
+}
+
+// packed [S*B, (Hq+2Hk)*D] (sequence-first tokens) -> q [B,S,Hq,D], k [B,S,Hk,D], v [B,S,Hk,D]
+std::vector<at::Tensor> qkv_rope_split_fwd(const at::Tensor& packed, const at::Tensor& cos, const at::Tensor& sin,
+                                           int64_t B, int64_t S, int64_t Hq, int64_t Hk) {
+  TORCH_CHECK(packed.is_cuda() && packed.is_contiguous() && packed.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(cos.is_contiguous() && sin.is_contiguous() && cos.scalar_type() == at::kFloat && cos.size(0) == S);
+  const int D = cos.size(1);
+  TORCH_CHECK(D % 16 == 0 && packed.numel() == B * S * (Hq + 2 * Hk) * D, "qkv_rope_split: shape mismatch");
+  c10::cuda::CUDAGuard guard(packed.device());
+  auto q = at::empty({B, S, Hq, D}, packed.options());
+  auto k = at::empty({B, S, Hk, D}, packed.options());
+  auto v = at::empty({B, S, Hk, D}, packed.options());
+  const size_t units = (size_t)B * S * (Hq + 2 * Hk) * (D / 16);
+  qkv_rope_split_kernel<false><<<grid_for(units, 256, 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      (__nv_bfloat16*)packed.data_ptr(), (__nv_bfloat16*)q.data_ptr(), (__nv_bfloat16*)k.data_ptr(),
+      (__nv_bfloat16*)v.data_ptr(), cos.data_ptr<float>(), sin.data_ptr<float>(), B, S, Hq, Hk, D, units);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {q, k, v};
+}
+
+at::Tensor qkv_rope_split_bwd(const at::Tensor& dq, const at::Tensor& dk, const at::Tensor& dv, const at::Tensor& cos,
+                              const at::Tensor& sin) {
+  TORCH_CHECK(dq.is_cuda() && dq.is_contiguous() && dk.is_contiguous() && dv.is_contiguous());
+  const int B = dq.size(0), S = dq.size(1), Hq = dq.size(2), D = dq.size(3), Hk = dk.size(2);
+  c10::cuda::CUDAGuard guard(dq.device());
+  auto packed = at::empty({(int64_t)S * B, (int64_t)(Hq + 2 * Hk) * D}, dq.options());
+  const size_t units = (size_t)B * S * (Hq + 2 * Hk) * (D / 16);
+  qkv_rope_split_kernel<true><<<grid_for(units, 256, 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      (__nv_bfloat16*)packed.data_ptr(), (__nv_bfloat16*)dq.data_ptr(), (__nv_bfloat16*)dk.data_ptr(),
+      (__nv_bfloat16*)dv.data_ptr(), cos.data_ptr<float>(), sin.data_ptr<float>(), B, S, Hq, Hk, D, units);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return packed;
+}
+
+std::vector<at::Tensor> ce_stats(const at::Tensor& logits, const at::Tensor& labels, int64_t vocab_start) {
+  TORCH_CHECK(logits.is_cuda() && logits.is_contiguous() && logits.scalar_type() == at::kBFloat16 && logits.dim() == 2);
+  TORCH_CHECK(labels.is_contiguous() && labels.scalar_type() == at::kLong && labels.numel() == logits.size(0));
+  const int T = logits.size(0), V = logits.size(1);
+  TORCH_CHECK(V % 8 == 0);
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto o = logits.options().dtype(at::kFloat);
+  auto mx = at::empty({T}, o), sm = at::empty({T}, o), tg = at::empty({T}, o);
+  const int grid = std::min(T, at::cuda::getCurrentDeviceProperties()->multiProcessorCount * 8);
+  ce_stats_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>((const __nv_bfloat16*)logits.data_ptr(), labels.data_ptr<int64_t>(),
+                                                                      T, V, vocab_start, mx.data_ptr<float>(), sm.data_ptr<float>(),
+                                                                      tg.data_ptr<float>());
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  return {mx, sm, tg};
+}
+
+void ce_grad_(at::Tensor logits, const at::Tensor& labels, int64_t vocab_start, const at::Tensor& gmax, const at::Tensor& gsum,
+              int64_t ignore_index) {
+  TORCH_CHECK(logits.is_cuda() && logits.is_contiguous() && logits.scalar_type() == at::kBFloat16 && logits.dim() == 2);
+  TORCH_CHECK(gmax.is_contiguous() && gsum.is_contiguous() && gmax.scalar_type() == at::kFloat && gsum.scalar_type() == at::kFloat);
+  const int T = logits.size(0), V = logits.size(1);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int grid = std::min(T, at::cuda::getCurrentDeviceProperties()->multiProcessorCount * 8);
+  ce_grad_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>((__nv_bfloat16*)logits.data_ptr(), labels.data_ptr<int64_t>(), T, V,
+                                                                     vocab_start, gmax.data_ptr<float>(), gsum.data_ptr<float>(), ignore_index);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

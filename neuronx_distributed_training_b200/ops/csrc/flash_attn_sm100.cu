@@ -222,6 +222,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           tcgen05_fence_before();
         }
       }
+      // a row can still be fully masked so far (sliding window): keep exp2(-inf - m) = 0 instead of NaN
+      const float m_exp = (m_used == -INFINITY) ? 0.f : m_used;
       float rs = 0.f;
       uint8_t* prow = sP + row * 128;
 #pragma unroll
@@ -229,7 +231,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         float e[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          e[t] = exp2f(s[c16 * 8 + t] - m_used);
+          e[t] = exp2f(s[c16 * 8 + t] - m_exp);
           rs += e[t];
         }
         uint4 o;

@@ -56,8 +56,10 @@ struct CommArgs {
   uint32_t* hs_peer[MAX_TP];       // every rank's handshake array
   uint32_t* hs_local;              // my handshake array [tp]
   uint32_t* flags;                 // my ready flags (== flags_peer[rank])
+  const uint8_t* x_peer[MAX_TP];   // pull mode: every rank's shard staged in its symmetric buffer (this parity)
   uint32_t epoch;
   int rank, tp, rows_per_rank, row_bytes, num_comm_ctas;
+  int push;                        // 1: owners push their shard to everybody; 0: consumers pull the peers' shards
 };
 
 struct AgGate {
@@ -67,7 +69,7 @@ struct AgGate {
   int local_lo, local_hi;   // row-blocks of my own shard: already in place, never waited on
   __device__ __forceinline__ void wait_flag(int blk) const {
     if (blk >= local_lo && blk < local_hi) return;
-    while (ld_acquire_sys(flags + blk) != epoch) __nanosleep(64);
+    while ((int)(ld_acquire_sys(flags + blk) - epoch) < 0) __nanosleep(64);   // flags only grow (epochs)
     fence_proxy_async_all();   // generic-proxy acquire -> subsequent async-proxy (TMA) reads
   }
   __device__ __forceinline__ void wait_m(int m_blk) const {
@@ -90,7 +92,7 @@ __device__ __forceinline__ void send_handshake(uint32_t* const* hs_peer, int ran
 // buffer.  Remote *stores* are posted (fire and forget), so the transfer runs at link rate instead of being bound by
 // NVLink round-trip latency x bytes in flight as a pull (remote loads) would be.  After a 128-row block has been
 // written everywhere, its ready flag is released (st.release.sys) on every peer.
-__device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
+__device__ void comm_cta_push(const CommArgs& a, uint8_t* smem_raw) {
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING_SLOTS * PIECE_BYTES);
   if (threadIdx.x != 0) return;
@@ -155,6 +157,71 @@ __device__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
   dbg_stamp(3);
 }
 
+// PULL-mode all-gather: every comm CTA copies peers' staged shards into MY gathered buffer
+// (peer HBM --bulk--> smem ring --bulk--> local), publishing a local ready flag per 128-row block.
+__device__ void comm_cta_pull(const CommArgs& a, uint8_t* smem_raw) {
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING_SLOTS * PIECE_BYTES);
+  if (threadIdx.x != 0) return;
+  dbg_stamp(0);
+  if (blockIdx.x == 0) send_handshake(a.hs_peer, a.rank, a.tp, a.epoch);
+  for (int i = 0; i < RING_SLOTS; ++i) mbar_init(&full[i], 1);
+  fence_barrier_init();
+  const int blocks_per_rank = a.rows_per_rank / 128;
+  const int total_blocks = blocks_per_rank * a.tp;
+  const size_t block_bytes = (size_t)128 * a.row_bytes;
+  const int pieces = (int)((block_bytes + PIECE_BYTES - 1) / PIECE_BYTES);
+  uint32_t slot_phase = 0;
+  int waited_rank_mask = 0;
+  uint8_t* xg = a.xg_peer[a.rank];
+  bool stamped = false;
+  for (int idx = blockIdx.x; idx < total_blocks; idx += a.num_comm_ctas) {
+    int blk = idx + a.rank * blocks_per_rank;
+    if (blk >= total_blocks) blk -= total_blocks;
+    const int src_rank = blk / blocks_per_rank;
+    if (src_rank == a.rank) continue;
+    if (!((waited_rank_mask >> src_rank) & 1)) {
+      while ((int)(ld_acquire_sys(a.hs_local + src_rank) - a.epoch) < 0) __nanosleep(100);
+      waited_rank_mask |= 1 << src_rank;
+    }
+    if (!stamped) { dbg_stamp(1); stamped = true; }
+    const uint8_t* src = a.x_peer[src_rank] + (size_t)(blk - src_rank * blocks_per_rank) * block_bytes;
+    uint8_t* dst = xg + (size_t)blk * block_bytes;
+    auto piece_bytes = [&](int p) -> uint32_t {
+      const size_t off = (size_t)p * PIECE_BYTES;
+      return (uint32_t)min((size_t)PIECE_BYTES, block_bytes - off);
+    };
+    const int prime = min(pieces, RING_SLOTS);
+    for (int p = 0; p < prime; ++p) {
+      mbar_expect_tx(&full[p], piece_bytes(p));
+      bulk_g2s(ring + p * PIECE_BYTES, src + (size_t)p * PIECE_BYTES, piece_bytes(p), &full[p]);
+    }
+    for (int p = 0; p < pieces; ++p) {
+      const int s = p % RING_SLOTS;
+      mbar_wait(&full[s], (slot_phase >> s) & 1);
+      slot_phase ^= 1u << s;
+      bulk_s2g(dst + (size_t)p * PIECE_BYTES, ring + s * PIECE_BYTES, piece_bytes(p));
+      tma_store_commit();
+      const int r = p - STORE_LAG;
+      if (r >= 0 && r + RING_SLOTS < pieces) {
+        tma_store_wait_read<STORE_LAG>();
+        const int rs = r % RING_SLOTS, np = r + RING_SLOTS;
+        mbar_expect_tx(&full[rs], piece_bytes(np));
+        bulk_g2s(ring + rs * PIECE_BYTES, src + (size_t)np * PIECE_BYTES, piece_bytes(np), &full[rs]);
+      }
+    }
+    tma_store_wait<0>();
+    fence_proxy_async_all();
+    __threadfence();
+    st_release_sys(a.flags + blk, a.epoch);
+  }
+  dbg_stamp(3);
+}
+
+__device__ __forceinline__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
+  if (a.push) comm_cta_push(a, smem_raw); else comm_cta_pull(a, smem_raw);
+}
+
 template <bool A_MN, bool B_MN, int OUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -180,7 +247,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ag_only_kernel(const CommArgs 
   const int bpr = comm.rows_per_rank / 128;
   for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < bpr * comm.tp; blk += gridDim.x * blockDim.x) {
     if (blk / bpr == comm.rank) continue;
-    while (ld_acquire_sys(comm.flags + blk) != comm.epoch) __nanosleep(200);
+    while ((int)(ld_acquire_sys(comm.flags + blk) - comm.epoch) < 0) __nanosleep(200);
   }
 }
 
@@ -300,7 +367,7 @@ static void fill_ptrs(const std::vector<int64_t>& v, int tp, void** dst) {
 void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
              std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
              std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
-             bool accumulate, int64_t num_comm_ctas) {
+             bool accumulate, int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push) {
   using namespace fused;
   TORCH_CHECK(xg.is_cuda() && xg.is_contiguous() && xg.scalar_type() == at::kBFloat16 && xg.dim() == 2);
   TORCH_CHECK(tp >= 2 && tp <= MAX_TP);
@@ -315,13 +382,15 @@ void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::
   comm.x_local = reinterpret_cast<const uint8_t*>(x_local.data_ptr());
   fill_ptrs(xg_peer, tp, (void**)comm.xg_peer);
   fill_ptrs(flags_peer, tp, (void**)comm.flags_peer);
+  fill_ptrs(x_peer, tp, (void**)comm.x_peer);
+  comm.push = push ? 1 : 0;
   fill_ptrs(hs_peer, tp, (void**)comm.hs_peer);
   comm.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
   comm.flags = comm.flags_peer[rank];
   TORCH_CHECK(reinterpret_cast<uint8_t*>(xg.data_ptr()) == comm.xg_peer[rank], "xg must be my symmetric gathered buffer");
   comm.epoch = (uint32_t)epoch;
   comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
-  num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, rows_per_rank / 128));
+  num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, (push ? 1 : (tp - 1)) * (rows_per_rank / 128)));
   comm.num_comm_ctas = num_comm_ctas;
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   TORCH_CHECK(num_comm_ctas >= 1 && num_comm_ctas < sms);
@@ -364,7 +433,7 @@ void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::
 
 void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer,
              int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp,
-             int64_t num_comm_ctas) {
+             int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push) {
   using namespace fused;
   const int M_total = xg.size(0), Kx = xg.size(1);
   const int rows_per_rank = M_total / tp;
@@ -376,13 +445,15 @@ void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_p
   comm.x_local = reinterpret_cast<const uint8_t*>(x_local.data_ptr());
   fill_ptrs(xg_peer, tp, (void**)comm.xg_peer);
   fill_ptrs(flags_peer, tp, (void**)comm.flags_peer);
+  fill_ptrs(x_peer, tp, (void**)comm.x_peer);
+  comm.push = push ? 1 : 0;
   fill_ptrs(hs_peer, tp, (void**)comm.hs_peer);
   comm.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
   comm.flags = comm.flags_peer[rank];
   TORCH_CHECK(reinterpret_cast<uint8_t*>(xg.data_ptr()) == comm.xg_peer[rank], "xg must be my symmetric gathered buffer");
   comm.epoch = (uint32_t)epoch;
   comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
-  num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, rows_per_rank / 128));
+  num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, (push ? 1 : (tp - 1)) * (rows_per_rank / 128)));
   comm.num_comm_ctas = num_comm_ctas;
   set_smem(ag_only_kernel);
   ag_only_kernel<<<num_comm_ctas, NUM_THREADS, SMEM_BYTES, at::cuda::getCurrentCUDAStream()>>>(comm);

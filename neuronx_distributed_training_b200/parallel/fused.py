@@ -53,7 +53,11 @@ class FusedTP:
         self.max_gather_bytes = self.max_shard_bytes * self.tp
         self.max_stage_bytes = _align(max_stage_bytes)
         self.xg_off = [_DATA_OFF, _DATA_OFF + self.max_gather_bytes]
-        self.stage_off = [_DATA_OFF + 2 * self.max_gather_bytes, _DATA_OFF + 2 * self.max_gather_bytes + self.max_stage_bytes]
+        x0 = _DATA_OFF + 2 * self.max_gather_bytes
+        self.x_off = [x0, x0 + self.max_shard_bytes]           # pull mode: my shard staged where the peers can read it
+        s0 = x0 + 2 * self.max_shard_bytes
+        self.stage_off = [s0, s0 + self.max_stage_bytes]
+        self.push = os.environ.get("NXDT_AG_MODE", "pull") == "push"
         total = self.stage_off[1] + self.max_stage_bytes
         try:
             symm_mem.enable_symm_mem_for_group(self.group.group_name)
@@ -86,6 +90,10 @@ class FusedTP:
         off = self.xg_off[parity]
         xg = self.buf[off: off + nbytes].view(torch.bfloat16).view(m * self.tp, K)
         xg[self.rank * m:(self.rank + 1) * m].copy_(x2d)
+        if not self.push:
+            xo = self.x_off[parity]
+            self.buf[xo: xo + m * K * x2d.element_size()].view(torch.bfloat16).view(m, K).copy_(x2d)
+        self._x_peer = [p + self.x_off[parity] for p in self.base_ptrs]
         return xg, [p + off for p in self.base_ptrs], [p + _FLAG_OFF for p in self.base_ptrs]
 
     def supports(self, rows_local: int, *dims: int) -> bool:
@@ -95,7 +103,7 @@ class FusedTP:
     # peer handshake, so they win when the NVLink time is a sizeable fraction of the GEMM time) -----------------
     GEMM_FLOPS = 1.35e15          # sustained tcgen05 bf16 rate of gemm_sm100 on Llama shapes
     LINK_BPS = 6.0e11             # ~600 GB/s effective inbound/outbound per GPU
-    PER_CTA_BPS = 1.5e11          # one comm CTA: local bulk loads + posted remote bulk stores
+    PER_CTA_BPS = 1.0e11          # one comm CTA with the pipelined bulk-copy loop
 
     def _ratio(self, m_total: int, n: int, k: int, bytes_moved: float) -> float:
         return (bytes_moved / self.LINK_BPS) / max(2.0 * m_total * n * k / self.GEMM_FLOPS, 1e-9)
@@ -134,7 +142,7 @@ class FusedTP:
         ops._count()
         nc = self._comm_ctas(m * self.tp, N, K, m * (self.tp - 1) * K * 2)
         ops.C().ag_gemm(xg, x2d, w, out, out, xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank, self.tp,
-                        0, trans_b, False, nc)
+                        0, trans_b, False, nc, self._x_peer, self.push)
         # NOTE: the gathered view lives in the double-buffered workspace: consume it before the second next fused call
         return (out, xg) if return_gathered else out
 
@@ -148,7 +156,7 @@ class FusedTP:
         ops._count()
         nc = self._comm_ctas(dy2d.shape[1], K, m * self.tp, m * (self.tp - 1) * K * 2)
         ops.C().ag_gemm(xg, x2d, xg, out, dy2d.contiguous(), xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank,
-                        self.tp, 1, True, accumulate, nc)
+                        self.tp, 1, True, accumulate, nc, self._x_peer, self.push)
         return out
 
     def all_gather(self, x2d: torch.Tensor) -> torch.Tensor:
@@ -158,7 +166,8 @@ class FusedTP:
         xg, xg_peer, flags_peer = self._gather_buffer(x2d, par)
         hs_local, hs_peer = self._hs()
         ops._count()
-        ops.C().ag_only(xg, x2d, xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank, self.tp, self.num_comm_ctas)
+        ops.C().ag_only(xg, x2d, xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank, self.tp, self.num_comm_ctas,
+                        self._x_peer, self.push)
         return xg.clone()
 
     def gemm_reduce_scatter(self, a2d: torch.Tensor, w: torch.Tensor, trans_b: bool = True) -> torch.Tensor:

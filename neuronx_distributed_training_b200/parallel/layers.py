@@ -520,6 +520,12 @@ class GQAQKVColumnParallelLinear(nn.Module):
                 self.weight_k.copy_(ks.to(self.weight_k.dtype))
                 self.weight_v.copy_(vs.to(self.weight_v.dtype))
 
+    def forward_packed(self, x: torch.Tensor) -> torch.Tensor:
+        """the fused projection output ``[..., q_local + 2*kv_local]`` before it is split (fuse_qkv only)"""
+        assert self.fuse_qkv
+        return _ColumnParallelLinearFn.apply(x, self.weight_qkv, self.bias_qkv, self.group,
+                                             self.sequence_parallel_enabled, self.fused)
+
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         if self.fuse_qkv:
             y = _ColumnParallelLinearFn.apply(x, self.weight_qkv, self.bias_qkv, self.group,

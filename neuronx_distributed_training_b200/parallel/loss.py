@@ -147,6 +147,19 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
             e = min(T, s + chunk)
             h = hidden[s:e]
             logits = ops.gemm_nt(h, weight)
+            if ops.native_ce_available(logits):
+                # two fused passes on the bf16 logits; the buffer is turned into d(logits) in place
+                loss, dlog = ops.cross_entropy_fused_(logits, labels[s:e].contiguous(), _vocab_range(weight.shape[0], group)[0],
+                                                      group, ignore_index, need_grad)
+                loss_sum += loss.sum()
+                if per_tok is not None:
+                    per_tok[s:e] = loss
+                if need_grad:
+                    dh[s:e] = ops.gemm_nn(dlog, weight)
+                    if dw_acc is not None:
+                        ops.gemm_wgrad(dlog, h, out=dw_acc, accumulate=True)
+                del logits, dlog
+                continue
             loss, probs, tmask, local_t, ignore = _ce_stats(logits, labels[s:e], group, ignore_index)
             del logits
             loss_sum += loss.sum()

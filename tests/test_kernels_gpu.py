@@ -160,3 +160,41 @@ def test_flash_attn_fwd(C, B, S, Hq, Hk, window):
     assert torch.isfinite(out.float()).all()
     assert _rel_err(out, ref) < 1e-2, _rel_err(out, ref)
     assert (lse - lse_ref).abs().max().item() < 2e-2
+
+
+def test_qkv_rope_split(C):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    S, B, Hq, Hk, D = 256, 2, 8, 2, 128
+    packed = torch.randn(S, B, (Hq + 2 * Hk) * D, device="cuda").bfloat16().requires_grad_(True)
+    inv = 1.0 / (500000.0 ** (torch.arange(0, D, 2, device="cuda").float() / D))
+    emb = torch.cat([torch.outer(torch.arange(S, device="cuda").float(), inv)] * 2, -1)
+    cos, sin = emb.cos(), emb.sin()
+    q, k, v = ops.qkv_rope_split(packed, cos, sin, Hq, Hk, D)
+    assert q.shape == (B, S, Hq, D) and q.is_contiguous() and v.shape == (B, S, Hk, D)
+    gq, gk, gv = torch.randn_like(q), torch.randn_like(k), torch.randn_like(v)
+    torch.autograd.backward([q, k, v], [gq, gk, gv])
+    p2 = packed.detach().float().requires_grad_(True)
+    ops.set_backend("torch")
+    try:
+        q2, k2, v2 = ops.qkv_rope_split(p2, cos, sin, Hq, Hk, D)
+    finally:
+        ops.set_backend("auto")
+    torch.autograd.backward([q2, k2, v2], [gq.float(), gk.float(), gv.float()])
+    assert _rel_err(q, q2) < 1e-2 and _rel_err(k, k2) < 1e-2 and _rel_err(v, v2) < 1e-6
+    assert _rel_err(packed.grad, p2.grad) < 1e-2
+
+
+def test_fused_cross_entropy(C):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    T, V = 300, 128256
+    logits = (torch.randn(T, V, device="cuda") * 3).bfloat16()
+    labels = torch.randint(0, V, (T,), device="cuda"); labels[:7] = -100
+    ref_in = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, labels, ignore_index=-100, reduction="none")
+    ref.sum().backward()
+    loss, dlog = ops.cross_entropy_fused_(logits.clone(), labels, 0, None, -100, True)
+    assert (loss - ref).abs().max().item() < 2e-3
+    assert _rel_err(dlog, ref_in.grad) < 1e-2
+    assert dlog[:7].abs().max().item() == 0
