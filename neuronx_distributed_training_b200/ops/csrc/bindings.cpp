@@ -29,6 +29,14 @@ void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_p
              int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp,
              int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push);
 void fused_tp_set_debug(at::Tensor buf);
+at::Tensor zero1_reduce(std::vector<int64_t> grads, std::vector<int64_t> params, std::vector<int64_t> hs, int64_t rank,
+                        int64_t epoch, at::Tensor gshard, int64_t shard_lo, bool grads_fp32, double scale,
+                        const at::Tensor& count_mask);
+void zero1_adam_push(std::vector<int64_t> grads, std::vector<int64_t> params, std::vector<int64_t> hs, int64_t rank,
+                     int64_t epoch, at::Tensor master, at::Tensor m, at::Tensor v, const at::Tensor& gshard, int64_t shard_lo,
+                     std::vector<int64_t> seg_lo, std::vector<int64_t> seg_hi, std::vector<double> seg_lr,
+                     std::vector<double> seg_wd, double b1, double b2, double eps, double bc1, double bc2,
+                     const at::Tensor& clip, bool sr, int64_t seed, at::Tensor done_ctr);
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
              int64_t rank, int64_t tp, bool b_kmajor);
@@ -50,5 +58,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");
   m.def("ag_only", &ag_only);
   m.def("fused_tp_set_debug", &fused_tp_set_debug);
+  m.def("zero1_reduce", &zero1_reduce, "ZeRO-1 gradient reduce-scatter by peer pulls");
+  m.def("zero1_adam_push", &zero1_adam_push, "partitioned AdamW + parameter all-gather by peer pushes");
   m.def("gemm_rs", &gemm_rs, "fused tcgen05 GEMM -> reduce-scatter over peer memory");
 }

@@ -67,10 +67,17 @@ struct AgGate {
   uint32_t epoch;
   int mode;   // 0: gathered operand indexed by m-block, 1: by k-block (wgrad)
   int local_lo, local_hi;   // row-blocks of my own shard: already in place, never waited on
+  int total_blocks;
+  mutable unsigned long long ready_lo = 0, ready_hi = 0;   // per-thread cache: blocks already observed ready
   __device__ __forceinline__ void wait_flag(int blk) const {
     if (blk >= local_lo && blk < local_hi) return;
+    // a block that has been seen ready stays ready for the rest of the call: poll each flag at most once
+    const unsigned long long bit = 1ull << (blk & 63);
+    unsigned long long& word = (blk < 64) ? ready_lo : ready_hi;
+    if (blk < 128 && (word & bit)) return;
     while ((int)(ld_acquire_sys(flags + blk) - epoch) < 0) __nanosleep(64);   // flags only grow (epochs)
     fence_proxy_async_all();   // generic-proxy acquire -> subsequent async-proxy (TMA) reads
+    if (blk < 128) word |= bit;
   }
   __device__ __forceinline__ void wait_m(int m_blk) const {
     if (mode == 0) wait_flag(m_blk);
@@ -232,7 +239,7 @@ ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     return;
   }
   const int bpr = comm.rows_per_rank / 128;
-  AgGate gate{comm.flags, comm.epoch, mode, comm.rank * bpr, (comm.rank + 1) * bpr};
+  AgGate gate{comm.flags, comm.epoch, mode, comm.rank * bpr, (comm.rank + 1) * bpr, bpr * comm.tp};
   dbg_stamp(0);
   gemm_body<A_MN, B_MN, OUT, AgGate>(&tma_a, &tma_b, &tma_c, p, smem_raw, gate, (int)blockIdx.x - comm.num_comm_ctas,
                                      (int)gridDim.x - comm.num_comm_ctas);
@@ -317,28 +324,46 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       while (ld_acquire_sys(rs.counter_local + rb) < target) __nanosleep(200);
     }
     __syncthreads();
-    for (int u = threadIdx.x; u < 128 * 32; u += NUM_THREADS) {
-      const int r = u >> 5, c8 = (u & 31) * 8;
-      const int col = nc * 256 + c8;
-      if (col >= rs.N) continue;
-      float acc[8];
+    // 128 rows x 32 sixteen-byte columns per item; every thread keeps 4 independent outputs in flight and issues all
+    // tp x 4 slab loads before the adds (the loads are L2 / HBM latency bound otherwise)
+    constexpr int ILP = 4;
+    for (int u0 = threadIdx.x; u0 < 128 * 32; u0 += NUM_THREADS * ILP) {
+      uint4 v[ILP][MAX_TP];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int s = 0; s < rs.tp; ++s) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(
-            rs.stage_local + ((size_t)s * rs.rows_per_rank + rb * 128 + r) * rs.N + col));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+      for (int i = 0; i < ILP; ++i) {
+        const int u = u0 + i * NUM_THREADS;
+        const int r = u >> 5, col = nc * 256 + (u & 31) * 8;
+        const bool ok = u < 128 * 32 && col < rs.N;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h[i]);
-          acc[2 * i] += f.x;
-          acc[2 * i + 1] += f.y;
-        }
+        for (int sl = 0; sl < MAX_TP; ++sl)
+          if (ok && sl < rs.tp)
+            v[i][sl] = __ldcg(reinterpret_cast<const uint4*>(rs.stage_local + ((size_t)sl * rs.rows_per_rank + rb * 128 + r) * rs.N + col));
       }
-      uint4 o;
-      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(rs.out + ((size_t)rb * 128 + r) * rs.N + col) = o;
+#pragma unroll
+      for (int i = 0; i < ILP; ++i) {
+        const int u = u0 + i * NUM_THREADS;
+        const int r = u >> 5, col = nc * 256 + (u & 31) * 8;
+        if (u >= 128 * 32 || col >= rs.N) continue;
+        float acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < MAX_TP; ++sl) {
+          if (sl < rs.tp) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[i][sl]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(h[t]);
+              acc[2 * t] += f.x;
+              acc[2 * t + 1] += f.y;
+            }
+          }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(rs.out + ((size_t)rb * 128 + r) * rs.N + col) = o;
+      }
     }
     __syncthreads();
   }

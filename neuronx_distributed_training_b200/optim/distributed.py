@@ -143,6 +143,15 @@ class DistributedOptimizer:
         self.exp_avg_sq = torch.zeros(n, dtype=self.state_dtype, device=dev) if self.algorithm in ("adamw", "adam") else None
         self.state = {"step": 0}
 
+    def rebind_buffers(self, new_param_buffer: torch.Tensor, new_grad_buffer: torch.Tensor) -> None:
+        """Move the flat buffers to new storage (e.g. symmetric memory); contents must already be copied."""
+        assert new_param_buffer.numel() == self.total and new_grad_buffer.numel() == self.total
+        self.param_buffer, self.grad_buffer = new_param_buffer, new_grad_buffer
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                p.data = self.param_buffer[o:o + p.numel()].view(p.shape)
+                p.main_grad = self.grad_buffer[o:o + p.numel()].view(p.shape)
+
     @staticmethod
     def _make_hook():
         def hook(p):

@@ -103,7 +103,7 @@ class FusedTP:
     # peer handshake, so they win when the NVLink time is a sizeable fraction of the GEMM time) -----------------
     GEMM_FLOPS = 1.35e15          # sustained tcgen05 bf16 rate of gemm_sm100 on Llama shapes
     LINK_BPS = 6.0e11             # ~600 GB/s effective inbound/outbound per GPU
-    PER_CTA_BPS = 1.0e11          # one comm CTA with the pipelined bulk-copy loop
+    PER_CTA_BPS = 3.0e10          # measured: ~30 GB/s per comm CTA
 
     def _ratio(self, m_total: int, n: int, k: int, bytes_moved: float) -> float:
         return (bytes_moved / self.LINK_BPS) / max(2.0 * m_total * n * k / self.GEMM_FLOPS, 1e-9)
@@ -124,10 +124,16 @@ class FusedTP:
         """enough comm CTAs to finish the gather in ~half the GEMM time, bounded by what the link can take"""
         if self.num_comm_ctas_fixed:
             return self.num_comm_ctas_fixed
+        # A comm CTA moves ~30 GB/s (every byte crosses its SM twice: bulk load + bulk store), so the gather takes
+        # bytes_in / (nc * 30 GB/s) while the GEMM gets (148 - nc) SMs: pick nc that balances the two, capped by the link.
         t_gemm = 2.0 * m_total * n * k / self.GEMM_FLOPS
-        need = bytes_in / self.PER_CTA_BPS / max(0.5 * t_gemm, 1e-9)
-        cap = int(self.LINK_BPS * 1.5 / self.PER_CTA_BPS)
-        return int(max(2, min(cap, round(need + 0.5))))
+        best, best_t = 2, float("inf")
+        for nc in range(2, 33, 2):
+            t_comm = max(bytes_in / (nc * self.PER_CTA_BPS), bytes_in / self.LINK_BPS)
+            t = max(t_comm, t_gemm * 148.0 / (148 - nc)) + 0.25 * min(t_comm, t_gemm)
+            if t < best_t - 1e-9:
+                best, best_t = nc, t
+        return best
 
     # ---- ops ---------------------------------------------------------------------------------------
     def all_gather_gemm(self, x2d: torch.Tensor, w: torch.Tensor, trans_b: bool = True, return_gathered: bool = False):
