@@ -21,6 +21,11 @@ assert enable_fused_zero1(o2)
 g = torch.Generator(device="cpu").manual_seed(100 + rank)
 for step in range(4):
     x = torch.randn(64, 1024, generator=g).to(dev).bfloat16(); y = torch.randn(64, 1024, generator=g).to(dev).bfloat16()
+    # start every step from identical state so the comparison is a one-step equivalence (Adam amplifies ulp-level
+    # differences of near-zero gradients, so trajectories may drift apart legitimately)
+    with torch.no_grad():
+        o2.param_buffer.copy_(o1.param_buffer); o2.master.copy_(o1.master)
+        o2.exp_avg.copy_(o1.exp_avg); o2.exp_avg_sq.copy_(o1.exp_avg_sq)
     for m, o in ((m1, o1), (m2, o2)):
         o.zero_grad()
         ((m(x) - y).float() ** 2).mean().backward()
@@ -30,7 +35,7 @@ for step in range(4):
     err = max((p.float() - q.float()).abs().max().item() for p, q in zip(m1.parameters(), m2.parameters()))
     merr = (o1.master - o2.master).abs().max().item()
     if rank == 0: print(f"step {step}: grad_norm {float(o1.grad_norm):.5f} vs fused {float(o2.grad_norm):.5f}  param max|diff| {err:.3e} master {merr:.3e}", flush=True)
-    assert dn < 1e-3 and err < 1e-2 and merr < 1e-5, (dn, err, merr)
+    assert dn < 1e-3 and err < 4e-3 and merr < 1e-6, (dn, err, merr)
 # timing on a larger flat buffer
 def bench(o, iters=5):
     for _ in range(2): o.step()
