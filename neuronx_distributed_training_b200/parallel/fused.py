@@ -108,17 +108,22 @@ class FusedTP:
     def _ratio(self, m_total: int, n: int, k: int, bytes_moved: float) -> float:
         return (bytes_moved / self.LINK_BPS) / max(2.0 * m_total * n * k / self.GEMM_FLOPS, 1e-9)
 
+    # Measured on 2 / 8 B200s (tests/gpu_checks/check_fused_tp.py): fusing wins when the transfer is neither negligible
+    # (ratio < lo: nothing to hide, the comm CTAs only take SMs away) nor dominant (ratio > hi: the GEMM is too short to
+    # hide anything and NCCL's all-gather / reduce-scatter is as fast as the in-kernel transfer).
+    def _in_band(self, ratio: float) -> bool:
+        lo = float(os.environ.get("NXDT_FUSE_THRESHOLD", "0.30"))
+        hi = float(os.environ.get("NXDT_FUSE_MAX_RATIO", "1.80"))
+        return lo <= ratio <= hi
+
     def prefer_ag_gemm(self, rows_local: int, k: int, n: int) -> bool:
-        thr = float(os.environ.get("NXDT_FUSE_THRESHOLD", "0.30"))
-        return self._ratio(rows_local * self.tp, n, k, rows_local * (self.tp - 1) * k * 2) >= thr
+        return self._in_band(self._ratio(rows_local * self.tp, n, k, rows_local * (self.tp - 1) * k * 2))
 
     def prefer_ag_wgrad(self, rows_local: int, k: int, n: int) -> bool:
-        thr = float(os.environ.get("NXDT_FUSE_THRESHOLD", "0.30"))
-        return self._ratio(rows_local * self.tp, n, k, rows_local * (self.tp - 1) * k * 2) >= thr
+        return self._in_band(self._ratio(rows_local * self.tp, n, k, rows_local * (self.tp - 1) * k * 2))
 
     def prefer_gemm_rs(self, rows_total: int, k: int, n: int) -> bool:
-        thr = float(os.environ.get("NXDT_FUSE_THRESHOLD", "0.30"))
-        return self._ratio(rows_total, n, k, rows_total * n * 2 * (self.tp - 1) / self.tp) >= thr
+        return self._in_band(self._ratio(rows_total, n, k, rows_total * n * 2 * (self.tp - 1) / self.tp))
 
     def _comm_ctas(self, m_total: int, n: int, k: int, bytes_in: float) -> int:
         """enough comm CTAs to finish the gather in ~half the GEMM time, bounded by what the link can take"""
