@@ -29,6 +29,7 @@ from ..parallel import state as ps
 from ..parallel.layers import param_is_tp_duplicate
 from ..parallel.random import set_random_seed
 from ..utils.throughput import Throughput
+from ..utils.profiling import nvtx_range
 
 log = logging.getLogger("nxdt")
 
@@ -164,10 +165,12 @@ class BaseModelModule:
             running = torch.zeros((), dtype=torch.float32, device=self.device)
             for mb in self.get_batch_iterator(batch):
                 with contextlib.nullcontext() if is_training else torch.no_grad():
-                    loss, _ = self.model_fwd_calc_loss(mb)
+                    with nvtx_range("forward"):
+                        loss, _ = self.model_fwd_calc_loss(mb)
                     loss = loss.float() / self.num_microbatches
                 if is_training:
-                    loss.backward()
+                    with nvtx_range("backward"):
+                        loss.backward()
                 running += loss.detach()
         # loss mean over CP then DP (reference base.py:387-395)
         cpg, dpg = ps.get_context_model_parallel_group(), ps.get_data_parallel_group()
@@ -193,7 +196,8 @@ class BaseModelModule:
         if ps.group_size(ppg) > 1:
             dist.all_reduce(loss_mean, group=ppg)       # last stage holds the loss, the others 0
         self.sync_special_grads()
-        self.optimizer.step()
+        with nvtx_range("optimizer_step"):
+            self.optimizer.step()
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
         return loss_mean

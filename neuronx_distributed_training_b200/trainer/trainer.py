@@ -26,6 +26,7 @@ from ..config import Config
 from ..parallel import state as ps
 from ..utils.exp_manager import ExpManager, consumed_samples_from_path, step_from_path
 from ..utils.throughput import DeviceStepTimer
+from ..utils.profiling import StepProfiler, nvtx_range
 
 log = logging.getLogger("nxdt")
 
@@ -48,7 +49,7 @@ class Trainer:
                  log_every_n_steps: int = 10, val_check_interval: Any = None, check_val_every_n_epoch: Any = None,
                  num_sanity_val_steps: int = 0, limit_val_batches: Any = 1.0, limit_test_batches: Any = 1.0,
                  gradient_clip_val: Optional[float] = None, max_time: Any = None, accumulate_grad_batches: int = 1,
-                 enable_progress_bar: bool = False, **ignored):
+                 enable_progress_bar: bool = False, profiler: Any = None, **ignored):
         if accumulate_grad_batches not in (None, 1):
             raise ValueError("accumulate_grad_batches>1 is not supported; gradient accumulation is expressed "
                              "through global_batch_size / micro_batch_size")
@@ -64,6 +65,9 @@ class Trainer:
         self.gradient_clip_val = gradient_clip_val
         self.max_time = _parse_max_time(max_time)
         self.ignored_args = ignored           # Neuron-only knobs (lnc, sequential_move_factor, ...)
+        self.profiler_cfg = profiler          # {start_step, end_step, dir} -> torch.profiler trace of those steps
+        self.profiler: Optional[StepProfiler] = None
+        self.ema = None
         self.global_step = 0
         self.current_epoch = 0
         self.steps_since_resume = 0
@@ -166,10 +170,17 @@ class Trainer:
         if n <= 0:
             return None
         losses = []
-        for i, batch in enumerate(loader):
-            if i >= n:
-                break
-            losses.append(self.model.validation_step(batch, i))
+        if self.ema is not None and (self.exp_manager.cfg.ema or {}).get("validate_original_weights", False) is False:
+            self.ema.swap_in()
+        try:
+            for i, batch in enumerate(loader):
+                if i >= n:
+                    break
+                with nvtx_range("validation_step"):
+                    losses.append(self.model.validation_step(batch, i))
+        finally:
+            if self.ema is not None:
+                self.ema.swap_out()
         if not losses:
             return None
         val = float(torch.stack([l.detach().float() for l in losses]).mean())
@@ -194,6 +205,14 @@ class Trainer:
             self.restore(ckpt_path, weight_init_only=weight_init_only and
                          not os.path.dirname(ckpt_path.rstrip("/")).startswith(str(self.log_dir or "\0")))
         model.on_train_start(self)
+        if self.profiler_cfg:
+            pc = dict(self.profiler_cfg) if not hasattr(self.profiler_cfg, "to_dict") else self.profiler_cfg.to_dict()
+            self.profiler = StepProfiler(pc.get("start_step", 3), pc.get("end_step", 5),
+                                         pc.get("dir", os.path.join(self.log_dir or ".", "profiler")), ps.get_rank())
+        ema_cfg = self.exp_manager.cfg.ema if self.exp_manager is not None else None
+        if ema_cfg and ema_cfg.get("enable", False):
+            from ..utils.ema import EMA
+            self.ema = EMA(model.optimizer, float(ema_cfg.get("decay", 0.999)), int(ema_cfg.get("every_n_steps", 1)))
         for i in range(self.num_sanity_val_steps and 1):
             self.validate()
         t_start = time.time()
@@ -206,9 +225,14 @@ class Trainer:
                     if self.max_steps > 0 and self.global_step >= self.max_steps:
                         self.should_stop = True
                         break
+                    if self.profiler is not None:
+                        self.profiler.step(self.global_step)
                     self.step_timer.start()
-                    loss = model.training_step(batch, batch_idx)
+                    with nvtx_range(f"train_step_{self.global_step}"):
+                        loss = model.training_step(batch, batch_idx)
                     self.step_timer.stop()
+                    if self.ema is not None:
+                        self.ema.update(self.global_step + 1)
                     n_batches += 1
                     self.global_step += 1
                     self.steps_since_resume += 1

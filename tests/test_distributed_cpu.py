@@ -49,3 +49,18 @@ def test_ring_attention_context_parallel(cp):
 
 def test_moe_expert_parallel_matches_single_process():
     run_dist("moe_ep.py", 2, {"EP": "2"})
+
+
+def test_kill_and_resume_fault_injection(tmp_path):
+    """SURVEY section 4 fault-injection tier: hard-kill a rank mid-run, relaunch, identical end state."""
+    env = {"WORKDIR": str(tmp_path)}
+    run_dist("kill_resume.py", 2, {**env, "PHASE": "full"})
+    _PORT[0] += 1
+    e = dict(os.environ); e.update({"OMP_NUM_THREADS": "1", **env, "PHASE": "crash", "KILL_AT": "5", "TORCH_NCCL_ASYNC_ERROR_HANDLING": "1"})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_PORT[0]), os.path.join(HERE, "dist_scripts", "kill_resume.py")]
+    r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600, cwd=os.path.join(HERE, "dist_scripts"))
+    assert r.returncode != 0                                   # the job really died
+    ck = os.listdir(tmp_path / "faulty" / "checkpoints")
+    assert any("step=4" in c for c in ck) and not any("step=6" in c for c in ck)
+    run_dist("kill_resume.py", 2, {**env, "PHASE": "resume"})
