@@ -75,7 +75,7 @@ struct AgGate {
     const unsigned long long bit = 1ull << (blk & 63);
     unsigned long long& word = (blk < 64) ? ready_lo : ready_hi;
     if (blk < 128 && (word & bit)) return;
-    while ((int)(ld_acquire_sys(flags + blk) - epoch) < 0) __nanosleep(64);   // flags only grow (epochs)
+    spin_until_ge_sys(flags + blk, epoch, 64);
     fence_proxy_async_all();   // generic-proxy acquire -> subsequent async-proxy (TMA) reads
     if (blk < 128) word |= bit;
   }
@@ -111,7 +111,7 @@ __device__ void comm_cta_push(const CommArgs& a, uint8_t* smem_raw) {
   // entered call (epoch - 1)
   for (int p = 0; p < a.tp; ++p) {
     if (p == a.rank) continue;
-    while ((int)ld_acquire_sys(a.hs_local + p) < (int)a.epoch - 1) __nanosleep(100);
+    spin_until_ge_sys(a.hs_local + p, (uint32_t)(a.epoch - 1), 100);
   }
   dbg_stamp(1);
   const int blocks_per_rank = a.rows_per_rank / 128;
@@ -188,7 +188,7 @@ __device__ void comm_cta_pull(const CommArgs& a, uint8_t* smem_raw) {
     const int src_rank = blk / blocks_per_rank;
     if (src_rank == a.rank) continue;
     if (!((waited_rank_mask >> src_rank) & 1)) {
-      while ((int)(ld_acquire_sys(a.hs_local + src_rank) - a.epoch) < 0) __nanosleep(100);
+      spin_until_ge_sys(a.hs_local + src_rank, a.epoch, 100);
       waited_rank_mask |= 1 << src_rank;
     }
     if (!stamped) { dbg_stamp(1); stamped = true; }
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ag_only_kernel(const CommArgs 
   const int bpr = comm.rows_per_rank / 128;
   for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < bpr * comm.tp; blk += gridDim.x * blockDim.x) {
     if (blk / bpr == comm.rank) continue;
-    while ((int)(ld_acquire_sys(comm.flags + blk) - comm.epoch) < 0) __nanosleep(200);
+    spin_until_ge_sys(comm.flags + blk, comm.epoch, 200);
   }
 }
 
@@ -283,7 +283,7 @@ struct RsGate {
   __device__ __forceinline__ void before_first_store() const {
     if (threadIdx.x == 64) {
       for (int p = 0; p < a.tp; ++p)
-        while (ld_acquire_sys(a.hs_local + p) < a.epoch) __nanosleep(100);
+        spin_until_ge_sys(a.hs_local + p, a.epoch, 100);
       dbg_stamp(1);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -321,7 +321,7 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   for (int item = blockIdx.x; item < bpr * n_chunks; item += gridDim.x) {
     const int rb = item / n_chunks, nc = item - rb * n_chunks;
     if (threadIdx.x == 0) {
-      while (ld_acquire_sys(rs.counter_local + rb) < target) __nanosleep(200);
+      spin_until_ge_sys(rs.counter_local + rb, target, 200);
     }
     __syncthreads();
     // 128 rows x 32 sixteen-byte columns per item; every thread keeps 4 independent outputs in flight and issues all

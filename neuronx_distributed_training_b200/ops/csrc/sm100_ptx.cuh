@@ -289,6 +289,20 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   return v;
 }
 
+// Bounded spin on a cross-GPU flag: a lost signal becomes a trap (CUDA error on the host) instead of a silent hang.
+// `ge` semantics: wait until (int)(*p - target) >= 0 (flags are monotonically increasing epochs / counters).
+__device__ __forceinline__ void spin_until_ge_sys(const uint32_t* p, uint32_t target, int sleep_ns = 100) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - target) < 0) {
+    __nanosleep(sleep_ns);
+    if (clock64() - t0 > 40000000000ll) {   // ~20 s at 2 GHz
+      printf("[nxdt] cross-GPU wait timed out: flag %p = %u, waiting for >= %u (block %d)\n", (const void*)p,
+             ld_acquire_sys(p), target, (int)blockIdx.x);
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

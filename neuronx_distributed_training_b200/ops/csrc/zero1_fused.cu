@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) zero1_reduce_kernel(const Peers pr, float
     for (int p = 0; p < pr.dp; ++p) st_release_sys(pr.hs[p] + 2 * pr.rank, pr.epoch);
   if (threadIdx.x == 0)
     for (int p = 0; p < pr.dp; ++p)
-      while ((int)(ld_acquire_sys(pr.hs_local + 2 * p) - pr.epoch) < 0) __nanosleep(200);
+      spin_until_ge_sys(pr.hs_local + 2 * p, pr.epoch, 200);
   __syncthreads();
   float sq = 0.f;
   const long long n4 = n / 4;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) zero1_adam_push_kernel(const Peers pr, fl
     __threadfence_system();
     for (int p = 0; p < pr.dp; ++p) st_release_sys(pr.hs[p] + 2 * pr.rank + 1, pr.epoch);
     for (int p = 0; p < pr.dp; ++p)
-      while ((int)(ld_acquire_sys(pr.hs_local + 2 * p + 1) - pr.epoch) < 0) __nanosleep(200);
+      spin_until_ge_sys(pr.hs_local + 2 * p + 1, pr.epoch, 200);
   }
 }
 
