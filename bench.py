@@ -27,6 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the 1-GPU run keeps 144 GB of persistent state on a 180 GB part: growable segments avoid fragmentation OOMs
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 
 def parse():
@@ -138,10 +140,14 @@ def main():
         ops.set_backend("torch")
     recompute = args.recompute
     if recompute == "auto":
-        # single GPU holds the full fp32 optimizer state (144 GB): recompute the MLP as the reference's
-        # 70B config does; with TP >= 2 the per-rank footprint needs no extra recompute.
-        recompute = "mlp" if world == 1 else "none"
+        # single GPU holds the full fp32 optimizer state (144 GB): selective recomputation of the SwiGLU
+        # activation (the reference's `ActivationMultiplyMLP` recompute class); with TP >= 2 the per-rank
+        # footprint needs no recompute.
+        recompute = "swiglu" if world == 1 else "none"
     gran, rec_list = {"none": (None, None), "mlp": ("selective", ["CoreAttention", "LlamaMLP"]),
+                      "mlp_only": ("selective", ["LlamaMLP"]),
+                      "swiglu": ("selective", ["ActivationMultiplyMLP"]),
+                      "swiglu_norm": ("selective", ["ActivationMultiplyMLP", "LlamaRMSNorm"]),
                       "full": ("full", None)}[recompute]
     cfg = from_dict({
         "name": "hf_llama", "model_source": "hf", "seed": 1234,

@@ -32,6 +32,7 @@ import torch
 import torch.distributed as dist
 
 from ..parallel import state as ps
+from . import storage
 
 _MAGIC = b"NXDTB200"
 _DTYPES = [torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int8, torch.uint8, torch.int16,
@@ -156,7 +157,7 @@ g_iostate = _IOState()
 
 # ---- helpers -------------------------------------------------------------------------------------------
 def _is_remote(path: str) -> bool:
-    return path.startswith("s3://")
+    return storage.is_remote(path)
 
 
 def shard_file_name(dp_rank: int, tp_rank: int, pp_rank: int) -> str:
@@ -244,11 +245,13 @@ def _load_object(path: str, map_location="cpu") -> Any:
 def save_checkpoint(checkpoint_dir: str, tag: str, model: Optional[Dict[str, Any]] = None,
                     optimizer: Optional[Dict[str, Any]] = None, user_content: Optional[Dict[str, Any]] = None,
                     use_xser: bool = True, async_save: bool = False, zero1_optimizer: bool = True,
-                    num_kept_ckpts: Optional[int] = None) -> str:
-    """Every rank calls this.  ``model`` / ``optimizer`` are (already sharded) state dicts."""
+                    num_kept_ckpts: Optional[int] = None, _publish: bool = True) -> str:
+    """Every rank calls this.  ``model`` / ``optimizer`` are (already sharded) state dicts.  ``checkpoint_dir`` may be
+    an object-store URL (``s3://bucket/prefix``): shards are written to node-local staging and uploaded, the ``done``
+    marker last (see ``checkpoint/storage.py``)."""
     if _is_remote(checkpoint_dir):
-        raise NotImplementedError("s3:// checkpoint paths need an object-store client, which this offline "
-                                  "image does not have; mount the bucket (e.g. mountpoint-s3) and pass the path")
+        return _save_checkpoint_remote(checkpoint_dir, tag, model, optimizer, user_content, use_xser, async_save,
+                                       zero1_optimizer)
     root = os.path.join(checkpoint_dir, tag)
     dp_rank = ps.get_data_parallel_rank() if ps.get_context_model_parallel_size() == 1 else \
         ps.group_rank(ps.get_data_context_parallel_group())
@@ -278,6 +281,8 @@ def save_checkpoint(checkpoint_dir: str, tag: str, model: Optional[Dict[str, Any
             with open(os.path.join(root, "done"), "w") as f:
                 f.write(str(time.time()) + "\n")
 
+    if not _publish:
+        return root          # the caller (object-store path) publishes the markers itself
     if async_save:
         # per-rank completion markers let rank 0 publish "done" without a collective on the IO thread
         mdir = os.path.join(root, ".ranks")
@@ -302,6 +307,105 @@ def save_checkpoint(checkpoint_dir: str, tag: str, model: Optional[Dict[str, Any
     return root
 
 
+def _my_shard_names() -> Tuple[str, str]:
+    dp_rank = ps.get_data_parallel_rank() if ps.get_context_model_parallel_size() == 1 else \
+        ps.group_rank(ps.get_data_context_parallel_group())
+    tp_rank, pp_rank = ps.get_tensor_model_parallel_rank(), ps.get_pipeline_model_parallel_rank()
+    return shard_file_name(0, tp_rank, pp_rank), shard_file_name(dp_rank, tp_rank, pp_rank)
+
+
+def _save_checkpoint_remote(url_dir, tag, model, optimizer, user_content, use_xser, async_save, zero1_optimizer) -> str:
+    store = storage.get_store(url_dir)
+    local_dir = storage.staging_dir(url_dir)
+    root_url = storage.join_url(url_dir, tag)
+    rank, world = ps.get_rank(), ps.get_world_size()
+    dp_rank = ps.get_data_parallel_rank() if ps.get_context_model_parallel_size() == 1 else \
+        ps.group_rank(ps.get_data_context_parallel_group())
+    if rank == 0:
+        store.remove_prefix(root_url)          # a re-used tag must not keep a stale 'done'
+    ps.barrier()
+    local_root = save_checkpoint(local_dir, tag, model, optimizer, user_content, use_xser, async_save, zero1_optimizer,
+                                 _publish=False)
+    model_name, optim_name = _my_shard_names()
+    mine = []
+    if model is not None and dp_rank == 0:
+        mine.append("model/" + model_name)
+    if optimizer is not None and (zero1_optimizer or dp_rank == 0):
+        mine.append("optim/" + optim_name)
+    pending = list(g_iostate.pending)
+
+    def publish():
+        for f in pending:
+            f.result()
+        store.upload_tree(local_root, root_url, only=lambda rel: any(rel.startswith(m) for m in mine))
+        marker = os.path.join(local_root, f".uploaded_{rank}")
+        open(marker, "w").close()
+        store.upload_file(marker, storage.join_url(root_url, ".ranks", f"{rank}.ok"))
+        os.remove(marker)
+        for dirpath, _, files in os.walk(local_root):          # this rank's staged copies are no longer needed
+            for f in files:
+                rel = os.path.relpath(os.path.join(dirpath, f), local_root).replace(os.sep, "/")
+                if any(rel.startswith(m) for m in mine):
+                    os.remove(os.path.join(dirpath, f))
+        if rank == 0:
+            deadline = time.time() + 3600
+            while time.time() < deadline:
+                if len([u for u in store.list(storage.join_url(root_url, ".ranks")) if u.endswith(".ok")]) >= world:
+                    break
+                time.sleep(0.05)
+            with open(os.path.join(local_root, "checkpoint"), "w") as f:
+                f.write(tag + "\n")
+            with open(os.path.join(local_root, "done"), "w") as f:
+                f.write(str(time.time()) + "\n")
+            for name in ("user_content.pt", "checkpoint", "done"):       # 'done' strictly last
+                lp = os.path.join(local_root, name)
+                if os.path.exists(lp):
+                    store.upload_file(lp, storage.join_url(root_url, name))
+                    os.remove(lp)
+
+    if async_save:
+        g_iostate.submit(publish)
+    else:
+        publish()
+        ps.barrier()
+    return root_url
+
+
+def _load_checkpoint_remote(url_dir, tag, model, optimizer, strict_done, map_location):
+    store = storage.get_store(url_dir)
+    root_url = storage.join_url(url_dir, tag)
+    if strict_done and not store.exists(storage.join_url(root_url, "done")):
+        raise FileNotFoundError(f"checkpoint {root_url} has no 'done' marker (incomplete save?)")
+    local_dir = os.path.join(storage.staging_dir(url_dir), f"load_rank{ps.get_rank()}")
+    local_root = os.path.join(local_dir, tag)
+    shutil.rmtree(local_root, ignore_errors=True)
+    os.makedirs(local_root, exist_ok=True)
+    model_name, optim_name = _my_shard_names()
+    wanted = []
+    if model:
+        wanted.append("model/" + model_name)
+    if optimizer:
+        have = store.list(storage.join_url(root_url, "optim"))
+        prefix = storage.join_url(root_url, "optim", optim_name)
+        wanted.append("optim/" + (optim_name if any(u.startswith(prefix) for u in have) else model_name))
+    for w in wanted:
+        sub = w.split("/")[0]
+        for u in store.list(storage.join_url(root_url, sub)):
+            if u.startswith(storage.join_url(root_url, w)):
+                rel = u[len(root_url) + 1:]
+                lp = os.path.join(local_root, *rel.split("/"))
+                os.makedirs(os.path.dirname(lp), exist_ok=True)
+                store.download_file(u, lp)
+    for name in ("user_content.pt", "done"):
+        u = storage.join_url(root_url, name)
+        if store.exists(u):
+            store.download_file(u, os.path.join(local_root, name))
+    try:
+        return load_checkpoint(local_dir, tag, model, optimizer, strict_done, map_location)
+    finally:
+        shutil.rmtree(local_root, ignore_errors=True)
+
+
 def finalize_checkpoint() -> None:
     """Block until all asynchronous writes / removals are done (call at teardown)."""
     g_iostate.wait_all()
@@ -309,12 +413,16 @@ def finalize_checkpoint() -> None:
 
 
 def has_checkpoint(checkpoint_dir: str, tag: str) -> bool:
+    if _is_remote(checkpoint_dir):
+        return storage.get_store(checkpoint_dir).exists(storage.join_url(checkpoint_dir, tag, "done"))
     return os.path.exists(os.path.join(checkpoint_dir, tag, "done"))
 
 
 def load_checkpoint(checkpoint_dir: str, tag: str, model: bool = True, optimizer: bool = True,
                     strict_done: bool = True, map_location="cpu") -> Tuple[Optional[dict], Optional[dict], Optional[dict]]:
     """Returns (model_state, optimizer_state, user_content) for THIS rank's shard."""
+    if _is_remote(checkpoint_dir):
+        return _load_checkpoint_remote(checkpoint_dir, tag, model, optimizer, strict_done, map_location)
     root = os.path.join(checkpoint_dir, tag)
     if strict_done and not os.path.exists(os.path.join(root, "done")):
         raise FileNotFoundError(f"checkpoint {root} has no 'done' marker (incomplete save?)")
@@ -336,5 +444,13 @@ def load_checkpoint(checkpoint_dir: str, tag: str, model: bool = True, optimizer
 
 
 def remove_checkpoint(path: str, async_remove: bool = True) -> None:
+    if _is_remote(path):
+        if ps.get_rank() == 0:
+            store = storage.get_store(path)
+            if async_remove:
+                g_iostate.submit(store.remove_prefix, path)
+            else:
+                store.remove_prefix(path)
+        return
     if ps.get_rank() == 0:
         g_iostate.submit_remove(path, async_remove)

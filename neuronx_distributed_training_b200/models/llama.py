@@ -149,7 +149,17 @@ class LlamaRotaryEmbedding(nn.Module):
 
 
 class ActivationMultiplyMLP(nn.Module):
-    """SwiGLU on the fused gate||up activation (reference :164-173)."""
+    """SwiGLU on the fused gate||up activation (reference :164-173).
+
+    Selecting this class for activation recomputation (``activations_checkpoint_recompute``) does not wrap it
+    in a checkpoint: ``enable_recompute`` makes the consuming ``down_proj`` node compute the activation itself
+    and recompute it in backward from the saved gate||up tensor."""
+
+    recompute_in_consumer = False
+
+    def enable_recompute(self) -> bool:
+        self.recompute_in_consumer = True
+        return True
 
     def forward(self, gate_up: torch.Tensor) -> torch.Tensor:
         return ops.swiglu(gate_up)
@@ -169,7 +179,11 @@ class LlamaMLP(nn.Module):
                                            input_is_parallel=True, init_method=init, **kw)
 
     def forward(self, x):
-        return self.down_proj(self.activation_multiply(self.gate_up_proj(x)))
+        gate_up = self.gate_up_proj(x)
+        if self.activation_multiply.recompute_in_consumer and torch.is_grad_enabled() \
+                and type(self.down_proj) is RowParallelLinear:      # not when wrapped (e.g. LoRA)
+            return self.down_proj(gate_up, pre_act="swiglu")
+        return self.down_proj(self.activation_multiply(gate_up))
 
 
 class CoreAttention(nn.Module):

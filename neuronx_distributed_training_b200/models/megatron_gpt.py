@@ -212,6 +212,10 @@ class CoreAttention(nn.Module):
             # layer scaling cancels analytically (scores / n then softmax in fp32 * n), so the flash path is exact
             return ops.flash_attention(q, k, v, causal=True, window=self.window, scale=self.scale)
         with get_rng_tracker().fork():
+            if q.is_cuda:
+                # scores in the compute dtype + fused scale/mask/softmax kernel (apex FusedScaleMaskSoftmax role)
+                return ops.attention_eager(q, k, v, causal=True, window=self.window, scale=self.scale,
+                                           dropout_p=self.dropout_p if self.training else 0.0)
             return ops.attention_ref(q, k, v, causal=True, window=self.window, scale=self.scale,
                                      dropout_p=self.dropout_p if self.training else 0.0)
 

@@ -14,6 +14,7 @@ modeling_mixtral.py:342-374,872-878, transformer.py:376-467, gpt_model.py:300-30
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -144,8 +145,34 @@ class ExpertMLPs(nn.Module):
             return ops.bias_act(g, None, self.activation) * u
         return ops.bias_act(h, None, self.activation)
 
+    def forward_grouped(self, x_sorted: torch.Tensor, tokens_per_expert) -> torch.Tensor:
+        """Dropless expert FFNs as two grouped GEMMs (+ one for each gradient): tokens are scattered into a layout
+        where every expert's rows are padded to a multiple of 128, built on the device from the routing counts,
+        so there is no host sync and no per-expert launch (the reference's blockwise NKI kernel, X19)."""
+        dev = x_sorted.device
+        counts = tokens_per_expert if torch.is_tensor(tokens_per_expert) else torch.tensor(list(tokens_per_expert))
+        counts = counts.to(dev)
+        n = x_sorted.shape[0]
+        dest, block_expert, offsets, t_cap = ops.grouped_layout(counts, n)
+        xp = x_sorted.new_zeros(t_cap, x_sorted.shape[1]).index_copy(0, dest, x_sorted)
+        h = ops.grouped_linear(xp, self.mlp_op.gate_up_proj, block_expert, offsets)
+        h = self._act(h)
+        y = ops.grouped_linear(h, self.mlp_op.down_proj, block_expert, offsets)
+        return y.index_select(0, dest)
+
+    def _use_grouped(self, x: torch.Tensor) -> bool:
+        mode = os.environ.get("NXDT_MOE_GROUPED", "auto")
+        if mode in ("0", "off"):
+            return False
+        if mode in ("1", "on"):
+            return True
+        return x.is_cuda and x.dtype == torch.bfloat16 and ops.get_backend() != "torch" and ops.C() is not None \
+            and hasattr(ops.C(), "grouped_gemm") and self.H % 128 == 0 and self.I_local % 128 == 0
+
     def forward_sorted(self, x_sorted: torch.Tensor, tokens_per_expert: torch.Tensor) -> torch.Tensor:
         """x_sorted [N,H] grouped by (local) expert; tokens_per_expert [E_local] (host list or tensor)."""
+        if x_sorted.shape[0] > 0 and self._use_grouped(x_sorted):
+            return self.forward_grouped(x_sorted, tokens_per_expert)
         counts = tokens_per_expert.tolist() if torch.is_tensor(tokens_per_expert) else list(tokens_per_expert)
         outs, off = [], 0
         for e, n in enumerate(counts):

@@ -136,6 +136,112 @@ def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = 
 
 
 # =====================================================================================================
+# Grouped (per-expert) GEMM for dropless MoE.  Tokens are sorted by expert and every expert's run of rows is
+# padded to a multiple of 128 so one persistent kernel covers all experts; the routing result never visits
+# the host (reference: NKI blockwise dropless kernel).
+# =====================================================================================================
+GROUP_BLOCK = 128
+
+
+def grouped_layout(counts: torch.Tensor, n_rows: int):
+    """Padded row layout for ``n_rows`` tokens sorted by expert with ``counts[e]`` tokens each.
+
+    Returns ``(dest, block_expert, offsets, t_cap)``: ``dest[i]`` = row of sorted token ``i`` in the padded buffer
+    of ``t_cap`` rows (a static worst-case bound, so no device->host sync), ``block_expert`` int32 [t_cap/128]
+    (-1 = unused block) and ``offsets`` int32 [E+1] (padded segment boundaries)."""
+    E = counts.numel()
+    dev = counts.device
+    counts = counts.to(torch.int64)
+    t_cap = (n_rows + E * (GROUP_BLOCK - 1) + GROUP_BLOCK - 1) // GROUP_BLOCK * GROUP_BLOCK
+    padded = (counts + GROUP_BLOCK - 1) // GROUP_BLOCK * GROUP_BLOCK
+    ends = torch.cumsum(padded, 0)
+    starts = ends - padded
+    ustarts = torch.cumsum(counts, 0) - counts
+    e_row = torch.repeat_interleave(torch.arange(E, device=dev), counts, output_size=n_rows)
+    dest = starts[e_row] + torch.arange(n_rows, device=dev) - ustarts[e_row]
+    blk_start = torch.arange(t_cap // GROUP_BLOCK, device=dev) * GROUP_BLOCK
+    be = torch.searchsorted(ends, blk_start, right=True)
+    block_expert = torch.where(be < E, be, torch.full_like(be, -1)).to(torch.int32)
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), ends]).to(torch.int32)
+    return dest, block_expert, offsets, t_cap
+
+
+def _grouped_native_ok(a: torch.Tensor, w: torch.Tensor) -> bool:
+    return _use_native(a) and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and hasattr(C(), "grouped_gemm") \
+        and a.shape[0] % GROUP_BLOCK == 0 and a.shape[1] % 8 == 0 and w.shape[1] % 8 == 0 and w.shape[2] % 8 == 0
+
+
+def grouped_gemm(a: torch.Tensor, w: torch.Tensor, block_expert: torch.Tensor, offsets: torch.Tensor,
+                 trans_w: bool = False) -> torch.Tensor:
+    """Rows of expert e (``offsets[e]:offsets[e+1]``) times ``w[e]`` ([K,N]; ``trans_w``: ``w[e]`` is [N,K])."""
+    n_out = w.shape[1] if trans_w else w.shape[2]
+    if _grouped_native_ok(a, w):
+        a = a if a.is_contiguous() else a.contiguous()
+        w = w if w.is_contiguous() else w.contiguous()
+        out = torch.empty(a.shape[0], n_out, dtype=a.dtype, device=a.device)
+        _count()
+        C().grouped_gemm(a, w, out, block_expert, trans_w)
+        return out
+    out = a.new_zeros(a.shape[0], n_out)
+    offs = offsets.tolist()
+    for e in range(w.shape[0]):
+        lo, hi = offs[e], offs[e + 1]
+        if hi > lo:
+            out[lo:hi] = a[lo:hi] @ (w[e].t() if trans_w else w[e])
+    return out
+
+
+def grouped_wgrad(x: torch.Tensor, dy: torch.Tensor, offsets: torch.Tensor, out: torch.Tensor,
+                  accumulate: bool) -> torch.Tensor:
+    """out[e] (+)= x[rows of e]^T @ dy[rows of e];  out [E, K, N] fp32 or the activations' dtype."""
+    if _use_native(x) and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and hasattr(C(), "grouped_wgrad") \
+            and x.shape[1] % GROUP_BLOCK == 0 and dy.shape[1] % 8 == 0 and x.shape[0] % GROUP_BLOCK == 0 \
+            and out.dtype in (torch.float32, torch.bfloat16) and out.is_contiguous():
+        if not accumulate:
+            out.zero_()          # experts without tokens are skipped by the kernel
+        _count()
+        C().grouped_wgrad(x.contiguous(), dy.contiguous(), out, offsets, accumulate)
+        return out
+    offs = offsets.tolist()
+    for e in range(out.shape[0]):
+        lo, hi = offs[e], offs[e + 1]
+        g = (x[lo:hi].t() @ dy[lo:hi]).to(out.dtype) if hi > lo else torch.zeros_like(out[e])
+        if accumulate:
+            out[e].add_(g)
+        else:
+            out[e].copy_(g)
+    return out
+
+
+class _GroupedLinearFn(torch.autograd.Function):
+    """y[rows of e] = x[rows of e] @ w[e] with w [E, K, N]; dW accumulates into ``w.main_grad`` when present."""
+
+    @staticmethod
+    def forward(ctx, x, w, block_expert, offsets):
+        ctx.save_for_backward(x, w, block_expert, offsets)
+        return grouped_gemm(x, w, block_expert, offsets, trans_w=False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, block_expert, offsets = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = grouped_gemm(dy, w, block_expert, offsets, trans_w=True) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            main_grad = getattr(w, "main_grad", None)
+            if main_grad is not None:
+                grouped_wgrad(x, dy, offsets, main_grad, True)
+                w.grad_added_to_main_grad = True
+            else:
+                dw = grouped_wgrad(x, dy, offsets, torch.empty_like(w), False)
+        return dx, dw, None, None
+
+
+def grouped_linear(x: torch.Tensor, w: torch.Tensor, block_expert: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    return _GroupedLinearFn.apply(x, w, block_expert, offsets)
+
+
+# =====================================================================================================
 # RMSNorm / LayerNorm
 # =====================================================================================================
 def rmsnorm_ref(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
@@ -171,10 +277,38 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-5) -> torch.Tensor
     return rmsnorm_ref(x, w, eps)
 
 
-def layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float = 1e-5,
-              one_plus: bool = False) -> torch.Tensor:
+def layernorm_ref(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float = 1e-5,
+                  one_plus: bool = False) -> torch.Tensor:
     ww = w + 1.0 if one_plus else w
     return F.layer_norm(x.float(), (x.shape[-1],), ww.float(), None if b is None else b.float(), eps).to(x.dtype)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps, one_plus):
+        x2 = x.reshape(-1, x.shape[-1])
+        _count()
+        y, mean, rstd = C().layernorm_fwd(x2, w, b, eps, one_plus)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.one_plus, ctx.has_bias = one_plus, b is not None
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        _count()
+        dx, dw, db = C().layernorm_bwd(dy.reshape(x2.shape).contiguous(), x2, w, mean, rstd, ctx.one_plus)
+        return dx.view(dy.shape), dw.to(w.dtype), (db.to(w.dtype) if ctx.has_bias else None), None, None
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float = 1e-5,
+              one_plus: bool = False) -> torch.Tensor:
+    """Affine LayerNorm (``one_plus``: Megatron layernorm1p, weight stored as w-1); fp32 statistics."""
+    if _use_native(x) and hasattr(C(), "layernorm_fwd") and x.dtype in (torch.bfloat16, torch.float32) \
+            and w.dtype == x.dtype and (b is None or b.dtype == x.dtype) and x.is_contiguous() \
+            and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192:
+        return _LayerNormFn.apply(x, w, b, eps, one_plus)
+    return layernorm_ref(x, w, b, eps, one_plus)
 
 
 # =====================================================================================================
@@ -279,14 +413,29 @@ def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
     return swiglu_ref(gate_up)
 
 
-def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], activation: str) -> torch.Tensor:
-    """bias + activation for the Megatron MLP (gelu / geglu / reglu / swiglu / relu / squared-relu)."""
+def swiglu_backward(dout: torch.Tensor, gate_up: torch.Tensor) -> torch.Tensor:
+    """d(gate||up) of ``swiglu`` given d(out); used by nodes that recompute the activation themselves."""
+    if _use_native(gate_up) and gate_up.dtype == torch.bfloat16 and gate_up.is_contiguous() \
+            and gate_up.shape[-1] % 16 == 0:
+        _count()
+        return C().swiglu_bwd(dout.contiguous(), gate_up)
+    g, u = gate_up.float().chunk(2, dim=-1)
+    d = dout.float()
+    sg = torch.sigmoid(g)
+    return torch.cat([d * u * (sg * (1.0 + g * (1.0 - sg))), d * (g * sg)], dim=-1).to(gate_up.dtype)
+
+
+_ACT_MODES = {"gelu": 0, "geglu": 1, "fast-geglu": 1, "reglu": 2, "fast-reglu": 2, "swiglu": 3, "fast-swiglu": 3,
+              "relu": 4, "squared-relu": 5, "silu": 6}
+
+
+def bias_act_ref(x: torch.Tensor, bias: Optional[torch.Tensor], activation: str) -> torch.Tensor:
     if bias is not None:
         x = x + bias
     if activation == "gelu":
         return F.gelu(x, approximate="tanh")
     if activation in ("swiglu", "fast-swiglu"):
-        return swiglu(x) if bias is None else swiglu_ref(x)
+        return swiglu_ref(x)
     if activation in ("geglu", "fast-geglu"):
         g, u = x.chunk(2, dim=-1)
         return F.gelu(g, approximate="tanh") * u
@@ -302,13 +451,133 @@ def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], activation: str) -> 
     raise ValueError(f"unknown activation {activation}")
 
 
+class _BiasActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, mode):
+        ctx.save_for_backward(x, bias)
+        ctx.mode = mode
+        _count()
+        return C().bias_act_fwd(x, bias, mode)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, bias = ctx.saved_tensors
+        _count()
+        dx = C().bias_act_bwd(dout.contiguous(), x, bias, ctx.mode)
+        db = None
+        if bias is not None and ctx.needs_input_grad[1]:
+            db = dx.reshape(-1, dx.shape[-1]).sum(0, dtype=torch.float32).to(bias.dtype)
+        return dx, db, None
+
+
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], activation: str) -> torch.Tensor:
+    """bias + activation for the Megatron MLP (gelu / geglu / reglu / swiglu / relu / squared-relu / silu)."""
+    if activation not in _ACT_MODES:
+        raise ValueError(f"unknown activation {activation}")
+    mode = _ACT_MODES[activation]
+    width = x.shape[-1] // 2 if mode in (1, 2, 3) else x.shape[-1]
+    if _use_native(x) and hasattr(C(), "bias_act_fwd") and x.dtype in (torch.bfloat16, torch.float32) \
+            and (bias is None or bias.dtype == x.dtype) and x.is_contiguous() and width % 8 == 0:
+        return _BiasActFn.apply(x, bias, mode)
+    return bias_act_ref(x, bias, activation)
+
+
+class _BiasDropoutAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, residual, p):
+        _count()
+        out, mask = C().bias_dropout_add_fwd(x, bias, residual, p)
+        ctx.save_for_backward(mask)
+        ctx.p, ctx.has_bias = p, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        _count()
+        dx = C().dropout_bwd(dout, mask, ctx.p)
+        db = dx.reshape(-1, dx.shape[-1]).sum(0, dtype=torch.float32).to(dx.dtype) if ctx.has_bias else None
+        return dx, db, dout, None
+
+
 def bias_dropout_add(x: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor, p: float,
                      training: bool) -> torch.Tensor:
+    """``residual + dropout(x + bias)`` (reference transformer.py:1453-1465); one kernel when dropout is active."""
+    if p > 0.0 and training and _use_native(x) and hasattr(C(), "bias_dropout_add_fwd") \
+            and x.dtype in (torch.bfloat16, torch.float32) and residual.dtype == x.dtype and x.shape == residual.shape \
+            and (bias is None or bias.dtype == x.dtype) and x.is_contiguous() and residual.is_contiguous() \
+            and x.shape[-1] % 8 == 0:
+        return _BiasDropoutAddFn.apply(x, bias, residual, float(p))
     if bias is not None:
         x = x + bias
     if p > 0.0 and training:
         x = F.dropout(x, p=p, training=True)
     return residual + x
+
+
+# =====================================================================================================
+# scale + mask + softmax (eager attention path; reference: apex FusedScaleMaskSoftmax / Neuron fused softmax)
+# =====================================================================================================
+def scale_mask_softmax_ref(scores: torch.Tensor, scale: float, causal: bool = True, window: Optional[int] = None,
+                           q_offset: int = 0) -> torch.Tensor:
+    Sq, Sk = scores.shape[-2], scores.shape[-1]
+    s = scores.float() * scale
+    qi = torch.arange(Sq, device=scores.device).unsqueeze(-1) + q_offset
+    ki = torch.arange(Sk, device=scores.device).unsqueeze(0)
+    mask = torch.zeros(Sq, Sk, dtype=torch.bool, device=scores.device)
+    if causal:
+        mask |= ki > qi
+    if window is not None and window > 0:
+        mask |= ki <= qi - window
+    s = s.masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return torch.nan_to_num(p, nan=0.0).to(scores.dtype)
+
+
+class _ScaleMaskSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, scale, causal, window, q_offset):
+        _count()
+        y = C().scale_mask_softmax_fwd(scores, scale, causal, window, q_offset)
+        ctx.save_for_backward(y)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        _count()
+        return C().scale_mask_softmax_bwd(dy.contiguous(), y, ctx.scale), None, None, None, None
+
+
+def scale_mask_softmax(scores: torch.Tensor, scale: float, causal: bool = True, window: Optional[int] = None,
+                       q_offset: int = 0) -> torch.Tensor:
+    """softmax(scale * scores + mask) over the last dim of ``[..., Sq, Sk]``; fully masked rows give zeros."""
+    if _use_native(scores) and hasattr(C(), "scale_mask_softmax_fwd") and scores.is_contiguous() \
+            and scores.dtype in (torch.bfloat16, torch.float32) and scores.shape[-1] % 8 == 0:
+        return _ScaleMaskSoftmaxFn.apply(scores, float(scale), bool(causal), int(window or 0), int(q_offset))
+    return scale_mask_softmax_ref(scores, scale, causal, window, q_offset)
+
+
+def attention_eager(q, k, v, causal: bool = True, window: Optional[int] = None, scale: Optional[float] = None,
+                    dropout_p: float = 0.0):
+    """Materialised-scores attention in the compute dtype: batched GEMM -> fused scale-mask-softmax (-> dropout) ->
+    batched GEMM.  Used where probabilities must exist (attention dropout, flash disabled); q [B,S,Hq,D]."""
+    B, Sq, Hq, D = q.shape
+    Hk = k.shape[2]
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    qh = q.transpose(1, 2)
+    kh = k.transpose(1, 2)
+    vh = v.transpose(1, 2)
+    if Hk != Hq:
+        kh = kh.repeat_interleave(Hq // Hk, dim=1)
+        vh = vh.repeat_interleave(Hq // Hk, dim=1)
+    s = torch.matmul(qh, kh.transpose(-1, -2)).contiguous()
+    p = scale_mask_softmax(s, scale, causal, window, 0)
+    if dropout_p > 0.0:
+        p = F.dropout(p, dropout_p)
+    return torch.matmul(p, vh).transpose(1, 2).contiguous()
 
 
 # =====================================================================================================

@@ -40,6 +40,19 @@ void zero1_adam_push(std::vector<int64_t> grads, std::vector<int64_t> params, st
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
              int64_t rank, int64_t tp, bool b_kmajor);
+void grouped_gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, const at::Tensor& block_expert, bool b_kmajor);
+void grouped_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor& out, const at::Tensor& offsets, bool accumulate);
+std::vector<at::Tensor> layernorm_fwd(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& b,
+                                      double eps, bool one_plus);
+std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w,
+                                      const at::Tensor& mean, const at::Tensor& rstd, bool one_plus);
+at::Tensor bias_act_fwd(const at::Tensor& x, const c10::optional<at::Tensor>& bias, int64_t mode);
+at::Tensor bias_act_bwd(const at::Tensor& dout, const at::Tensor& x, const c10::optional<at::Tensor>& bias, int64_t mode);
+at::Tensor scale_mask_softmax_fwd(const at::Tensor& x, double scale, bool causal, int64_t window, int64_t q_offset);
+at::Tensor scale_mask_softmax_bwd(const at::Tensor& dy, const at::Tensor& y, double scale);
+std::vector<at::Tensor> bias_dropout_add_fwd(const at::Tensor& x, const c10::optional<at::Tensor>& bias,
+                                             const at::Tensor& residual, double p);
+at::Tensor dropout_bwd(const at::Tensor& dout, const at::Tensor& mask, double p);
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
@@ -61,4 +74,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("zero1_reduce", &zero1_reduce, "ZeRO-1 gradient reduce-scatter by peer pulls");
   m.def("zero1_adam_push", &zero1_adam_push, "partitioned AdamW + parameter all-gather by peer pushes");
   m.def("gemm_rs", &gemm_rs, "fused tcgen05 GEMM -> reduce-scatter over peer memory");
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("bias_act_fwd", &bias_act_fwd, "fused bias + activation (gelu/geglu/reglu/swiglu/relu/squared-relu/silu)");
+  m.def("bias_act_bwd", &bias_act_bwd);
+  m.def("scale_mask_softmax_fwd", &scale_mask_softmax_fwd, "fused scale + causal/window mask + softmax");
+  m.def("scale_mask_softmax_bwd", &scale_mask_softmax_bwd);
+  m.def("bias_dropout_add_fwd", &bias_dropout_add_fwd, "residual + dropout(x + bias)");
+  m.def("dropout_bwd", &dropout_bwd);
+  m.def("grouped_gemm", &grouped_gemm, "per-expert tcgen05 GEMM over 128-row-padded token groups (dropless MoE)");
+  m.def("grouped_wgrad", &grouped_wgrad, "per-expert weight-gradient GEMM with device-side row ranges");
 }

@@ -59,6 +59,16 @@ struct NoGate {
   __device__ __forceinline__ void tile_done(int /*m_blk*/) const {}
 };
 
+// Grouped (per-expert) GEMMs specialise this trait.  A grouped gate provides
+//   bool tile_info(m_blk, a_m0, b_group, kb_begin, kb_count)
+// returning false for tiles that must be skipped (padding blocks, experts without tokens), the row coordinate
+// of the A tile, the expert whose B matrix the tile multiplies (3-D tensor map when `b_3d`) and the K range.
+template <class Gate>
+struct gate_traits {
+  static constexpr bool grouped = false;
+  static constexpr bool b_3d = false;
+};
+
 __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, int& n_blk) {
   const int per_group = p.group_m * p.num_n_blocks;
   const int g = t / per_group;
@@ -75,6 +85,7 @@ template <bool A_MN, bool B_MN, int OUT, class TileGate = NoGate>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a, const CUtensorMap* __restrict__ tma_b,
                                           const CUtensorMap* __restrict__ tma_c, const Params& p, uint8_t* smem_raw,
                                           const TileGate& gate, int cta_first_tile, int cta_tile_stride) {
+  using GT = gate_traits<TileGate>;
   const uint32_t warp_idx = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
 
@@ -121,10 +132,20 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
         int m_blk, n_blk;
         tile_coords(p, t, m_blk, n_blk);
         gate.wait_m(m_blk);
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-        for (int kbi = 0; kbi < num_k_blocks; ++kbi) {
-          int kb = kbi + p.k_first;
-          if (kb >= num_k_blocks) kb -= num_k_blocks;
+        int m0 = m_blk * BLOCK_M;
+        const int n0 = n_blk * BLOCK_N;
+        int b_group = 0, kb_begin = 0, tile_k_blocks = num_k_blocks;
+        if constexpr (GT::grouped) {
+          if (!gate.tile_info(m_blk, m0, b_group, kb_begin, tile_k_blocks)) continue;
+        }
+        for (int kbi = 0; kbi < tile_k_blocks; ++kbi) {
+          int kb;
+          if constexpr (GT::grouped) {
+            kb = kb_begin + kbi;
+          } else {
+            kb = kbi + p.k_first;
+            if (kb >= num_k_blocks) kb -= num_k_blocks;
+          }
           gate.wait_k(kb);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
@@ -138,7 +159,16 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
             for (int i = 0; i < BLOCK_M / 64; ++i)                                  // boxes {64 m, 64 k}
               tma_load_2d(sa + i * (64 * BLOCK_K * 2), tma_a, &full_bar[stage], m0 + i * 64, k0);
           }
-          if constexpr (!B_MN) {
+          if constexpr (GT::b_3d) {
+            // stacked per-expert B: third coordinate selects the expert, OOB rows/cols zero-fill per expert
+            if constexpr (!B_MN) {
+              tma_load_3d(sb, tma_b, &full_bar[stage], k0, n0, b_group);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BLOCK_N / 64; ++i)
+                tma_load_3d(sb + i * (64 * BLOCK_K * 2), tma_b, &full_bar[stage], n0 + i * 64, k0, b_group);
+            }
+          } else if constexpr (!B_MN) {
             tma_load_2d(sb, tma_b, &full_bar[stage], k0, n0);                       // box {64 k, 256 n}
           } else {
 #pragma unroll
@@ -154,10 +184,16 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
     constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
+      int tile_k_blocks = num_k_blocks;
+      if constexpr (GT::grouped) {
+        int m_blk, n_blk, m0, b_group, kb_begin;
+        tile_coords(p, t, m_blk, n_blk);
+        if (!gate.tile_info(m_blk, m0, b_group, kb_begin, tile_k_blocks)) continue;
+      }
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
+      for (int kb = 0; kb < tile_k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (elect_one()) {
@@ -173,7 +209,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
             umma_f16<1>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+          if (kb == tile_k_blocks - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -194,6 +230,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
     for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
       int m_blk, n_blk;
       tile_coords(p, t, m_blk, n_blk);
+      if constexpr (GT::grouped) {
+        int m0, b_group, kb_begin, nkb;
+        if (!gate.tile_info(m_blk, m0, b_group, kb_begin, nkb)) continue;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BLOCK_N;

@@ -10,6 +10,10 @@ _OPTIMIZERS = {
     "fused_adam": ("adamw", {}),
     "adam": ("adam", {}),
     "sgd": ("sgd", {}),
+    "adamax": ("adamax", {}),
+    "adagrad": ("adagrad", {}),
+    "rmsprop": ("rmsprop", {}),
+    "novograd": ("novograd", {}),
 }
 
 

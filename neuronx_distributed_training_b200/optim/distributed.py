@@ -41,7 +41,7 @@ def _align(n: int, a: int) -> int:
 
 
 class DistributedOptimizer:
-    """AdamW / Adam / SGD over flat buffers.
+    """AdamW / Adam / SGD / Adamax / Adagrad / RMSprop / NovoGrad over flat buffers.
 
     Args:
         param_groups: list of dicts ``{"params": [...], "weight_decay": .., "lr": ..}``.
@@ -140,7 +140,10 @@ class DistributedOptimizer:
         need_master = self.master_weights and pdtype != torch.float32
         self.master = self.param_buffer[self.shard_lo:self.shard_hi].float() if need_master else None
         self.exp_avg = torch.zeros(n, dtype=self.state_dtype, device=dev)
-        self.exp_avg_sq = torch.zeros(n, dtype=self.state_dtype, device=dev) if self.algorithm in ("adamw", "adam") else None
+        two_buffers = self.algorithm in ("adamw", "adam", "adamax", "adagrad", "rmsprop")
+        self.exp_avg_sq = torch.zeros(n, dtype=self.state_dtype, device=dev) if two_buffers else None
+        # NovoGrad keeps ONE second-moment scalar per tensor (layer-wise normalisation)
+        self.layer_v = torch.zeros(len(self.params), dtype=torch.float32, device=dev) if self.algorithm == "novograd" else None
         self.state = {"step": 0}
 
     def rebind_buffers(self, new_param_buffer: torch.Tensor, new_grad_buffer: torch.Tensor) -> None:
@@ -251,6 +254,8 @@ class DistributedOptimizer:
         clip = torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0) if self.max_grad_norm is not None else None
         gshard = self._gshard
         pshard = self.param_buffer[self.shard_lo:self.shard_hi]
+        if self.algorithm == "novograd":
+            self._novograd_layer_moments(gshard, clip)
         for s, lo, hi in self._seg_ranges():
             g = self.param_groups[s.group_idx]
             self._update(pshard[lo:hi], gshard[lo:hi], lo, hi, g, clip)
@@ -274,6 +279,51 @@ class DistributedOptimizer:
                                 float(group["eps"]), wd_eff, self.step_count,
                                 grad_scale=scale if scale is not None else 1.0,
                                 stochastic_rounding=self.stochastic_rounding, seed=self.step_count * 7919 + lo)
+        elif self.algorithm in ("adamax", "adagrad", "rmsprop"):
+            gg = g.float() * (clip if clip is not None else 1.0)
+            p32 = master if master is not None else p.float()
+            if wd != 0.0:
+                gg = gg + wd * p32
+            eps = float(group["eps"])
+            if self.algorithm == "adamax":
+                b1, b2 = group["betas"]
+                m, u = self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi]
+                m.mul_(b1).add_(gg, alpha=1.0 - b1)
+                torch.maximum(u.mul_(b2), gg.abs().add_(eps), out=u)
+                p32.addcdiv_(m, u, value=-lr / (1.0 - b1 ** self.step_count))
+            elif self.algorithm == "adagrad":
+                acc = self.exp_avg_sq[lo:hi]
+                acc.addcmul_(gg, gg)
+                p32.addcdiv_(gg, acc.sqrt().add_(eps), value=-lr)
+            else:   # rmsprop (alpha = betas[1]-style smoothing constant; optional momentum)
+                alpha = float(group.get("alpha", 0.99))
+                sq = self.exp_avg_sq[lo:hi]
+                sq.mul_(alpha).addcmul_(gg, gg, value=1.0 - alpha)
+                upd = gg / sq.sqrt().add_(eps)
+                mom = float(group.get("momentum", 0.0))
+                if mom > 0.0:
+                    buf = self.exp_avg[lo:hi]
+                    buf.mul_(mom).add_(upd)
+                    upd = buf
+                p32.add_(upd, alpha=-lr)
+            if master is not None:
+                p.copy_(p32)
+            elif p32.data_ptr() != p.data_ptr():
+                p.copy_(p32)
+        elif self.algorithm == "novograd":
+            b1, _ = group["betas"]
+            p32 = master if master is not None else p.float()
+            gg = g.float() * (clip if clip is not None else 1.0)
+            denom = self._novograd_denom[lo:hi]
+            upd = gg / denom
+            if wd != 0.0:
+                upd = upd + wd * p32
+            if bool(group.get("grad_averaging", False)):
+                upd = upd * (1.0 - b1)
+            m = self.exp_avg[lo:hi]
+            m.mul_(b1).add_(upd)
+            p32.add_(m, alpha=-lr)
+            p.copy_(p32)
         elif self.algorithm == "sgd":
             gg = g.float() * (clip if clip is not None else 1.0)
             p32 = master if master is not None else p.float()
@@ -289,6 +339,33 @@ class DistributedOptimizer:
         else:
             raise ValueError(f"unsupported flat optimizer algorithm {self.algorithm}")
 
+    def _novograd_layer_moments(self, gshard: torch.Tensor, clip) -> None:
+        """Per-tensor ||g||^2 (summed over the ZeRO-1 shards that hold pieces of the tensor), EMA into ``layer_v`` and
+        expansion to a per-element denominator for this rank's shard."""
+        n = len(self.params)
+        sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        pieces = []
+        for i, (o, p) in enumerate(zip(self.offsets, self.params)):
+            lo, hi = max(o, self.shard_lo), min(o + p.numel(), self.shard_hi)
+            if lo < hi:
+                pieces.append((i, lo - self.shard_lo, hi - self.shard_lo))
+                sq[i] = gshard[lo - self.shard_lo:hi - self.shard_lo].float().pow(2).sum()
+        if clip is not None:
+            sq = sq * clip * clip
+        if self.zero1:
+            dist.all_reduce(sq, group=self.dp_group)
+        b2 = float(self.param_groups[0]["betas"][1])
+        if self.step_count <= 1:
+            self.layer_v.copy_(sq)
+        else:
+            self.layer_v.mul_(b2).add_(sq, alpha=1.0 - b2)
+        eps = float(self.param_groups[0]["eps"])
+        denom = torch.ones(self.shard_size, dtype=torch.float32, device=self.device)
+        d = self.layer_v.sqrt() + eps
+        for i, lo, hi in pieces:
+            denom[lo:hi] = d[i]
+        self._novograd_denom = denom
+
     # ------------------------------------------------------------------------------------------
     def state_dict(self) -> Dict[str, Any]:
         """This rank's shard (every DP rank saves its own under ZeRO-1)."""
@@ -300,6 +377,8 @@ class DistributedOptimizer:
             "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
             "layout": [(o, int(p.numel())) for o, p in zip(self.offsets, self.params)],
         }
+        if self.layer_v is not None:
+            sd["layer_v"] = self.layer_v
         return sd
 
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
@@ -311,6 +390,8 @@ class DistributedOptimizer:
         self.exp_avg.copy_(sd["exp_avg"])
         if self.exp_avg_sq is not None and sd.get("exp_avg_sq") is not None:
             self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        if self.layer_v is not None and sd.get("layer_v") is not None:
+            self.layer_v.copy_(sd["layer_v"])
         if self.master is not None:
             if sd.get("master") is not None:
                 self.master.copy_(sd["master"])

@@ -204,14 +204,23 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
 
 class _RowParallelLinearFn(torch.autograd.Function):
     """Z = RS_seq(A @ W^T) (or all-reduce without SP).  Backward: dA = AG_seq(dZ) @ W,
-    dW = AG_seq(dZ)^T @ A."""
+    dW = AG_seq(dZ)^T @ A.
+
+    ``pre_act="swiglu"``: the input is the fused gate||up activation and ``A = silu(gate) * up`` is computed
+    inside the node.  Only gate||up is saved; A is recomputed in backward (one bandwidth-bound kernel) instead
+    of being kept alive for the weight gradient -- selective recomputation of ``ActivationMultiplyMLP`` without
+    a checkpoint wrapper and without re-running any GEMM."""
 
     @staticmethod
-    def forward(ctx, x, weight, group, sequence_parallel, reduce_dtype, fused):
-        ctx.group, ctx.sp, ctx.fused = group, sequence_parallel, fused
+    def forward(ctx, x, weight, group, sequence_parallel, reduce_dtype, fused, pre_act=None):
+        ctx.group, ctx.sp, ctx.fused, ctx.pre_act = group, sequence_parallel, fused, pre_act
         ctx.x_shape = x.shape
         tp = ps.group_size(group)
         x2d = x.reshape(-1, x.shape[-1])
+        if pre_act == "swiglu":
+            x2d = ops.swiglu(x2d)
+        elif pre_act is not None:
+            raise ValueError(f"unknown pre_act {pre_act!r}")
         can_fuse = fused is not None and sequence_parallel and tp > 1 and x2d.dtype == torch.bfloat16 and \
             fused.ok(x2d.shape[0] // tp, x2d.shape[1], weight.shape[0]) and x2d.shape[0] % tp == 0
         ctx.can_fuse = can_fuse
@@ -236,6 +245,9 @@ class _RowParallelLinearFn(torch.autograd.Function):
         group, tp = ctx.group, ps.group_size(ctx.group)
         dy2d = dy.reshape(-1, dy.shape[-1])
         x2d = x.reshape(-1, x.shape[-1])
+        pre = x2d
+        if ctx.pre_act == "swiglu":
+            x2d = ops.swiglu(pre)                      # recompute A from the saved gate||up
         dx = dw = None
         if ctx.sp and tp > 1:
             if ctx.can_fuse and ctx.fused.prefer_ag_gemm(dy2d.shape[0], dy2d.shape[1], weight.shape[1]):
@@ -250,8 +262,11 @@ class _RowParallelLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = _wgrad(dy_total, x2d, weight)
         if dx is not None:
+            if ctx.pre_act == "swiglu":
+                del x2d
+                dx = ops.swiglu_backward(dx, pre)
             dx = dx.view(ctx.x_shape)
-        return dx, dw, None, None, None, None
+        return dx, dw, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -354,11 +369,12 @@ class RowParallelLinear(nn.Module):
             with torch.no_grad():
                 self.bias.zero_()
 
-    def forward(self, x: torch.Tensor):
+    def forward(self, x: torch.Tensor, pre_act: Optional[str] = None):
         if not self.input_is_parallel:
+            assert pre_act is None
             x = mp.scatter_to_tensor_model_parallel_region(x, self.group)
         y = _RowParallelLinearFn.apply(x, self.weight, self.group, self.sequence_parallel_enabled,
-                                       self.reduce_dtype, self.fused)
+                                       self.reduce_dtype, self.fused, pre_act)
         if self.skip_bias_add:
             return y, self.bias
         if self.bias is not None:

@@ -68,6 +68,9 @@ def apply_activation_checkpointing(model: nn.Module, spec: Union[None, str, Sequ
     targets -= skip
     for name, mod in model.named_modules():
         if type(mod).__name__ in targets:
-            checkpoint_wrap(mod)
+            # a module may implement its own (cheaper) recomputation, e.g. SwiGLU recomputed by its consumer
+            own = getattr(mod, "enable_recompute", None)
+            if own is None or not own():
+                checkpoint_wrap(mod)
             wrapped.append(name)
     return wrapped

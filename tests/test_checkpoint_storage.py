@@ -1,0 +1,68 @@
+"""Object-store checkpoint paths through a directory-backed store registered for the ``s3`` scheme."""
+import os
+
+import pytest
+import torch
+
+from neuronx_distributed_training_b200.checkpoint import io as ckpt
+from neuronx_distributed_training_b200.checkpoint import storage
+from neuronx_distributed_training_b200.parallel import state as ps
+
+
+@pytest.fixture()
+def fake_s3(tmp_path, monkeypatch):
+    ps.initialize_model_parallel(1, 1, 1)
+    root = tmp_path / "buckets"
+    storage.register_object_store("s3", lambda: storage.DirectoryStore(str(root)))
+    monkeypatch.setenv("NXDT_CKPT_STAGING", str(tmp_path / "staging"))
+    yield root
+    ckpt.finalize_checkpoint()
+    storage.register_object_store("s3", storage.S3Store)
+    ps.destroy_model_parallel()
+
+
+def _state():
+    torch.manual_seed(0)
+    return ({"w": torch.randn(4, 5), "nested": {"b": torch.arange(6).float()}},
+            {"step": 3, "exp_avg": torch.randn(20)}, {"global_step": 3, "note": "x"})
+
+
+@pytest.mark.parametrize("async_save,use_xser", [(False, True), (True, True), (False, False)])
+def test_save_load_roundtrip_through_object_store(fake_s3, async_save, use_xser):
+    m, o, uc = _state()
+    url = "s3://my-bucket/run1/checkpoints"
+    out = ckpt.save_checkpoint(url, "step_3", m, o, uc, use_xser=use_xser, async_save=async_save)
+    assert out == url + "/step_3"
+    ckpt.finalize_checkpoint()
+    assert ckpt.has_checkpoint(url, "step_3") and not ckpt.has_checkpoint(url, "step_4")
+    keys = storage.get_store(url).list(url + "/step_3")
+    assert any(k.endswith("/done") for k in keys) and any("/model/dp_rank_00_tp_rank_00_pp_rank_00.pt" in k for k in keys)
+    assert any("/optim/" in k for k in keys) and any(k.endswith("user_content.pt") for k in keys)
+    m2, o2, uc2 = ckpt.load_checkpoint(url, "step_3")
+    assert torch.equal(m2["w"], m["w"]) and torch.equal(m2["nested"]["b"], m["nested"]["b"])
+    assert torch.equal(o2["exp_avg"], o["exp_avg"]) and o2["step"] == 3 and uc2["note"] == "x"
+    # staging holds no leftover shard files
+    left = [f for _, _, fs in os.walk(os.environ["NXDT_CKPT_STAGING"]) for f in fs]
+    assert left == [], left
+    ckpt.remove_checkpoint(url + "/step_3", async_remove=False)
+    assert not ckpt.has_checkpoint(url, "step_3")
+
+
+def test_incomplete_remote_checkpoint_is_rejected(fake_s3):
+    m, o, uc = _state()
+    url = "s3://b/ck"
+    ckpt.save_checkpoint(url, "t", m, o, uc)
+    os.remove(fake_s3 / "b" / "ck" / "t" / "done")
+    with pytest.raises(FileNotFoundError):
+        ckpt.load_checkpoint(url, "t")
+
+
+def test_s3_without_boto3_gives_actionable_error(monkeypatch):
+    storage.register_object_store("s3", storage.S3Store)
+    try:
+        import boto3  # noqa: F401
+        pytest.skip("boto3 present")
+    except ImportError:
+        pass
+    with pytest.raises(RuntimeError, match="boto3"):
+        storage.get_store("s3://bucket/x")

@@ -198,3 +198,202 @@ def test_fused_cross_entropy(C):
     assert (loss - ref).abs().max().item() < 2e-3
     assert _rel_err(dlog, ref_in.grad) < 1e-2
     assert dlog[:7].abs().max().item() == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# grouped (per-expert) GEMM
+# ---------------------------------------------------------------------------------------------------
+def _grouped_case(counts, K, N, seed=0):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(seed)
+    counts = torch.tensor(counts, device="cuda")
+    n = int(counts.sum())
+    dest, be, offs, t_cap = ops.grouped_layout(counts, n)
+    x = torch.zeros(t_cap, K, device="cuda", dtype=torch.bfloat16)
+    x.index_copy_(0, dest, torch.randn(n, K, device="cuda").bfloat16())
+    w = (torch.randn(counts.numel(), K, N, device="cuda") * 0.05).bfloat16()
+    return x, w, be, offs, dest
+
+
+@pytest.mark.parametrize("counts,K,N", [([300, 0, 129, 1], 256, 512), ([128, 128], 128, 264), ([0, 0, 77], 384, 256),
+                                        ([513, 1000, 7, 255, 0, 64, 1, 130], 1024, 768)])
+def test_grouped_gemm_fwd_dgrad(C, counts, K, N):
+    x, w, be, offs, dest = _grouped_case(counts, K, N)
+    o = offs.tolist()
+    out = torch.full((x.shape[0], N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    C.grouped_gemm(x, w, out, be, False)
+    torch.cuda.synchronize()
+    for e in range(len(counts)):
+        if o[e + 1] > o[e]:
+            ref = x[o[e]:o[e + 1]].float() @ w[e].float()
+            assert _rel_err(out[o[e]:o[e + 1]], ref) < 6e-3, f"fwd expert {e}"
+    # blocks past the last expert are left untouched
+    assert torch.isnan(out[o[-1]:].float()).all()
+    # dgrad: dy [T, N] @ w[e]^T, w used as the K-major operand
+    dy = torch.zeros(x.shape[0], N, device="cuda", dtype=torch.bfloat16)
+    dy.index_copy_(0, dest, torch.randn(dest.numel(), N, device="cuda").bfloat16())
+    dx = torch.full((x.shape[0], K), float("nan"), device="cuda", dtype=torch.bfloat16)
+    C.grouped_gemm(dy, w, dx, be, True)
+    torch.cuda.synchronize()
+    for e in range(len(counts)):
+        if o[e + 1] > o[e]:
+            ref = dy[o[e]:o[e + 1]].float() @ w[e].float().t()
+            assert _rel_err(dx[o[e]:o[e + 1]], ref) < 6e-3, f"dgrad expert {e}"
+
+
+@pytest.mark.parametrize("counts,K,N", [([300, 0, 129, 1], 256, 512), ([0, 64, 0], 128, 264),
+                                        ([513, 1000, 7, 255, 0, 64, 1, 130], 1024, 768)])
+def test_grouped_wgrad(C, counts, K, N):
+    x, w, be, offs, dest = _grouped_case(counts, K, N, seed=1)
+    o = offs.tolist()
+    dy = torch.zeros(x.shape[0], N, device="cuda", dtype=torch.bfloat16)
+    dy.index_copy_(0, dest, torch.randn(dest.numel(), N, device="cuda").bfloat16())
+    E = len(counts)
+    ref = torch.stack([x[o[e]:o[e + 1]].float().t() @ dy[o[e]:o[e + 1]].float() for e in range(E)])
+    acc = torch.ones(E, K, N, device="cuda")
+    C.grouped_wgrad(x, dy, acc, offs, True)
+    C.grouped_wgrad(x, dy, acc, offs, True)
+    torch.cuda.synchronize()
+    assert _rel_err(acc, 1.0 + 2 * ref) < 1e-3
+    out = torch.zeros(E, K, N, device="cuda", dtype=torch.bfloat16)
+    C.grouped_wgrad(x, dy, out, offs, False)
+    torch.cuda.synchronize()
+    assert _rel_err(out, ref) < 6e-3
+    for e in range(E):
+        if o[e + 1] == o[e]:
+            assert (out[e] == 0).all() and (acc[e] == 1).all()
+
+
+def test_moe_grouped_matches_loop_on_gpu(monkeypatch):
+    from neuronx_distributed_training_b200.models.moe import ExpertMLPs
+    from neuronx_distributed_training_b200.parallel import state as ps
+    ps.initialize_model_parallel(1, 1, 1)
+    try:
+        torch.manual_seed(0)
+        counts = [700, 0, 129, 1, 300, 64, 5, 2000]
+        mlp = ExpertMLPs(8, 256, 512, glu=True, dtype=torch.bfloat16, device="cuda", init_std=0.05)
+        n = sum(counts)
+        x = torch.randn(n, 256, device="cuda").bfloat16().requires_grad_(True)
+        g = torch.randn(n, 256, device="cuda").bfloat16()
+        res = {}
+        for mode in ("off", "auto"):
+            monkeypatch.setenv("NXDT_MOE_GROUPED", mode)
+            for p in mlp.parameters():
+                p.grad = None
+            x.grad = None
+            y = mlp.forward_sorted(x, torch.tensor(counts, device="cuda"))
+            (y.float() * g.float()).sum().backward()
+            res[mode] = (y.detach(), x.grad, mlp.mlp_op.gate_up_proj.grad, mlp.mlp_op.down_proj.grad)
+        for a, b in zip(res["off"], res["auto"]):
+            assert _rel_err(b, a) < 1.5e-2
+    finally:
+        ps.destroy_model_parallel()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Megatron-family fused kernels
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,H,one_plus,bias", [(64, 1024, False, True), (1000, 4096, True, True), (33, 8192, False, False),
+                                                  (7, 264, True, False)])
+def test_layernorm_fwd_bwd(C, dtype, rows, H, one_plus, bias):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    x = (torch.randn(rows, H, device="cuda") * 2 + 0.5).to(dtype).requires_grad_(True)
+    w = (torch.randn(H, device="cuda") * 0.1 + (0.0 if one_plus else 1.0)).to(dtype).requires_grad_(True)
+    b = (torch.randn(H, device="cuda") * 0.1).to(dtype).requires_grad_(True) if bias else None
+    g = torch.randn(rows, H, device="cuda").to(dtype)
+    y = ops.layernorm(x, w, b, 1e-5, one_plus)
+    y.backward(g)
+    got = (y.detach(), x.grad, w.grad) + ((b.grad,) if bias else ())
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    br = b.detach().float().requires_grad_(True) if bias else None
+    yr = torch.nn.functional.layer_norm(xr, (H,), wr + 1.0 if one_plus else wr, br, 1e-5)
+    yr.backward(g.float())
+    ref = (yr.detach(), xr.grad, wr.grad) + ((br.grad,) if bias else ())
+    tol = 1.2e-2 if dtype == torch.bfloat16 else 1e-4
+    for a, r in zip(got, ref):
+        assert _rel_err(a, r) < tol
+
+
+@pytest.mark.parametrize("act", ["gelu", "geglu", "reglu", "swiglu", "relu", "squared-relu", "silu"])
+@pytest.mark.parametrize("dtype,use_bias", [(torch.bfloat16, True), (torch.float32, True), (torch.bfloat16, False)])
+def test_bias_act_fwd_bwd(C, act, dtype, use_bias):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(3, 130, 512, device="cuda").to(dtype).requires_grad_(True)
+    b = (torch.randn(512, device="cuda") * 0.2).to(dtype).requires_grad_(True) if use_bias else None
+    y = ops.bias_act(x, b, act)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr = x.detach().float().requires_grad_(True)
+    br = b.detach().float().requires_grad_(True) if use_bias else None
+    yr = ops.bias_act_ref(xr, br, act)
+    yr.backward(g.float())
+    tol = 1.2e-2 if dtype == torch.bfloat16 else 2e-4
+    assert y.shape == yr.shape
+    assert _rel_err(y, yr) < tol and _rel_err(x.grad, xr.grad) < tol
+    if use_bias:
+        assert _rel_err(b.grad, br.grad) < 2 * tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("Sq,Sk,causal,window,q_offset", [(128, 128, True, 0, 0), (96, 4096, True, 0, 4000),
+                                                          (256, 256, True, 64, 0), (40, 72, False, 0, 0),
+                                                          (64, 64, True, 0, -10)])
+def test_scale_mask_softmax(C, dtype, Sq, Sk, causal, window, q_offset):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    s = (torch.randn(2, 3, Sq, Sk, device="cuda") * 3).to(dtype).requires_grad_(True)
+    y = ops.scale_mask_softmax(s, 0.37, causal, window, q_offset)
+    g = torch.randn_like(y)
+    y.backward(g)
+    sr = s.detach().float().requires_grad_(True)
+    yr = ops.scale_mask_softmax_ref(sr, 0.37, causal, window, q_offset)
+    yr.backward(g.float())
+    tol = 1.2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert torch.isfinite(y.float()).all()
+    assert _rel_err(y, yr) < tol and _rel_err(s.grad, sr.grad) < 2 * tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_bias_dropout_add(C, dtype):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(512, 4, 1024, device="cuda").to(dtype).requires_grad_(True)
+    b = torch.randn(1024, device="cuda").to(dtype).requires_grad_(True)
+    r = torch.randn(512, 4, 1024, device="cuda").to(dtype).requires_grad_(True)
+    p = 0.25
+    torch.cuda.manual_seed(7)
+    y = ops.bias_dropout_add(x, b, r, p, True)
+    kept = ((y.float() - r.float()).abs() > 0)
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 5e-3
+    ref = r.float() + torch.where(kept, (x.float() + b.float()) / (1 - p), torch.zeros((), device="cuda"))
+    assert _rel_err(y, ref) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+    g = torch.randn_like(y)
+    y.backward(g)
+    assert _rel_err(r.grad, g) < 1e-6
+    assert _rel_err(x.grad, torch.where(kept, g.float() / (1 - p), torch.zeros((), device="cuda"))) < 1e-2
+    assert _rel_err(b.grad, x.grad.float().reshape(-1, 1024).sum(0)) < 2e-2
+    # same generator state -> same mask; different state -> different mask
+    torch.cuda.manual_seed(7)
+    y2 = ops.bias_dropout_add(x.detach(), b.detach(), r.detach(), p, True)
+    assert torch.equal(y2, y.detach())
+    y3 = ops.bias_dropout_add(x.detach(), b.detach(), r.detach(), p, True)
+    assert not torch.equal(y3, y2)
+    # inference / p = 0 path
+    y4 = ops.bias_dropout_add(x.detach(), b.detach(), r.detach(), p, False)
+    assert _rel_err(y4, r.float() + x.float() + b.float()) < 1e-2
+
+
+def test_attention_eager_matches_reference(C):
+    from neuronx_distributed_training_b200 import ops
+    torch.manual_seed(0)
+    q = torch.randn(2, 256, 8, 64, device="cuda").bfloat16()
+    k = torch.randn(2, 256, 2, 64, device="cuda").bfloat16()
+    v = torch.randn(2, 256, 2, 64, device="cuda").bfloat16()
+    for window in (None, 100):
+        o = ops.attention_eager(q, k, v, causal=True, window=window)
+        ref = ops.attention_ref(q, k, v, causal=True, window=window)
+        assert _rel_err(o, ref) < 2e-2

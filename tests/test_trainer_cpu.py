@@ -93,6 +93,23 @@ def test_activation_checkpointing_is_exact(tmp_path, gran, rec):
     assert losses["none"] == pytest.approx(losses["ckpt"], abs=1e-6)
 
 
+def test_swiglu_recompute_runs_inside_down_proj_node(tmp_path):
+    """Selecting ActivationMultiplyMLP keeps only gate||up: no checkpoint wrapper, identical losses."""
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    losses = {}
+    for tag, kw in (("none", {}), ("swiglu", {"activations_checkpoint_granularity": "selective",
+                                              "activations_checkpoint_recompute": ["ActivationMultiplyMLP"]})):
+        cfg = process_config(_cfg(str(tmp_path / tag), **kw), 1)
+        mod = HFLlamaModule(cfg, None); mod.setup(); mod.configure_optimizers(10)
+        ids = torch.randint(0, 128, (2, 32), generator=torch.Generator().manual_seed(0))
+        losses[tag] = [float(mod.training_step({"input_ids": ids, "labels": ids.clone()})) for _ in range(3)]
+        if tag == "swiglu":
+            acts = [m for m in mod.model.modules() if type(m).__name__ == "ActivationMultiplyMLP"]
+            assert len(acts) == 2 and all(m.recompute_in_consumer for m in acts)
+            assert not any(getattr(m, "_activation_checkpointed", False) for m in mod.model.modules())
+    assert losses["none"] == pytest.approx(losses["swiglu"], abs=1e-6)
+
+
 def test_unknown_recompute_class_and_exp_manager_keys(tmp_path):
     from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
     from neuronx_distributed_training_b200.utils.exp_manager import ExpManagerConfig
