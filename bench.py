@@ -252,7 +252,8 @@ def main():
                        "seq_len": args.seq_len, "parallelism": f"tp{tp}" + ("+sp" if tp > 1 else ""),
                        "precision": "bf16 compute, fp32 master weights + fp32 grad accumulation, AdamW fp32 state",
                        "recompute": recompute, "l2_policy": "inputs larger than L2 (weights+activations >> 126 MB per step)",
-                       "peak_mem_gb": round(mem_gb, 1), "final_loss": float(loss)},
+                       "peak_mem_gb": round(mem_gb, 1), "final_loss": float(loss),
+                       "cuda_graph": getattr(module, "_mb_graph", None) is not None},
             "clocks": clocks, "gpu_launches": launches,
         }
         if not args.no_e2e:

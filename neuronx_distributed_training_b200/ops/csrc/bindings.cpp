@@ -24,10 +24,10 @@ std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k,
 void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
              std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
              std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
-             bool accumulate, int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push);
+             bool accumulate, int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push, int64_t epoch_ptr);
 void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer,
              int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp,
-             int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push);
+             int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push, int64_t epoch_ptr);
 void fused_tp_set_debug(at::Tensor buf);
 at::Tensor zero1_reduce(std::vector<int64_t> grads, std::vector<int64_t> params, std::vector<int64_t> hs, int64_t rank,
                         int64_t epoch, at::Tensor gshard, int64_t shard_lo, bool grads_fp32, double scale,
@@ -39,7 +39,8 @@ void zero1_adam_push(std::vector<int64_t> grads, std::vector<int64_t> params, st
                      const at::Tensor& clip, bool sr, int64_t seed, at::Tensor done_ctr);
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
-             int64_t rank, int64_t tp, bool b_kmajor);
+             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr);
+void tp_barrier(int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t rank, int64_t tp, int64_t epoch_ptr);
 void grouped_gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, const at::Tensor& block_expert, bool b_kmajor);
 void grouped_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor& out, const at::Tensor& offsets, bool accumulate);
 std::vector<at::Tensor> layernorm_fwd(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& b,
@@ -71,6 +72,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");
   m.def("ag_only", &ag_only);
   m.def("fused_tp_set_debug", &fused_tp_set_debug);
+  m.def("tp_barrier", &tp_barrier, "all-peer barrier over the symmetric handshake slots (device-side epoch)");
   m.def("zero1_reduce", &zero1_reduce, "ZeRO-1 gradient reduce-scatter by peer pulls");
   m.def("zero1_adam_push", &zero1_adam_push, "partitioned AdamW + parameter all-gather by peer pushes");
   m.def("gemm_rs", &gemm_rs, "fused tcgen05 GEMM -> reduce-scatter over peer memory");

@@ -58,6 +58,7 @@ struct CommArgs {
   uint32_t* flags;                 // my ready flags (== flags_peer[rank])
   const uint8_t* x_peer[MAX_TP];   // pull mode: every rank's shard staged in its symmetric buffer (this parity)
   uint32_t epoch;
+  const uint32_t* epoch_ptr;       // != nullptr: the epoch lives on the device (CUDA-graph replay safe), see bump_epoch
   int rank, tp, rows_per_rank, row_bytes, num_comm_ctas;
   int push;                        // 1: owners push their shard to everybody; 0: consumers pull the peers' shards
 };
@@ -232,8 +233,10 @@ __device__ __forceinline__ void comm_cta(const CommArgs& a, uint8_t* smem_raw) {
 template <bool A_MN, bool B_MN, int OUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const Params p, const CommArgs comm, const int mode) {
+               const __grid_constant__ CUtensorMap tma_c, const Params p, const CommArgs comm_in, const int mode) {
   extern __shared__ uint8_t smem_raw[];
+  CommArgs comm = comm_in;
+  if (comm.epoch_ptr != nullptr) comm.epoch = ld_acquire_gpu(comm.epoch_ptr);
   if ((int)blockIdx.x < comm.num_comm_ctas) {
     comm_cta(comm, smem_raw);
     return;
@@ -247,8 +250,10 @@ ag_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // pure all-gather (same comm CTAs, no GEMM): used where the gathered tensor is needed on its own
-__global__ void __launch_bounds__(NUM_THREADS, 1) ag_only_kernel(const CommArgs comm) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) ag_only_kernel(const CommArgs comm_in) {
   extern __shared__ uint8_t smem_raw[];
+  CommArgs comm = comm_in;
+  if (comm.epoch_ptr != nullptr) comm.epoch = ld_acquire_gpu(comm.epoch_ptr);
   comm_cta(comm, smem_raw);
   // the kernel completes only when every peer's rows have landed in my gathered buffer
   const int bpr = comm.rows_per_rank / 128;
@@ -268,6 +273,7 @@ struct RsArgs {
   uint32_t* counter_local;
   __nv_bfloat16* out;                  // [rows_per_rank, N]
   uint32_t epoch;
+  const uint32_t* epoch_ptr;
   int rank, tp, rows_per_rank, N, num_n_blocks;
 };
 
@@ -306,8 +312,10 @@ struct RsGate {
 template <bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ RsMaps maps, const Params p, const RsArgs rs) {
+               const __grid_constant__ RsMaps maps, const Params p, const RsArgs rs_in) {
   extern __shared__ uint8_t smem_raw[];
+  RsArgs rs = rs_in;
+  if (rs.epoch_ptr != nullptr) rs.epoch = ld_acquire_gpu(rs.epoch_ptr);
   if (blockIdx.x == 0 && threadIdx.x == 0) send_handshake(rs.hs_peer, rs.rank, rs.tp, rs.epoch);
   RsGate gate{rs, maps.m};
   const CUtensorMap& tma_c = maps.m[0];
@@ -370,6 +378,22 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   dbg_stamp(3);
 }
 
+// Device-resident epoch: incremented by a one-thread kernel in stream order right before every fused op, so that a
+// captured CUDA graph advances the cross-GPU protocol on every replay (a host-passed epoch would be baked in).
+__global__ void bump_epoch_kernel(uint32_t* epoch) { *epoch = *epoch + 1u; }
+
+// All-peer barrier at the epoch held in `epoch_ptr`: every rank has finished everything it enqueued before this
+// kernel once the kernel completes on all ranks.  Placed at CUDA-graph boundaries, where the double-buffer parity of
+// the staged shards restarts.
+__global__ void tp_barrier_kernel(const RsArgs a) {
+  const uint32_t epoch = ld_acquire_gpu(a.epoch_ptr);
+  const int t = threadIdx.x;
+  if (t < a.tp) {
+    st_release_sys(a.hs_peer[t] + a.rank, epoch);
+    spin_until_ge_sys(a.hs_local + t, epoch, 100);
+  }
+}
+
 template <class K>
 static void set_smem(K kern) {
   // keyed by the function address: kernels of different template arguments share one signature type
@@ -392,7 +416,7 @@ static void fill_ptrs(const std::vector<int64_t>& v, int tp, void** dst) {
 void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
              std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
              std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
-             bool accumulate, int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push) {
+             bool accumulate, int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push, int64_t epoch_ptr) {
   using namespace fused;
   TORCH_CHECK(xg.is_cuda() && xg.is_contiguous() && xg.scalar_type() == at::kBFloat16 && xg.dim() == 2);
   TORCH_CHECK(tp >= 2 && tp <= MAX_TP);
@@ -414,6 +438,8 @@ void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::
   comm.flags = comm.flags_peer[rank];
   TORCH_CHECK(reinterpret_cast<uint8_t*>(xg.data_ptr()) == comm.xg_peer[rank], "xg must be my symmetric gathered buffer");
   comm.epoch = (uint32_t)epoch;
+  comm.epoch_ptr = reinterpret_cast<const uint32_t*>(epoch_ptr);
+  if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
   comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
   num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, (push ? 1 : (tp - 1)) * (rows_per_rank / 128)));
   comm.num_comm_ctas = num_comm_ctas;
@@ -458,7 +484,7 @@ void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::
 
 void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer,
              int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp,
-             int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push) {
+             int64_t num_comm_ctas, std::vector<int64_t> x_peer, bool push, int64_t epoch_ptr) {
   using namespace fused;
   const int M_total = xg.size(0), Kx = xg.size(1);
   const int rows_per_rank = M_total / tp;
@@ -477,6 +503,9 @@ void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_p
   comm.flags = comm.flags_peer[rank];
   TORCH_CHECK(reinterpret_cast<uint8_t*>(xg.data_ptr()) == comm.xg_peer[rank], "xg must be my symmetric gathered buffer");
   comm.epoch = (uint32_t)epoch;
+  comm.epoch_ptr = reinterpret_cast<const uint32_t*>(epoch_ptr);
+  if (epoch_ptr != 0)
+    bump_epoch_kernel<<<1, 1, 0, at::cuda::getCurrentCUDAStream()>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
   comm.rank = rank; comm.tp = tp; comm.rows_per_rank = rows_per_rank; comm.row_bytes = Kx * 2;
   num_comm_ctas = std::max<int64_t>(1, std::min<int64_t>(num_comm_ctas, (push ? 1 : (tp - 1)) * (rows_per_rank / 128)));
   comm.num_comm_ctas = num_comm_ctas;
@@ -488,7 +517,7 @@ void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_p
 // out[rows_per_rank, N] = reduce_scatter_rows( a[M_total, K] * op(b) )
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
-             int64_t rank, int64_t tp, bool b_kmajor) {
+             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr) {
   using namespace fused;
   TORCH_CHECK(a.is_cuda() && a.is_contiguous() && b.is_contiguous() && out.is_contiguous());
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16);
@@ -509,6 +538,8 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   rs.counter_local = rs.counter_peer[rank];
   rs.out = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
   rs.epoch = (uint32_t)epoch;
+  rs.epoch_ptr = reinterpret_cast<const uint32_t*>(epoch_ptr);
+  if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
   rs.rank = rank; rs.tp = tp; rs.rows_per_rank = rows_per_rank; rs.N = N;
   CUtensorMap ta, tb;
   make_operand_maps(a.data_ptr(), b.data_ptr(), M_total, N, K, true, b_kmajor, ta, tb);
@@ -528,6 +559,21 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
     kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, maps, p, rs);
   };
   if (b_kmajor) run(gemm_rs_kernel<false>); else run(gemm_rs_kernel<true>);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// all-peer barrier on the current stream (advances the device epoch); see tp_barrier_kernel
+void tp_barrier(int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t rank, int64_t tp, int64_t epoch_ptr) {
+  using namespace fused;
+  TORCH_CHECK(epoch_ptr != 0 && tp >= 2 && tp <= MAX_TP);
+  auto stream = at::cuda::getCurrentCUDAStream();
+  RsArgs a{};
+  fill_ptrs(hs_peer, tp, (void**)a.hs_peer);
+  a.hs_local = reinterpret_cast<uint32_t*>(hs_local_ptr);
+  a.epoch_ptr = reinterpret_cast<const uint32_t*>(epoch_ptr);
+  a.rank = rank; a.tp = tp;
+  bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
+  tp_barrier_kernel<<<1, 32, 0, stream>>>(a);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

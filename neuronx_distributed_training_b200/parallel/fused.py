@@ -69,6 +69,11 @@ class FusedTP:
         self.base_ptrs: List[int] = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(self.base_ptrs) == self.tp
         self.epoch = 0
+        # The protocol epoch lives on the device and is advanced by a one-thread kernel in front of every fused op, so
+        # a captured CUDA graph advances it on every replay (NXDT_FUSED_DEVICE_EPOCH=0: host-passed epoch, eager only).
+        self.device_epoch = os.environ.get("NXDT_FUSED_DEVICE_EPOCH", "1") != "0" and hasattr(ops.C(), "tp_barrier")
+        self.epoch_dev = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._epoch_ptr = int(self.epoch_dev.data_ptr()) if self.device_epoch else 0
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
 
@@ -76,6 +81,19 @@ class FusedTP:
     def _next_epoch(self) -> Tuple[int, int]:
         self.epoch += 1
         return self.epoch, self.epoch & 1
+
+    def graph_boundary(self) -> None:
+        """All-peer barrier on the current stream + restart of the staging parity.  Called at the start and at the end
+        of a captured region: inside a graph the buffer parities are baked in, so consecutive replays (or a replay
+        after eager calls) must not overlap across ranks."""
+        if not self.device_epoch:
+            raise RuntimeError("CUDA-graph capture of the fused TP kernels needs the device-side epoch")
+        if self.push:
+            raise RuntimeError("CUDA-graph capture of the fused TP kernels needs NXDT_AG_MODE=pull")
+        hs_local, hs_peer = self._hs()
+        ops._count()
+        ops.C().tp_barrier(hs_local, hs_peer, self.rank, self.tp, self._epoch_ptr)
+        self.epoch = 0
 
     def _hs(self) -> Tuple[int, List[int]]:
         return self.base_ptrs[self.rank] + _HS_OFF, [p + _HS_OFF for p in self.base_ptrs]
@@ -153,7 +171,7 @@ class FusedTP:
         ops._count()
         nc = self._comm_ctas(m * self.tp, N, K, m * (self.tp - 1) * K * 2)
         ops.C().ag_gemm(xg, x2d, w, out, out, xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank, self.tp,
-                        0, trans_b, False, nc, self._x_peer, self.push)
+                        0, trans_b, False, nc, self._x_peer, self.push, self._epoch_ptr)
         # NOTE: the gathered view lives in the double-buffered workspace: consume it before the second next fused call
         return (out, xg) if return_gathered else out
 
@@ -167,7 +185,7 @@ class FusedTP:
         ops._count()
         nc = self._comm_ctas(dy2d.shape[1], K, m * self.tp, m * (self.tp - 1) * K * 2)
         ops.C().ag_gemm(xg, x2d, xg, out, dy2d.contiguous(), xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank,
-                        self.tp, 1, True, accumulate, nc, self._x_peer, self.push)
+                        self.tp, 1, True, accumulate, nc, self._x_peer, self.push, self._epoch_ptr)
         return out
 
     def all_gather(self, x2d: torch.Tensor) -> torch.Tensor:
@@ -178,7 +196,7 @@ class FusedTP:
         hs_local, hs_peer = self._hs()
         ops._count()
         ops.C().ag_only(xg, x2d, xg_peer, flags_peer, hs_local, hs_peer, epoch, self.rank, self.tp, self.num_comm_ctas,
-                        self._x_peer, self.push)
+                        self._x_peer, self.push, self._epoch_ptr)
         return xg.clone()
 
     def gemm_reduce_scatter(self, a2d: torch.Tensor, w: torch.Tensor, trans_b: bool = True) -> torch.Tensor:
@@ -195,7 +213,8 @@ class FusedTP:
         out = torch.empty(rows, N, dtype=a2d.dtype, device=a2d.device)
         hs_local, hs_peer = self._hs()
         ops._count()
-        ops.C().gemm_rs(a2d.contiguous(), w, out, stage, cnt, hs_local, hs_peer, epoch, self.rank, self.tp, trans_b)
+        ops.C().gemm_rs(a2d.contiguous(), w, out, stage, cnt, hs_local, hs_peer, epoch, self.rank, self.tp, trans_b,
+                        self._epoch_ptr)
         return out
 
 

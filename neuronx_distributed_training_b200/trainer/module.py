@@ -15,6 +15,7 @@ from __future__ import annotations
 import contextlib
 import logging
 import math
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import torch
@@ -79,6 +80,14 @@ class BaseModelModule:
         self.throughput = Throughput(self.micro_batch_size, self.dims.dp, self.num_microbatches, 10)
         self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self._logged: Dict[str, float] = {}
+        # CUDA-graph replay of the micro-batch forward+backward (utils/cuda_graph.py): opt-in
+        fus = self.config.get("fusions", Config({})) if "fusions" in self.config else Config({})
+        env = os.environ.get("NXDT_CUDA_GRAPH")
+        self.use_cuda_graph = (bool(fus.get("cuda_graph", False)) if env is None else env == "1") \
+            and self.device.type == "cuda" and self.dims.pp == 1
+        self.cuda_graph_warmup_steps = int(os.environ.get("NXDT_CUDA_GRAPH_WARMUP", "1"))
+        self._mb_graph = None
+        self._eager_train_steps = 0
 
     # ---- to be provided by subclasses -------------------------------------------------------------
     def build_model(self) -> nn.Module:
@@ -164,6 +173,8 @@ class BaseModelModule:
         else:
             running = torch.zeros((), dtype=torch.float32, device=self.device)
             for mb in self.get_batch_iterator(batch):
+                if is_training and self._graphed_microbatch(mb, running):
+                    continue
                 with contextlib.nullcontext() if is_training else torch.no_grad():
                     with nvtx_range("forward"):
                         loss, _ = self.model_fwd_calc_loss(mb)
@@ -172,6 +183,8 @@ class BaseModelModule:
                     with nvtx_range("backward"):
                         loss.backward()
                 running += loss.detach()
+            if is_training:
+                self._eager_train_steps += 1
         # loss mean over CP then DP (reference base.py:387-395)
         cpg, dpg = ps.get_context_model_parallel_group(), ps.get_data_parallel_group()
         if ps.group_size(cpg) > 1:
@@ -181,6 +194,32 @@ class BaseModelModule:
             dist.all_reduce(running, group=dpg)
             running /= ps.group_size(dpg)
         return running
+
+    def _graphed_microbatch(self, mb: Dict[str, Any], running: torch.Tensor) -> bool:
+        """Replay (capturing first if needed) the CUDA graph of one micro-batch; False -> run it eagerly."""
+        if not self.use_cuda_graph or self._eager_train_steps < self.cuda_graph_warmup_steps:
+            return False
+        from ..utils.cuda_graph import MicrobatchGraph
+        if self._mb_graph is None:
+            def fwd_bwd(static_mb):
+                loss, _ = self.model_fwd_calc_loss(static_mb)
+                loss = loss.float() / self.num_microbatches
+                loss.backward()
+                return loss
+            g = MicrobatchGraph(fwd_bwd)
+            try:
+                g.capture(mb)
+            except Exception as e:  # noqa
+                log.warning("CUDA-graph capture of the micro-batch failed (%s); continuing eagerly", e)
+                self.use_cuda_graph = False
+                return False
+            self._mb_graph = g
+            if ps.get_rank() == 0:
+                log.info("captured the micro-batch forward+backward as a CUDA graph")
+        if not self._mb_graph.matches(mb):
+            return False
+        running += self._mb_graph.run(mb)
+        return True
 
     def training_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0) -> torch.Tensor:
         self.optimizer.zero_grad()

@@ -128,6 +128,51 @@ class TensorBoardLogger:
             self.writer.close()
 
 
+class WandbLogger:
+    """``exp_manager.create_wandb_logger`` + ``wandb_logger_kwargs`` (name / project / ...); needs the wandb package."""
+
+    def __init__(self, log_dir: str, **kw):
+        self.run = None
+        try:
+            import wandb
+            self.run = wandb.init(dir=log_dir, **kw)
+        except Exception as e:  # package missing or no network: keep training, scalars still go to metrics.jsonl
+            log.warning("wandb logger unavailable (%s); skipped", e)
+
+    def log_metrics(self, metrics: Dict[str, float], step: int):
+        if self.run is not None:
+            self.run.log(dict(metrics), step=step)
+
+    def close(self):
+        if self.run is not None:
+            self.run.finish()
+
+
+class MLflowLogger:
+    """``exp_manager.create_mlflow_logger`` + ``mlflow_logger_kwargs`` (experiment_name / tracking_uri / run_name ...)."""
+
+    def __init__(self, log_dir: str, experiment_name: Optional[str] = None, tracking_uri: Optional[str] = None,
+                 run_name: Optional[str] = None, tags: Optional[dict] = None, **unused):
+        self.mlflow = None
+        try:
+            import mlflow
+            mlflow.set_tracking_uri(tracking_uri or "file:" + os.path.join(log_dir, "mlruns"))
+            if experiment_name:
+                mlflow.set_experiment(experiment_name)
+            mlflow.start_run(run_name=run_name, tags=tags)
+            self.mlflow = mlflow
+        except Exception as e:
+            log.warning("mlflow logger unavailable (%s); skipped", e)
+
+    def log_metrics(self, metrics: Dict[str, float], step: int):
+        if self.mlflow is not None:
+            self.mlflow.log_metrics({k.replace("/", "_"): float(v) for k, v in metrics.items()}, step=step)
+
+    def close(self):
+        if self.mlflow is not None:
+            self.mlflow.end_run()
+
+
 class JsonlLogger:
     def __init__(self, path: str):
         self.f = open(path, "a")
@@ -316,8 +361,10 @@ class ExpManager:
             self.loggers.append(JsonlLogger(os.path.join(self.log_dir, "metrics.jsonl")))
             if c.create_tensorboard_logger:
                 self.loggers.append(TensorBoardLogger(self.log_dir, **(c.summary_writer_kwargs or {})))
-            if c.create_wandb_logger or c.create_mlflow_logger:
-                log.warning("wandb / mlflow loggers requested but those packages are not available offline; skipped")
+            if c.create_wandb_logger:
+                self.loggers.append(WandbLogger(self.log_dir, **(c.wandb_logger_kwargs or {})))
+            if c.create_mlflow_logger:
+                self.loggers.append(MLflowLogger(self.log_dir, **(c.mlflow_logger_kwargs or {})))
         self.timing = TimingCallback() if c.log_step_timing else None
         self.checkpoint_callback = None
         if c.create_checkpoint_callback:

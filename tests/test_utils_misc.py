@@ -1,0 +1,103 @@
+"""EMA, step profiler, throughput meter, MFU helper, optional W&B / MLflow loggers (CPU)."""
+import glob
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from neuronx_distributed_training_b200.optim import DistributedOptimizer
+from neuronx_distributed_training_b200.parallel import state as ps
+from neuronx_distributed_training_b200.utils import exp_manager as em
+from neuronx_distributed_training_b200.utils.ema import EMA
+from neuronx_distributed_training_b200.utils.perf_estimate import calculate_mfu, llama_flops_per_seq
+from neuronx_distributed_training_b200.utils.profiling import StepProfiler, nvtx_range
+from neuronx_distributed_training_b200.utils.throughput import Throughput
+
+
+@pytest.fixture(autouse=True)
+def _mp():
+    ps.initialize_model_parallel(1, 1, 1)
+    yield
+    ps.destroy_model_parallel()
+
+
+def test_ema_tracks_and_swaps():
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 4)
+    opt = DistributedOptimizer([{"params": list(lin.parameters())}], lr=0.1, zero1=False, max_grad_norm=None, dp_group="self")
+    ema = EMA(opt, decay=0.5)
+    w0 = lin.weight.detach().clone()
+    for step in range(1, 4):
+        opt.zero_grad()
+        lin(torch.ones(2, 4)).sum().backward()
+        opt.step()
+        ema.update(step)
+    w_live = lin.weight.detach().clone()
+    assert not torch.allclose(w_live, w0)
+    ema.swap_in()
+    w_avg = lin.weight.detach().clone()
+    # the average lies strictly between the initial and the live weights
+    assert ((w_avg - w0).abs() < (w_live - w0).abs() + 1e-7).all() and not torch.allclose(w_avg, w_live)
+    ema.swap_out()
+    assert torch.equal(lin.weight.detach(), w_live)
+    sd = ema.state_dict()
+    ema2 = EMA(opt, decay=0.9)
+    ema2.load_state_dict(sd)
+    assert torch.equal(ema2.shadow, ema.shadow) and ema2.decay == 0.5
+
+
+def test_step_profiler_writes_a_trace(tmp_path):
+    p = StepProfiler(1, 3, str(tmp_path))
+    for step in range(5):
+        p.step(step)
+        with nvtx_range("work"):
+            torch.randn(16, 16) @ torch.randn(16, 16)
+    assert glob.glob(str(tmp_path / "trace_steps_1_3.json"))
+    assert StepProfiler(0, 1, str(tmp_path / "x"), rank=3).step(0) is None and not os.path.exists(tmp_path / "x")
+
+
+def test_throughput_window_and_mfu():
+    t = Throughput(batch_size=2, world_size_dp=4, grad_accum=8, moving_avg_window_size=3)
+    vals = [t.get_throughput() for _ in range(5)]
+    assert all(v >= 0 for v in vals) and t.seqs_per_iteration == 64
+    f = llama_flops_per_seq(4096, 32, 8192, 128256, 14336, 32, 8)
+    assert 4.9e14 < f < 5.1e14                                       # BASELINE.md derived value (~5.0e14 per sequence)
+    assert calculate_mfu(2.0, f, 1, peak_tflops_per_gpu=1000.0) == pytest.approx(2.0 * f / 1e15)
+
+
+def test_optional_loggers_use_their_packages_when_present(tmp_path, monkeypatch):
+    calls = []
+    w = types.ModuleType("wandb")
+
+    class Run:
+        def log(self, m, step=None):
+            calls.append(("wandb", dict(m), step))
+
+        def finish(self):
+            calls.append(("wandb_finish",))
+    w.init = lambda dir=None, **kw: Run()
+    m = types.ModuleType("mlflow")
+    m.set_tracking_uri = lambda u: calls.append(("uri", u))
+    m.set_experiment = lambda n: calls.append(("exp", n))
+    m.start_run = lambda run_name=None, tags=None: calls.append(("start", run_name))
+    m.log_metrics = lambda d, step=None: calls.append(("mlflow", d, step))
+    m.end_run = lambda: calls.append(("end",))
+    monkeypatch.setitem(sys.modules, "wandb", w)
+    monkeypatch.setitem(sys.modules, "mlflow", m)
+    a = em.WandbLogger(str(tmp_path), project="p")
+    a.log_metrics({"loss": 1.0}, 3)
+    a.close()
+    b = em.MLflowLogger(str(tmp_path), experiment_name="e", run_name="r")
+    b.log_metrics({"a/b": 2}, 4)
+    b.close()
+    assert ("wandb", {"loss": 1.0}, 3) in calls and ("mlflow", {"a_b": 2.0}, 4) in calls and ("end",) in calls
+
+
+def test_optional_loggers_degrade_without_their_packages(tmp_path, monkeypatch):
+    monkeypatch.setitem(sys.modules, "wandb", None)      # import raises ImportError
+    monkeypatch.setitem(sys.modules, "mlflow", None)
+    a, b = em.WandbLogger(str(tmp_path)), em.MLflowLogger(str(tmp_path))
+    a.log_metrics({"x": 1.0}, 0); b.log_metrics({"x": 1.0}, 0)
+    a.close(); b.close()
