@@ -39,9 +39,13 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "baseline", "reference"])
     ap.add_argument("--global-batch", type=int, default=int(os.environ.get("NXDT_BENCH_GBS", "8")))
     ap.add_argument("--seq-len", type=int, default=8192)
-    ap.add_argument("--layers", type=int, default=32, help="debug only; the reported config uses 32")
+    ap.add_argument("--layers", type=int, default=0, help="debug only (0 = the model's own depth, which is what the "
+                                                          "reported config uses)")
     ap.add_argument("--model", default="llama3_8b")
     ap.add_argument("--recompute", default=os.environ.get("NXDT_BENCH_RECOMPUTE", "auto"))
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel size (default: all GPUs, the headline config)")
+    ap.add_argument("--pp", type=int, default=1, help="pipeline-parallel size (BASELINE config 3: --model llama2_7b "
+                                                      "--tp 2 --pp 2 on 8 GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -134,8 +138,11 @@ def main():
     os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
     if world > 1:
         ps.init_distributed("nccl")
-    tp = world
-    ps.initialize_model_parallel(tensor_model_parallel_size=tp)
+    tp = args.tp or world
+    pp = args.pp
+    assert world % (tp * pp) == 0, f"world {world} not divisible by tp*pp = {tp * pp}"
+    dp = world // (tp * pp)
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp, pipeline_model_parallel_size=pp)
     if args.impl == "baseline":
         ops.set_backend("torch")
     recompute = args.recompute
@@ -154,11 +161,12 @@ def main():
         "trainer": {"devices": world, "num_nodes": 1, "max_steps": 100000, "log_every_n_steps": 1000000,
                     "gradient_clip_val": 1.0},
         "exp_manager": {"create_checkpoint_callback": False, "create_tensorboard_logger": False},
-        "distributed_strategy": {"tensor_model_parallel_size": tp, "pipeline_model_parallel_size": 1,
+        "distributed_strategy": {"tensor_model_parallel_size": tp, "pipeline_model_parallel_size": pp,
                                  "zero1": True, "sequence_parallel": tp > 1, "kv_replicator": 1},
         "data": {"micro_batch_size": 1, "global_batch_size": args.global_batch, "synthetic": True},
         "model": {"model_config": args.model, "encoder_seq_length": args.seq_len,
-                  "max_position_embeddings": args.seq_len, "num_layers": args.layers, "qkv_linear": True,
+                  "max_position_embeddings": args.seq_len, **({"num_layers": args.layers} if args.layers else {}),
+                  "qkv_linear": True,
                   "fuse_qkv": True, "activations_checkpoint_granularity": gran,
                   "activations_checkpoint_recompute": rec_list,
                   "fusions": {"flash_attention": True, "linear_cross_entropy": True},
@@ -170,7 +178,7 @@ def main():
     module = HFLlamaModule(cfg, None)
     module.setup("fit")
     module.configure_optimizers(100000)
-    if args.impl == "native" and world > 1:
+    if args.impl == "native" and tp > 1:
         try:
             from neuronx_distributed_training_b200.parallel.fused import enable_fused_tp
             enable_fused_tp(module.model)
@@ -242,14 +250,18 @@ def main():
     if rank == 0:
         value = tokens_per_step * args.steps / (dev_ms / 1e3)
         out = {
-            "metric": "Llama-3-8B training tokens/sec (whole job, device-timed, max over ranks)",
+            "metric": ("Llama-3-8B" if args.model == "llama3_8b" else args.model)
+                      + " training tokens/sec (whole job, device-timed, max over ranks)",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
             "impl": args.impl,
-            "config": {"model": "llama3-8b" if args.layers == 32 else f"llama3-8b-{args.layers}L",
+            "config": {"model": (args.model.replace("_", "-") if args.layers in (0, hf.num_hidden_layers)
+                                 else f"{args.model.replace('_', '-')}-{args.layers}L"),
                        "global_batch": args.global_batch, "micro_batch": 1,
-                       "seq_len": args.seq_len, "parallelism": f"tp{tp}" + ("+sp" if tp > 1 else ""),
+                       "seq_len": args.seq_len,
+                       "parallelism": f"tp{tp}" + ("+sp" if tp > 1 else "") + (f"+pp{pp}" if pp > 1 else "")
+                                      + (f"+dp{dp}(zero1)" if dp > 1 else ""),
                        "precision": "bf16 compute, fp32 master weights + fp32 grad accumulation, AdamW fp32 state",
                        "recompute": recompute, "l2_policy": "inputs larger than L2 (weights+activations >> 126 MB per step)",
                        "peak_mem_gb": round(mem_gb, 1), "final_loss": float(loss),

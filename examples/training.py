@@ -17,7 +17,11 @@ from neuronx_distributed_training_b200.utils.exp_manager import exp_manager
 
 def build_data_module(cfg, trainer):
     source = cfg.get("model_source", "hf")
-    if cfg.get("model_alignment_strategy", None) is not None:
+    if cfg.get("model_alignment_strategy", None) is not None or \
+            (cfg.data.get("use_sft_style_data_module", False) and cfg.data.get("train_dir", None)):
+        # the Megatron SFT config selects the HF-style (jsonl / arrow) data module with data.use_sft_style_data_module
+        if cfg.get("model_alignment_strategy", None) is None:
+            cfg["model_alignment_strategy"] = Config({"sft": Config({"packing": bool(cfg.data.get("packing", False))})})
         from neuronx_distributed_training_b200.data.alignment import ModelAlignmentDataModule
         return ModelAlignmentDataModule(cfg, trainer)
     if cfg.data.get("synthetic", False) or (source == "hf" and not cfg.data.get("train_dir", None)) \

@@ -54,6 +54,8 @@ at::Tensor scale_mask_softmax_bwd(const at::Tensor& dy, const at::Tensor& y, dou
 std::vector<at::Tensor> bias_dropout_add_fwd(const at::Tensor& x, const c10::optional<at::Tensor>& bias,
                                              const at::Tensor& residual, double p);
 at::Tensor dropout_bwd(const at::Tensor& dout, const at::Tensor& mask, double p);
+at::Tensor embedding_fwd(const at::Tensor& ids, const at::Tensor& w, int64_t vocab_start, bool seq_first);
+void embedding_bwd_(at::Tensor dw, const at::Tensor& ids, const at::Tensor& g, int64_t vocab_start, bool seq_first);
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
@@ -76,6 +78,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("zero1_reduce", &zero1_reduce, "ZeRO-1 gradient reduce-scatter by peer pulls");
   m.def("zero1_adam_push", &zero1_adam_push, "partitioned AdamW + parameter all-gather by peer pushes");
   m.def("gemm_rs", &gemm_rs, "fused tcgen05 GEMM -> reduce-scatter over peer memory");
+  m.def("embedding_fwd", &embedding_fwd, "vocab-parallel embedding lookup (optionally sequence-first output)");
+  m.def("embedding_bwd_", &embedding_bwd_, "scatter-add of token gradients into the fp32 main_grad rows");
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);
   m.def("bias_act_fwd", &bias_act_fwd, "fused bias + activation (gelu/geglu/reglu/swiglu/relu/squared-relu/silu)");

@@ -5,15 +5,18 @@
 //                            the remaining CTAs run the tcgen05 GEMM, whose TMA producer waits (acquire) on the
 //                            flag of the rows a tile / k-block needs.  Tile order is rotated so every rank starts
 //                            on its own shard and walks the ring, i.e. transfer and math overlap block by block.
-//   GEMM -> reduce-scatter : the GEMM epilogue writes each finished partial tile straight into the staging
-//                            buffer of the rank that owns those rows (st.global to a peer-mapped pointer) and
-//                            bumps that rank's per-row-block arrival counter (red.release.sys); after its last
-//                            tile every CTA turns into a reducer that sums the TP partial slabs of the row-blocks
-//                            that have fully arrived (fp32 accumulate) into the local output.
-// Cross-GPU ordering: one monotonically increasing epoch per call.  Kernels start with an all-peer
-// handshake (st.release.sys of the epoch into every peer's slot, ld.acquire.sys on the own slots) which both
-// publishes "my input shard is ready" and proves "the peer has finished the call that last used this
-// double-buffer parity", so buffers are reused safely two calls later.
+//   GEMM -> reduce-scatter : the GEMM epilogue TMA-stores each finished partial tile straight into the staging
+//                            buffer of the rank that owns those rows (one tensor map per destination over
+//                            peer-mapped memory) and, one tile later, bumps that rank's per-row-block arrival
+//                            counter (red.release.sys); after its last tile every CTA turns into a reducer that
+//                            sums the TP partial slabs of the row-blocks that have fully arrived (fp32 accumulate)
+//                            into the local output.
+// Cross-GPU ordering: one monotonically increasing epoch per call (flags and handshake slots compare >=).  Kernels
+// start with an all-peer handshake (st.release.sys of the epoch into every peer's slot, ld.acquire.sys on the own
+// slots) which both publishes "my input shard is ready" and proves "the peer has finished the call that last used
+// this double-buffer parity", so buffers are reused safely two calls later.  The epoch can live on the device
+// (epoch_ptr, advanced by bump_epoch_kernel in stream order) so that the kernels replay correctly inside a CUDA
+// graph; tp_barrier_kernel closes a captured region.  All cross-GPU spins are bounded and trap instead of hanging.
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>

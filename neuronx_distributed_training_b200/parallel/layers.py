@@ -558,11 +558,32 @@ class GQAQKVColumnParallelLinear(nn.Module):
         return q, k, v
 
 
+def _native_embedding_ok(ids: torch.Tensor, weight: torch.Tensor) -> bool:
+    return ids.is_cuda and ids.dim() == 2 and ids.dtype == torch.long and weight.dtype == torch.bfloat16 \
+        and weight.shape[1] % 8 == 0 and ops.get_backend() != "torch" and ops.C() is not None \
+        and hasattr(ops.C(), "embedding_fwd")
+
+
 class _VocabParallelEmbeddingFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, weight, vocab_start, vocab_end, group, sequence_parallel):
         ctx.group, ctx.sp = group, sequence_parallel
         tp = ps.group_size(group)
+        ctx.native = _native_embedding_ok(ids, weight)
+        ctx.num_emb = weight.shape[0]
+        ctx.wdtype = weight.dtype
+        if ctx.native:
+            # masked lookup in one kernel, written sequence-first when the reduce-scatter follows
+            ids = ids.contiguous()
+            seq_first = bool(tp > 1 and sequence_parallel)
+            ops._count()
+            out = ops.C().embedding_fwd(ids, weight, vocab_start if tp > 1 else 0, seq_first)
+            ctx.vocab_start = vocab_start if tp > 1 else 0
+            ctx.weight = weight
+            ctx.save_for_backward(ids)
+            if tp > 1:
+                out = mp.reduce_scatter_dim0(out, group) if sequence_parallel else mp.all_reduce(out, group)
+            return out
         if tp > 1:
             mask = (ids < vocab_start) | (ids >= vocab_end)
             local = (ids - vocab_start).masked_fill(mask, 0)
@@ -572,8 +593,6 @@ class _VocabParallelEmbeddingFn(torch.autograd.Function):
         if mask is not None:
             out = out.masked_fill(mask.unsqueeze(-1), 0.0)
         ctx.save_for_backward(local, mask)
-        ctx.num_emb = weight.shape[0]
-        ctx.wdtype = weight.dtype
         if tp > 1:
             if sequence_parallel:
                 # ids are [B, S] -> emit sequence-first [S/TP, B, H] directly
@@ -584,8 +603,25 @@ class _VocabParallelEmbeddingFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        local, mask = ctx.saved_tensors
         tp = ps.group_size(ctx.group)
+        if ctx.native:
+            (ids,) = ctx.saved_tensors
+            seq_first = bool(tp > 1 and ctx.sp)
+            if seq_first:
+                g = mp.all_gather_dim0(g, ctx.group)                      # [S, B, H]
+            g = g.contiguous()
+            weight = ctx.weight
+            main_grad = getattr(weight, "main_grad", None)
+            if main_grad is not None and main_grad.dtype == torch.float32 and g.dtype == torch.bfloat16:
+                ops._count()
+                ops.C().embedding_bwd_(main_grad, ids, g, ctx.vocab_start, seq_first)
+                weight.grad_added_to_main_grad = True
+                return None, None, None, None, None, None
+            dw = torch.zeros(ctx.num_emb, g.shape[-1], dtype=torch.float32, device=g.device)
+            ops._count()
+            ops.C().embedding_bwd_(dw, ids, g.to(torch.bfloat16), ctx.vocab_start, seq_first)
+            return None, dw.to(ctx.wdtype), None, None, None, None
+        local, mask = ctx.saved_tensors
         if tp > 1 and ctx.sp:
             g = mp.all_gather_dim0(g, ctx.group).transpose(0, 1)
         if mask is not None:

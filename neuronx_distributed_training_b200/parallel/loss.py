@@ -196,7 +196,9 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
         gw = None
         if dw_acc is not None:
             if ctx.dw_is_main:
-                ctx.weight.main_grad.add_(dw_acc, alpha=float(g_loss))
+                # scale by the upstream scalar on the device: no host read of g_loss (a sync here would stall the
+                # launch queue once per micro-batch and forbid CUDA-graph capture), no [V, H] temporary
+                ctx.weight.main_grad.addcmul_(dw_acc, g_loss.to(dw_acc.dtype))
                 ctx.weight.grad_added_to_main_grad = True
             else:
                 gw = (dw_acc * g_loss).to(ctx.wdtype)

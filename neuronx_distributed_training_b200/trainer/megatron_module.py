@@ -120,9 +120,18 @@ class MegatronGPTModel(MegatronBaseModel):
 
     def model_fwd_calc_loss(self, batch: Dict[str, torch.Tensor]):
         ids = batch.get("tokens", batch.get("input_ids"))
-        out = self.model(input_ids=ids, labels=batch["labels"], position_ids=batch.get("position_ids"),
+        labels = batch["labels"]
+        if "tokens" not in batch and self._hf_style_batches():
+            # HF-style (SFT / alignment) data modules hand out labels aligned with the inputs and -100 on masked
+            # positions; the Megatron model scores next-token labels, so shift here
+            labels = torch.cat([labels[:, 1:], labels.new_full((labels.shape[0], 1), -100)], dim=1)
+        out = self.model(input_ids=ids, labels=labels, position_ids=batch.get("position_ids"),
                          loss_mask=batch.get("loss_mask"))
         return out[0], out[1]
+
+    def _hf_style_batches(self) -> bool:
+        d = self.cfg.get("data", Config({})) if "data" in self.cfg else Config({})
+        return self.cfg.get("model_alignment_strategy", None) is not None or bool(d.get("use_sft_style_data_module", False))
 
     def to_device(self, batch):
         b = super().to_device(batch)

@@ -210,7 +210,8 @@ class BaseModelModule:
             try:
                 g.capture(mb)
             except Exception as e:  # noqa
-                log.warning("CUDA-graph capture of the micro-batch failed (%s); continuing eagerly", e)
+                log.warning("CUDA-graph capture of the micro-batch failed (%s); continuing eagerly", e,
+                            exc_info=os.environ.get("NXDT_CUDA_GRAPH_DEBUG", "0") == "1")
                 self.use_cuda_graph = False
                 return False
             self._mb_graph = g

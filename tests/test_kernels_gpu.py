@@ -364,9 +364,11 @@ def test_bias_dropout_add(C, dtype):
     b = torch.randn(1024, device="cuda").to(dtype).requires_grad_(True)
     r = torch.randn(512, 4, 1024, device="cuda").to(dtype).requires_grad_(True)
     p = 0.25
+    # the mask depends only on the generator state and the shape: read it off a run with a zero residual
+    torch.cuda.manual_seed(7)
+    kept = ops.bias_dropout_add(x.detach(), b.detach(), torch.zeros_like(r), p, True) != 0
     torch.cuda.manual_seed(7)
     y = ops.bias_dropout_add(x, b, r, p, True)
-    kept = ((y.float() - r.float()).abs() > 0)
     frac = kept.float().mean().item()
     assert abs(frac - (1 - p)) < 5e-3
     ref = r.float() + torch.where(kept, (x.float() + b.float()) / (1 - p), torch.zeros((), device="cuda"))
@@ -397,3 +399,44 @@ def test_attention_eager_matches_reference(C):
         o = ops.attention_eager(q, k, v, causal=True, window=window)
         ref = ops.attention_ref(q, k, v, causal=True, window=window)
         assert _rel_err(o, ref) < 2e-2
+
+
+@pytest.mark.parametrize("seq_first", [False, True])
+def test_vocab_parallel_embedding_kernels(C, seq_first):
+    torch.manual_seed(0)
+    B, S, H, V, start = 3, 200, 1024, 512, 256           # this "rank" owns vocab rows [256, 768)
+    ids = torch.randint(0, 1024, (B, S), device="cuda")
+    w = torch.randn(V, H, device="cuda").bfloat16()
+    out = C.embedding_fwd(ids, w, start, seq_first)
+    hit = (ids >= start) & (ids < start + V)
+    ref = torch.where(hit.unsqueeze(-1), w[(ids - start).clamp(0, V - 1)], torch.zeros((), device="cuda", dtype=torch.bfloat16))
+    if seq_first:
+        ref = ref.transpose(0, 1)
+    assert torch.equal(out, ref.contiguous())
+    g = torch.randn_like(out)
+    dw = torch.ones(V, H, device="cuda")
+    C.embedding_bwd_(dw, ids, g, start, seq_first)
+    gb = (g.transpose(0, 1) if seq_first else g).float()
+    expect = torch.ones(V, H, device="cuda")
+    expect.index_add_(0, (ids - start)[hit], gb[hit])
+    assert _rel_err(dw, expect) < 1e-5
+
+
+def test_parallel_embedding_module_accumulates_into_main_grad():
+    from neuronx_distributed_training_b200.parallel import state as ps
+    from neuronx_distributed_training_b200.parallel.layers import ParallelEmbedding
+    ps.initialize_model_parallel(1, 1, 1)
+    try:
+        torch.manual_seed(0)
+        emb = ParallelEmbedding(1000, 256, dtype=torch.bfloat16, device="cuda")
+        ids = torch.randint(0, 1000, (2, 64), device="cuda")
+        emb.weight.main_grad = torch.zeros(1000, 256, device="cuda")
+        out = emb(ids)
+        assert torch.equal(out, emb.weight.detach()[ids])
+        g = torch.randn_like(out)
+        out.backward(g)
+        assert emb.weight.grad is None and emb.weight.grad_added_to_main_grad
+        ref = torch.zeros(1000, 256, device="cuda").index_add_(0, ids.reshape(-1), g.reshape(-1, 256).float())
+        assert _rel_err(emb.weight.main_grad, ref) < 1e-5
+    finally:
+        ps.destroy_model_parallel()
