@@ -150,7 +150,8 @@ def main():
         # single GPU holds the full fp32 optimizer state (144 GB): selective recomputation of the SwiGLU
         # activation (the reference's `ActivationMultiplyMLP` recompute class); with TP >= 2 the per-rank
         # footprint needs no recompute.
-        recompute = "swiglu" if world == 1 else "none"
+        # (the library-path arm keeps whole-MLP recomputation: its unfused ops hold more activations)
+        recompute = ("swiglu" if args.impl == "native" else "mlp") if world == 1 else "none"
     gran, rec_list = {"none": (None, None), "mlp": ("selective", ["CoreAttention", "LlamaMLP"]),
                       "mlp_only": ("selective", ["LlamaMLP"]),
                       "swiglu": ("selective", ["ActivationMultiplyMLP"]),

@@ -386,7 +386,7 @@ class DistributedOptimizer:
         self.state["step"] = self.step_count
         if int(sd["total"]) != self.total or int(sd["shard_lo"]) != self.shard_lo or int(sd["shard_hi"]) != self.shard_hi:
             raise ValueError("optimizer shard layout mismatch: checkpoint was written with a different "
-                             "parallel layout; use checkpoint.reshard_optimizer_state() first")
+                             "parallel layout; use checkpoint.reshard.load_optimizer_state_any_dp() (DP change) or the converter")
         self.exp_avg.copy_(sd["exp_avg"])
         if self.exp_avg_sq is not None and sd.get("exp_avg_sq") is not None:
             self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -132,7 +132,14 @@ class Trainer:
             opt.sync_master_from_params()
             log.info("loaded weights only from %s", ckpt_path)
             return
-        opt.load_state_dict(o)
+        if hasattr(opt, "shard_lo") and not ckpt_io._is_remote(directory):
+            # ZeRO-1 shards written with another data-parallel size are re-assembled for this rank's slice
+            from ..checkpoint.reshard import load_optimizer_state_any_dp
+            if load_optimizer_state_any_dp(opt, o, directory, tag, ps.get_tensor_model_parallel_rank(),
+                                           ps.get_pipeline_model_parallel_rank()):
+                log.info("optimizer state re-sharded for data-parallel size %d", opt.dp_size)
+        else:
+            opt.load_state_dict(o)
         if uc is not None:
             if "pytorch-lightning_version" not in uc:
                 uc["pytorch-lightning_version"] = (self.exp_manager.cfg.ckpt_ptl_version if self.exp_manager else None) or "2.5.0"
