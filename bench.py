@@ -179,7 +179,7 @@ def main():
     module = HFLlamaModule(cfg, None)
     module.setup("fit")
     module.configure_optimizers(100000)
-    if args.impl == "native" and tp > 1:
+    if args.impl == "native" and tp > 1 and os.environ.get("NXDT_FUSED_TP", "1") != "0":
         try:
             from neuronx_distributed_training_b200.parallel.fused import enable_fused_tp
             enable_fused_tp(module.model)
@@ -273,9 +273,16 @@ def main():
             out["e2e"] = {"value": tokens_per_step * args.steps / (e2e_ms / 1e3), "unit": "tokens/s",
                           "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                           "ms_per_step": e2e_ms / args.steps}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if getattr(module, "_mb_graph", None) is not None:
+            # a captured graph holds NCCL kernels of this communicator: drop it before the group is destroyed
+            module._mb_graph = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -173,9 +173,15 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
                 handle = dist.all_gather_into_tensor(total_x, x2d.contiguous(), group=group, async_op=True)
         dx = None
         rs_handle = None
+        # A fused kernel occupies every SM and waits on its peers; an NCCL kernel in flight next to it can only be
+        # tolerated if both ranks start the two in the same order, which a CUDA graph (parallel branches) does not
+        # guarantee.  So an outstanding NCCL collective is completed before a fused kernel is launched.
         if need_dx:
             if ctx.sp and tp > 1:
                 if ctx.can_fuse and ctx.fused.prefer_gemm_rs(dy2d.shape[0], dy2d.shape[1], weight.shape[1]):
+                    if handle is not None:
+                        handle.wait()
+                        handle = None
                     dx = ctx.fused.gemm_reduce_scatter(dy2d, weight, trans_b=False)
                 else:
                     dx_total = ops.gemm_nn(dy2d, weight)
@@ -191,6 +197,9 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
             if handle is not None:
                 handle.wait()
             if fused_wgrad:
+                if rs_handle is not None:
+                    rs_handle.wait()
+                    rs_handle = None
                 dw = _wgrad_fused_gather(ctx.fused, dy2d, x2d, weight)
             else:
                 dw = _wgrad(dy2d, total_x, weight)

@@ -224,6 +224,13 @@ class Trainer:
             self.validate()
         t_start = time.time()
         cb = self.exp_manager.checkpoint_callback if self.exp_manager else None
+        # hang detection: top-level `neuron_rt_exec_timeout` (the reference's runtime timeout knob) or
+        # NXDT_STEP_TIMEOUT, in seconds; 0 / unset = off
+        timeout = float(os.environ.get("NXDT_STEP_TIMEOUT", model.cfg.get("neuron_rt_exec_timeout", 0) or 0) or 0)
+        self.watchdog = None
+        if timeout > 0:
+            from ..utils.watchdog import StepWatchdog
+            self.watchdog = StepWatchdog(timeout, os.path.join(self.log_dir or ".", f"nemo_error_log_rank{ps.get_rank()}.txt")).start()
         try:
             while not self.should_stop:
                 loader = datamodule.train_dataloader()
@@ -241,6 +248,8 @@ class Trainer:
                     if self.ema is not None:
                         self.ema.update(self.global_step + 1)
                     n_batches += 1
+                    if self.watchdog is not None:
+                        self.watchdog.pet()
                     self.global_step += 1
                     self.steps_since_resume += 1
                     datamodule.consumed_samples = datamodule.compute_consumed_samples(self.steps_since_resume)
@@ -251,6 +260,8 @@ class Trainer:
                         self.validate()
                     if cb is not None and cb.should_save(self.global_step):
                         cb.save(self, self._ckpt_metrics())
+                    if self.watchdog is not None:
+                        self.watchdog.pet()          # validation / checkpointing are not part of the step budget
                     if self.max_time is not None and time.time() - t_start > self.max_time:
                         log.info("max_time reached")
                         self.should_stop = True
@@ -267,6 +278,8 @@ class Trainer:
                     and self.global_step > 0:
                 cb.save(self, self._ckpt_metrics(), last=not self._emergency and cb.p.save_last)
         finally:
+            if self.watchdog is not None:
+                self.watchdog.stop()
             model.on_train_end(self)
             ckpt_io.finalize_checkpoint()
             if self.exp_manager:

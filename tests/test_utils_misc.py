@@ -101,3 +101,36 @@ def test_optional_loggers_degrade_without_their_packages(tmp_path, monkeypatch):
     a, b = em.WandbLogger(str(tmp_path)), em.MLflowLogger(str(tmp_path))
     a.log_metrics({"x": 1.0}, 0); b.log_metrics({"x": 1.0}, 0)
     a.close(); b.close()
+
+
+def test_step_watchdog_reports_a_stall(tmp_path):
+    import time
+    from neuronx_distributed_training_b200.utils.watchdog import StepWatchdog
+    seen = []
+    dump = tmp_path / "err" / "stall.txt"
+    wd = StepWatchdog(0.3, str(dump), abort=False, on_timeout=seen.append, poll_s=0.05).start()
+    for _ in range(5):                       # healthy: steps keep arriving
+        time.sleep(0.1)
+        wd.pet()
+    assert not wd.fired
+    wd.pause()
+    time.sleep(0.5)                          # paused (e.g. checkpoint write): no report
+    assert not wd.fired
+    wd.resume()
+    time.sleep(0.6)                          # stalled
+    wd.stop()
+    assert wd.fired and seen and seen[0] > 0.3
+    text = dump.read_text()
+    assert "no training step completed" in text and "Thread" in text
+
+
+def test_trainer_starts_the_watchdog_from_the_config_key(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_trainer_cpu_helpers", os.path.join(os.path.dirname(__file__), "test_trainer_cpu.py"))
+    helpers = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(helpers)
+    _cfg, _fit = helpers._cfg, helpers._fit
+    cfg = _cfg(str(tmp_path / "run"), max_steps=2)
+    cfg["neuron_rt_exec_timeout"] = 600
+    tr, _ = _fit(cfg)
+    assert tr.watchdog is not None and not tr.watchdog.fired and tr.global_step == 2
