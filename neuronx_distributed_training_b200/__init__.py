@@ -1,2 +1,2 @@
 """B200-native 3D-parallel LLM training framework (capabilities of neuronx-distributed-training)."""
-__version__ = "0.1.0"
+from ._version import __version__  # noqa: F401
