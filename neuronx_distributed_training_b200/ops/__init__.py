@@ -628,6 +628,26 @@ class _FlashAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
+class _FlashAttnPreviewFn(torch.autograd.Function):
+    """Native forward + the PREVIEW native backward (``NXDT_FLASH_BWD_PREVIEW=1``; see flash_attn_bwd_sm100.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, causal, window, scale):
+        _count()
+        o, lse = C().flash_attn_fwd(q, k, v, causal, window, scale)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.cfg = (causal, window, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        causal, window, scale = ctx.cfg
+        _count(2)
+        dq, dk, dv = C().flash_attn_bwd_preview(do.contiguous(), q, k, v, o, lse, causal, window, scale)
+        return dq, dk, dv, None, None, None
+
+
 def _sdpa(q, k, v, causal, scale):
     # torch SDPA wants [B,H,S,D]
     o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
@@ -639,6 +659,9 @@ def flash_attention(q, k, v, causal: bool = True, window: Optional[int] = None, 
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
     native_ok = (_use_native(q) and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and causal and q.shape[1] % 128 == 0
                  and q.shape[1] == k.shape[1] and hasattr(C(), "flash_attn_fwd"))
+    if native_ok and os.environ.get("NXDT_FLASH_BWD_PREVIEW", "0") == "1" and hasattr(C(), "flash_attn_bwd_preview"):
+        return _FlashAttnPreviewFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal,
+                                         int(window or 0), float(scale))
     if native_ok and hasattr(C(), "flash_attn_bwd"):
         return _FlashAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal,
                                   int(window or 0), float(scale))

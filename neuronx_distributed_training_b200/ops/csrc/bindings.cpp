@@ -56,6 +56,9 @@ std::vector<at::Tensor> bias_dropout_add_fwd(const at::Tensor& x, const c10::opt
 at::Tensor dropout_bwd(const at::Tensor& dout, const at::Tensor& mask, double p);
 at::Tensor embedding_fwd(const at::Tensor& ids, const at::Tensor& w, int64_t vocab_start, bool seq_first);
 void embedding_bwd_(at::Tensor dw, const at::Tensor& ids, const at::Tensor& g, int64_t vocab_start, bool seq_first);
+std::vector<at::Tensor> flash_attn_bwd_preview(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k,
+                                               const at::Tensor& v, const at::Tensor& out, const at::Tensor& lse,
+                                               bool causal, int64_t window, double scale);
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
@@ -71,6 +74,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("qkv_rope_split_fwd", &qkv_rope_split_fwd);
   m.def("qkv_rope_split_bwd", &qkv_rope_split_bwd);
   m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 causal flash attention forward (head_dim 128)");
+  m.def("flash_attn_bwd_preview", &flash_attn_bwd_preview,
+        "tcgen05 causal flash attention backward (preview: compiled, not yet validated on hardware)");
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");
   m.def("ag_only", &ag_only);
   m.def("fused_tp_set_debug", &fused_tp_set_debug);
