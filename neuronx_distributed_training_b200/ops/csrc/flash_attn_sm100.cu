@@ -1,4 +1,5 @@
-// Causal flash attention forward for sm_100a (head_dim 128, GQA-native, optional sliding window).
+// Flash attention forward for sm_100a (head_dim 128, GQA-native; causal with optional sliding window, or full
+// attention for the off-diagonal blocks of ring attention).
 //
 // One CTA = 128 query rows of one (batch, head).  192 threads:
 //   warp 0      TMA producer: Q once, then K_j / V_j tiles (128 keys each) through 2-stage rings
@@ -37,6 +38,7 @@ struct Params {
   int B, S, Hq, Hk;
   int num_q_blocks;
   int window;            // 0 = none; otherwise keys with k <= q - window are masked
+  int causal;            // 1: keys after the query are masked; 0: full attention (ring-attention off-diagonal blocks)
   float scale_log2;      // softmax scale * log2(e)
   float* lse;            // [B, Hq, S]
 };
@@ -79,7 +81,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   const int q0 = q_blk * BM;
   int j_lo = 0;
   if (p.window > 0) j_lo = max(0, (q0 - p.window + 1) / BN);
-  const int j_hi = q_blk;                                  // inclusive (diagonal block)
+  const int j_hi = p.causal ? q_blk : p.num_q_blocks - 1;  // inclusive (diagonal block when causal)
   const int n_blocks = j_hi - j_lo + 1;
   const int row_base = batch * p.S;                        // row of token 0 of this batch in the [B*S, H*D] views
 
@@ -187,14 +189,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
       const int k0 = j * BN;
-      const bool need_mask = (j == j_hi) || (p.window > 0 && k0 <= q_pos - p.window);
+      const bool need_mask = (p.causal && j == q_blk) || (p.window > 0 && k0 <= q_pos - p.window);
       float mx = -INFINITY;
 #pragma unroll
       for (int t = 0; t < BN; ++t) {
         float v = s[t] * p.scale_log2;
         if (need_mask) {
           const int kpos = k0 + t;
-          if (kpos > q_pos || (p.window > 0 && kpos <= q_pos - p.window)) v = -INFINITY;
+          if ((p.causal && kpos > q_pos) || (p.window > 0 && kpos <= q_pos - p.window)) v = -INFINITY;
         }
         s[t] = v;
         mx = fmaxf(mx, v);
@@ -296,7 +298,7 @@ std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k,
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16);
   TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.size(3) == D && k.size(3) == D && v.size(3) == D,
               "flash_attn_fwd: head_dim must be 128");
-  TORCH_CHECK(causal, "flash_attn_fwd: only causal attention is implemented");
+  TORCH_CHECK(causal || window == 0, "flash_attn_fwd: a sliding window needs causal attention");
   TORCH_CHECK(q.is_contiguous() && k.is_contiguous() && v.is_contiguous(), "flash_attn_fwd: contiguous [B,S,H,D] inputs required");
   const int B = q.size(0), S = q.size(1), Hq = q.size(2), Hk = k.size(2);
   TORCH_CHECK(k.size(1) == S && v.size(1) == S && v.size(2) == Hk && Hq % Hk == 0);
@@ -312,6 +314,7 @@ std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k,
   CUtensorMap to = tma::make_2d(out.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, 128, 64);
   Params p;
   p.B = B; p.S = S; p.Hq = Hq; p.Hk = Hk; p.num_q_blocks = S / BM; p.window = (int)window;
+  p.causal = causal ? 1 : 0;
   p.scale_log2 = (float)(scale * 1.4426950408889634);
   p.lse = lse.data_ptr<float>();
   static bool once = false;

@@ -14,6 +14,7 @@ equivalent); K/V transfers are issued before the block math so they overlap with
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -24,8 +25,21 @@ from . import state as ps
 _Q_CHUNK = 1024
 
 
+def _native_block_ok(q, k) -> bool:
+    # opt-in until the non-causal mode of the tcgen05 forward has been validated on hardware
+    if os.environ.get("NXDT_RING_NATIVE_FWD", "0") != "1" or not q.is_cuda:
+        return False
+    from .. import ops
+    return ops.get_backend() != "torch" and ops.C() is not None and hasattr(ops.C(), "flash_attn_fwd") \
+        and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and q.shape[1] == k.shape[1] and q.shape[1] % 128 == 0
+
+
 def _block_fwd(q, k, v, scale: float, causal: bool):
     """q [B,Sq,H,D], k/v [B,Sk,Hk,D] -> out [B,Sq,H,D] fp32, lse [B,H,Sq] fp32."""
+    if _native_block_ok(q, k):
+        from .. import ops
+        o, lse = ops.C().flash_attn_fwd(q.contiguous(), k.contiguous(), v.contiguous(), bool(causal), 0, float(scale))
+        return o.float(), lse
     B, Sq, H, D = q.shape
     Hk = k.shape[2]
     rep = H // Hk

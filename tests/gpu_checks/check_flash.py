@@ -11,6 +11,12 @@ for (B, S, Hq, Hk, w) in [(1, 256, 4, 1, 0), (2, 1024, 8, 2, 0), (1, 1024, 4, 1,
     o, lse = C.flash_attn_fwd(q, k, v, True, w, 1 / math.sqrt(128)); torch.cuda.synchronize()
     r, lr = ops.attention_ref(q, k, v, causal=True, window=w or None, return_lse=True)
     print(f"fwd B{B} S{S} Hq{Hq} Hk{Hk} w{w}: rel_err={rel(o, r):.3e} lse_err={(lse - lr).abs().max().item():.3e}", flush=True)
+# full (non-causal) attention: the off-diagonal blocks of ring attention (added after round 1's GPU budget; validate first)
+for (B, S, Hq, Hk) in [(1, 256, 4, 1), (2, 512, 8, 2)]:
+    q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16(); k = torch.randn(B, S, Hk, 128, device="cuda").bfloat16(); v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
+    o, lse = C.flash_attn_fwd(q, k, v, False, 0, 1 / math.sqrt(128)); torch.cuda.synchronize()
+    r, lr = ops.attention_ref(q, k, v, causal=False, return_lse=True)
+    print(f"fwd non-causal B{B} S{S} Hq{Hq} Hk{Hk}: rel_err={rel(o, r):.3e} lse_err={(lse - lr).abs().max().item():.3e}", flush=True)
 B, S, Hq, Hk = 1, 8192, 32, 8
 q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16(); k = torch.randn(B, S, Hk, 128, device="cuda").bfloat16(); v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
 def timeit(fn, n=10):
