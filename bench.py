@@ -179,7 +179,8 @@ def main():
     module = HFLlamaModule(cfg, None)
     module.setup("fit")
     module.configure_optimizers(100000)
-    if args.impl == "native" and tp > 1 and os.environ.get("NXDT_FUSED_TP", "1") != "0":
+    if args.impl == "native" and tp > 1 and os.environ.get("NXDT_FUSED_TP", "1") != "0" \
+            and os.environ.get("NXDT_MB_OVERLAP", "0") != "1":      # the two-stream overlap mode needs NCCL TP
         try:
             from neuronx_distributed_training_b200.parallel.fused import enable_fused_tp
             enable_fused_tp(module.model)
@@ -266,7 +267,8 @@ def main():
                        "precision": "bf16 compute, fp32 master weights + fp32 grad accumulation, AdamW fp32 state",
                        "recompute": recompute, "l2_policy": "inputs larger than L2 (weights+activations >> 126 MB per step)",
                        "peak_mem_gb": round(mem_gb, 1), "final_loss": float(loss),
-                       "cuda_graph": getattr(module, "_mb_graph", None) is not None},
+                       "cuda_graph": getattr(module, "_mb_graph", None) is not None,
+                       "microbatch_overlap": bool(getattr(module, "use_mb_overlap", False))},
             "clocks": clocks, "gpu_launches": launches,
         }
         if not args.no_e2e:

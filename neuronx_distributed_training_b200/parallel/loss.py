@@ -209,7 +209,9 @@ _SCRATCH = {}
 
 
 def _get_scratch(like: torch.Tensor, tag: str, dtype):
-    key = (tag, tuple(like.shape), dtype, like.device)
+    # one buffer per CUDA stream: micro-batches that run concurrently on different streams must not share it
+    stream = torch.cuda.current_stream(like.device).cuda_stream if like.is_cuda else 0
+    key = (tag, tuple(like.shape), dtype, like.device, stream)
     t = _SCRATCH.get(key)
     if t is None:
         t = torch.empty(like.shape, dtype=dtype, device=like.device)

@@ -88,6 +88,12 @@ class BaseModelModule:
         self.cuda_graph_warmup_steps = int(os.environ.get("NXDT_CUDA_GRAPH_WARMUP", "1"))
         self._mb_graph = None
         self._eager_train_steps = 0
+        # EXPERIMENTAL (written after round 1's GPU budget, unvalidated): issue pairs of micro-batches on two CUDA streams
+        # so that the tensor-parallel collectives of one overlap the compute of the other
+        env = os.environ.get("NXDT_MB_OVERLAP")
+        self.use_mb_overlap = (bool(fus.get("microbatch_overlap", False)) if env is None else env == "1") \
+            and self.device.type == "cuda" and self.dims.pp == 1 and not self.use_cuda_graph
+        self._mb_streams = None
 
     # ---- to be provided by subclasses -------------------------------------------------------------
     def build_model(self) -> nn.Module:
@@ -172,7 +178,10 @@ class BaseModelModule:
             running = fn(**batch)
         else:
             running = torch.zeros((), dtype=torch.float32, device=self.device)
-            for mb in self.get_batch_iterator(batch):
+            if is_training and self.use_mb_overlap and self.num_microbatches >= 2:
+                running = self._overlapped_microbatches(batch)
+                batch = {}          # nothing left for the sequential loop below
+            for mb in (self.get_batch_iterator(batch) if batch else ()):
                 if is_training and self._graphed_microbatch(mb, running):
                     continue
                 with contextlib.nullcontext() if is_training else torch.no_grad():
@@ -194,6 +203,40 @@ class BaseModelModule:
             dist.all_reduce(running, group=dpg)
             running /= ps.group_size(dpg)
         return running
+
+    def _overlapped_microbatches(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Forward + backward of the micro-batches, two at a time on two side streams.  Both streams share the flat
+        ``main_grad`` buffer: the wgrad GEMMs add into it with element-wise atomic TMA reductions, the small
+        read-modify-write accumulations are ordered by ``DistributedOptimizer.multi_stream``; per-stream scratch in the
+        fused LM-head / cross-entropy keeps the two micro-batches apart.  Requires NCCL tensor parallelism (the fused
+        TP kernels own every SM and one symmetric workspace, so they cannot run two at a time)."""
+        from ..parallel import fused as fused_mod
+        if fused_mod._FTP_CACHE:
+            raise RuntimeError("microbatch_overlap needs the NCCL tensor-parallel path (do not call enable_fused_tp)")
+        DistributedOptimizer.multi_stream = True
+        main = torch.cuda.current_stream()
+        if self._mb_streams is None:
+            self._mb_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        streams = self._mb_streams
+        partial = [torch.zeros((), dtype=torch.float32, device=self.device) for _ in streams]
+        for s in streams:
+            s.wait_stream(main)
+        mbs = list(self.get_batch_iterator(batch))
+        for k in range(0, len(mbs), 2):
+            losses = []
+            for idx, mb in enumerate(mbs[k:k + 2]):
+                with torch.cuda.stream(streams[idx]):
+                    with nvtx_range("forward"):
+                        loss, _ = self.model_fwd_calc_loss(mb)
+                    losses.append(loss.float() / self.num_microbatches)
+            for idx, loss in enumerate(losses):
+                with torch.cuda.stream(streams[idx]):
+                    with nvtx_range("backward"):
+                        loss.backward()
+                    partial[idx] += loss.detach()
+        for s in streams:
+            main.wait_stream(s)
+        return partial[0] + partial[1]
 
     def _graphed_microbatch(self, mb: Dict[str, Any], running: torch.Tensor) -> bool:
         """Replay (capturing first if needed) the CUDA graph of one micro-batch; False -> run it eagerly."""
