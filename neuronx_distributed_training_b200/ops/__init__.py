@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from . import native as _native_loader
+from . import fp8 as _fp8
 
 _BACKEND = os.environ.get("NXDT_OPS_BACKEND", "auto")
 _COUNTERS = {"native_launches": 0}
@@ -76,8 +77,15 @@ def _gemm_native_ok(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int) ->
     return (k % 8 == 0) and (n % 8 == 0) and (m % 8 == 0) and m > 0
 
 
-def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M,N] = a[M,K] @ b[N,K]^T   (linear forward)."""
+def _fp8_route(fp8: Optional[bool], a: torch.Tensor, b: torch.Tensor) -> bool:
+    use = _fp8.enabled() if fp8 is None else fp8
+    return bool(use) and a.dim() == 2 and b.dim() == 2 and a.dtype in (torch.bfloat16, torch.float32) and a.dtype == b.dtype
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, fp8: Optional[bool] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[N,K]^T   (linear forward).  ``fp8``: None = follow ``ops.fp8.enabled()``."""
+    if _fp8_route(fp8, a, b):
+        return _fp8.linear_fwd(a, b, out)
     if _use_native(a) and _gemm_native_ok(a, b, a.shape[0], b.shape[0], a.shape[1]):
         a = a if a.is_contiguous() else a.contiguous()
         b = b if b.is_contiguous() else b.contiguous()
@@ -93,8 +101,10 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     return r
 
 
-def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, fp8: Optional[bool] = None) -> torch.Tensor:
     """out[M,N] = a[M,K] @ b[K,N]   (dgrad: dY @ W)."""
+    if _fp8_route(fp8, a, b):
+        return _fp8.linear_dgrad(a, b, out)
     if _use_native(a) and _gemm_native_ok(a, b, a.shape[0], b.shape[1], a.shape[1]):
         a = a if a.is_contiguous() else a.contiguous()
         b = b if b.is_contiguous() else b.contiguous()
@@ -111,8 +121,10 @@ def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
 
 
 def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
-               accumulate: bool = False) -> torch.Tensor:
+               accumulate: bool = False, fp8: Optional[bool] = None) -> torch.Tensor:
     """out[N,K] (+)= dy[M,N]^T @ x[M,K]   (wgrad).  ``out`` may be fp32 (main_grad accumulation)."""
+    if _fp8_route(fp8, dy, x):
+        return _fp8.linear_wgrad(dy, x, out, accumulate)
     if _use_native(dy) and _gemm_native_ok(dy, x, dy.shape[1], x.shape[1], dy.shape[0]) and \
             (out is None or out.dtype in (torch.float32, torch.bfloat16)):
         dy = dy if dy.is_contiguous() else dy.contiguous()

@@ -59,9 +59,17 @@ void embedding_bwd_(at::Tensor dw, const at::Tensor& ids, const at::Tensor& g, i
 std::vector<at::Tensor> flash_attn_bwd_preview(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k,
                                                const at::Tensor& v, const at::Tensor& out, const at::Tensor& lse,
                                                bool causal, int64_t window, double scale);
+std::vector<at::Tensor> fp8_quantize_rows(const at::Tensor& x);
+std::vector<at::Tensor> fp8_quantize_cols_transposed(const at::Tensor& x);
+void gemm_fp8(const at::Tensor& a_q, const at::Tensor& a_scale, const at::Tensor& b_q, const at::Tensor& b_scale,
+              at::Tensor& out, bool accumulate);
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
+  m.def("gemm_fp8", &gemm_fp8, "preview: e4m3 tcgen05 GEMM (kind::f8f6f4) with per-row scales of both operands");
+  m.def("fp8_quantize_rows", &fp8_quantize_rows, "bf16 [R,C] -> e4m3 bytes + one fp32 scale per row");
+  m.def("fp8_quantize_cols_transposed", &fp8_quantize_cols_transposed,
+        "bf16 [R,C] -> e4m3 bytes of the transpose [C,R] + one fp32 scale per original column");
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("rope_fwd", &rope_fwd);

@@ -67,6 +67,9 @@ template <class Gate>
 struct gate_traits {
   static constexpr bool grouped = false;
   static constexpr bool b_3d = false;
+  // fp8 (e4m3) K-major operands: 128 elements per 128-byte swizzle row, tcgen05.mma.kind::f8f6f4 (K = 32 per
+  // instruction); the gate then also provides the dequantisation scales  out[m, n] = acc * row_scale(m) * col_scale(n)
+  static constexpr bool fp8 = false;
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, int& n_blk) {
@@ -122,7 +125,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  constexpr int K_ELEMS = GT::fp8 ? 2 * BLOCK_K : BLOCK_K;      // elements per 128-byte operand row
+  const int num_k_blocks = (p.K + K_ELEMS - 1) / K_ELEMS;
 
   if (warp_idx == 0) {
     // =========================== TMA producer ===========================
@@ -151,7 +155,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * K_ELEMS;
           if constexpr (!A_MN) {
             tma_load_2d(sa, tma_a, &full_bar[stage], k0, m0);                       // box {64 k, 128 m}
           } else {
@@ -181,7 +185,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
     }
   } else if (warp_idx == 1) {
     // =========================== MMA issuer ===========================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    static_assert(!GT::fp8 || (!A_MN && !B_MN), "the fp8 path takes K-major operands only");
+    constexpr uint32_t idesc = GT::fp8 ? make_idesc_f8(BLOCK_M, BLOCK_N, false, false)
+                                       : make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
       int tile_k_blocks = num_k_blocks;
@@ -206,7 +212,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
                                      : make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024)
                                      : make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-            umma_f16<1>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (GT::fp8) umma_f8(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16<1>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
           if (kb == tile_k_blocks - 1) umma_commit(&tmem_full[acc]);
@@ -255,6 +262,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + c * 32, v);
           tmem_ld_wait();
+          if constexpr (GT::fp8) {
+            const float rs = gate.row_scale(m_blk * BLOCK_M + (int)row);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(__uint_as_float(v[j]) * rs * gate.col_scale(n_blk * BLOCK_N + c * 32 + j));
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             uint4 o = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -265,6 +278,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
           tmem_ld_32x32b_x32(taddr + c * 64, v0);
           tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
           tmem_ld_wait();
+          if constexpr (GT::fp8) {
+            const float rs = gate.row_scale(m_blk * BLOCK_M + (int)row);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v0[j] = __float_as_uint(__uint_as_float(v0[j]) * rs * gate.col_scale(n_blk * BLOCK_N + c * 64 + j));
+              v1[j] = __float_as_uint(__uint_as_float(v1[j]) * rs * gate.col_scale(n_blk * BLOCK_N + c * 64 + 32 + j));
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;

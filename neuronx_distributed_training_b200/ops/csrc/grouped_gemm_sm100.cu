@@ -30,6 +30,7 @@ template <>
 struct gate_traits<GroupedRowsGate> {
   static constexpr bool grouped = true;
   static constexpr bool b_3d = true;
+  static constexpr bool fp8 = false;
 };
 
 struct GroupedWgradGate : NoGate {
@@ -49,6 +50,7 @@ template <>
 struct gate_traits<GroupedWgradGate> {
   static constexpr bool grouped = true;
   static constexpr bool b_3d = false;
+  static constexpr bool fp8 = false;
 };
 
 template <bool B_MN>

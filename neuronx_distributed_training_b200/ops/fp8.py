@@ -1,0 +1,131 @@
+"""fp8 (e4m3) GEMM path with row / column block scales (BASELINE config #4; the reference has no fp8 mode).
+
+Recipe: every GEMM operand is quantised along its reduction dimension with ONE scale per row (a 1 x K block), the
+product is dequantised by ``row_scale(m) * col_scale(n)`` in the GEMM epilogue, accumulation is fp32.  Tensors that are
+reduced along their other dimension in a backward GEMM get a second, transposed quantised copy (per-original-column
+scales), so forward, dgrad and wgrad all run as K-major "nt" GEMMs on ``tcgen05.mma.kind::f8f6f4``:
+
+    fwd    Y  = q_rows(X)    . q_rows(W)^T
+    dgrad  dX = q_rows(dY)   . q_colsT(W)^T
+    wgrad  dW = q_colsT(dY)  . q_colsT(X)^T          (fp32 accumulate into main_grad)
+
+The CUDA kernels (``ops/csrc/gemm_fp8_sm100.cu``) are a PREVIEW: compiled for sm_100a but not yet validated on hardware.
+The PyTorch implementation below (``torch.float8_e4m3fn``) is the numerics oracle and what runs on CPU; it is exact
+w.r.t. the recipe, so convergence behaviour can be tested without a GPU.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+
+E4M3_MAX = 448.0
+_STATE = {"enabled": os.environ.get("NXDT_FP8", "0") == "1"}
+
+
+def set_enabled(flag: bool) -> None:
+    _STATE["enabled"] = bool(flag)
+
+
+def enabled() -> bool:
+    return _STATE["enabled"]
+
+
+def _native(x: torch.Tensor):
+    from . import C, _use_native
+    if x.is_cuda and x.dtype == torch.bfloat16 and os.environ.get("NXDT_FP8_NATIVE", "0") == "1" and _use_native(x) \
+            and hasattr(C(), "gemm_fp8"):
+        return C()
+    return None
+
+
+# ---- quantisation ----------------------------------------------------------------------------------------
+def quantize_rows(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x [R, C] -> (e4m3 bytes [R, C] as uint8, fp32 scale [R]);  x ~= q * scale[:, None]."""
+    c = _native(x)
+    if c is not None and x.is_contiguous() and x.shape[1] % 8 == 0:
+        q, s = c.fp8_quantize_rows(x)
+        return q, s
+    xf = x.float()
+    amax = xf.abs().amax(dim=1)
+    scale = torch.where(amax > 0, amax / E4M3_MAX, torch.ones_like(amax))
+    q = (xf / scale[:, None]).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8), scale
+
+
+def quantize_cols_transposed(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x [R, C] -> (e4m3 bytes of x^T [C, R], fp32 scale [C] per original column)."""
+    c = _native(x)
+    if c is not None and x.is_contiguous() and x.shape[1] % 2 == 0:
+        q, s = c.fp8_quantize_cols_transposed(x)
+        return q, s
+    return quantize_rows(x.t().contiguous())
+
+
+def dequantize(q: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    return q.view(torch.float8_e4m3fn).float() * scale[:, None]
+
+
+# ---- GEMM ------------------------------------------------------------------------------------------------
+def gemm(a_q: torch.Tensor, a_scale: torch.Tensor, b_q: torch.Tensor, b_scale: torch.Tensor,
+         out: Optional[torch.Tensor] = None, accumulate: bool = False, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """out[M, N] (+)= (a_q[M, K] b_q[N, K]^T) * a_scale[:, None] * b_scale[None, :]."""
+    M, N = a_q.shape[0], b_q.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a_q.device)
+        accumulate = False
+    from . import C, _use_native, _count
+    if a_q.is_cuda and os.environ.get("NXDT_FP8_NATIVE", "0") == "1" and _use_native(a_q) and hasattr(C(), "gemm_fp8") \
+            and a_q.shape[1] % 16 == 0 and N % 8 == 0 and out.is_contiguous() and out.dtype in (torch.bfloat16, torch.float32):
+        _count()
+        C().gemm_fp8(a_q.contiguous(), a_scale.contiguous(), b_q.contiguous(), b_scale.contiguous(), out, accumulate)
+        return out
+    r = (a_q.view(torch.float8_e4m3fn).float() @ b_q.view(torch.float8_e4m3fn).float().t()) * a_scale[:, None] * b_scale[None, :]
+    if accumulate:
+        out.add_(r.to(out.dtype))
+    else:
+        out.copy_(r.to(out.dtype))
+    return out
+
+
+# ---- the three GEMMs of a linear layer ---------------------------------------------------------------------
+_WCACHE = {}
+
+
+def _cached(w: torch.Tensor, kind: str):
+    """Weights change once per optimizer step but are used by every micro-batch: keep their quantised copies until
+    the parameter is written again (``_version`` bumps on in-place updates)."""
+    key = (id(w), kind)
+    hit = _WCACHE.get(key)
+    ver = w._version
+    if hit is not None and hit[0] == ver and hit[1] == w.data_ptr():
+        return hit[2]
+    val = quantize_rows(w) if kind == "rows" else quantize_cols_transposed(w)
+    _WCACHE[key] = (ver, w.data_ptr(), val)
+    return val
+
+
+def clear_cache() -> None:
+    _WCACHE.clear()
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [M, K] @ w [N, K]^T"""
+    xq, xs = quantize_rows(x)
+    wq, ws = _cached(w, "rows")
+    return gemm(xq, xs, wq, ws, out=out, out_dtype=x.dtype)
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dy [M, N] @ w [N, K]"""
+    gq, gs = quantize_rows(dy)
+    wq, ws = _cached(w, "colsT")                  # [K, N], scale per input feature k
+    return gemm(gq, gs, wq, ws, out=out, out_dtype=dy.dtype)
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """dy [M, N]^T @ x [M, K] -> [N, K]"""
+    gq, gs = quantize_cols_transposed(dy)         # [N, M]
+    xq, xs = quantize_cols_transposed(x)          # [K, M]
+    return gemm(gq, gs, xq, xs, out=out, accumulate=accumulate, out_dtype=dy.dtype)

@@ -146,7 +146,7 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
         for s in range(0, T, chunk):
             e = min(T, s + chunk)
             h = hidden[s:e]
-            logits = ops.gemm_nt(h, weight)
+            logits = ops.gemm_nt(h, weight, fp8=False)          # the LM head stays in bf16
             if ops.native_ce_available(logits):
                 # two fused passes on the bf16 logits; the buffer is turned into d(logits) in place
                 loss, dlog = ops.cross_entropy_fused_(logits, labels[s:e].contiguous(), _vocab_range(weight.shape[0], group)[0],
@@ -155,9 +155,9 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
                 if per_tok is not None:
                     per_tok[s:e] = loss
                 if need_grad:
-                    dh[s:e] = ops.gemm_nn(dlog, weight)
+                    dh[s:e] = ops.gemm_nn(dlog, weight, fp8=False)
                     if dw_acc is not None:
-                        ops.gemm_wgrad(dlog, h, out=dw_acc, accumulate=True)
+                        ops.gemm_wgrad(dlog, h, out=dw_acc, accumulate=True, fp8=False)
                 del logits, dlog
                 continue
             loss, probs, tmask, local_t, ignore = _ce_stats(logits, labels[s:e], group, ignore_index)
@@ -171,9 +171,9 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
                 probs.masked_fill_(ignore.unsqueeze(-1), 0.0)
                 dlog = probs.to(hidden.dtype)
                 del probs
-                dh[s:e] = ops.gemm_nn(dlog, weight)
+                dh[s:e] = ops.gemm_nn(dlog, weight, fp8=False)
                 if dw_acc is not None:
-                    ops.gemm_wgrad(dlog, h, out=dw_acc, accumulate=True)
+                    ops.gemm_wgrad(dlog, h, out=dw_acc, accumulate=True, fp8=False)
                 del dlog
         if need_grad and tp > 1:
             # hidden is replicated over TP here (already gathered); sum the partial d(hidden)

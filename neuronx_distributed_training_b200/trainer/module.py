@@ -111,6 +111,10 @@ class BaseModelModule:
 
     # ---- lifecycle ---------------------------------------------------------------------------------
     def setup(self, stage: str = "fit"):
+        fus = self.config.get("fusions", Config({})) if "fusions" in self.config else Config({})
+        if "fp8_gemm" in fus or str(self.cfg.get("precision", Config({})).get("gemm_dtype", "")).lower() in ("fp8", "e4m3"):
+            # linear-layer GEMMs in e4m3 with row / column block scales (ops/fp8.py); LM head, attention, norms stay bf16
+            ops.fp8.set_enabled(bool(fus.get("fp8_gemm", True)))
         if self.model is None:
             self.model = self.build_model()
 
