@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) quant_rows_kernel(const __nv_bfloat16* __
     for (int c = threadIdx.x * 8; c < C; c += 256 * 8) {
       const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-      __nv_fp8_e4m3 o[8];
+      alignas(8) __nv_fp8_e4m3 o[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __bfloat1622float2(h[i]);
