@@ -8,19 +8,19 @@ if [ -n "$SLURM_NTASKS" ]; then
     export NTASKS=$SLURM_NTASKS
     export NODEID=$SLURM_NODEID
     export MASTER_ADDR=$(scontrol show hostnames "$SLURM_JOB_NODELIST" | head -n 1)
-    export LOG_PATH=logs/$SLURM_JOB_ID/${SLURM_RESTART_COUNT:-0}/$NODEID
+    export LOG_PATH=${LOG_PATH:-logs/$SLURM_JOB_ID/${SLURM_RESTART_COUNT:-0}/$NODEID}
     : ${NEMO_EXPM_VERSION:=$SLURM_JOB_ID}
 elif [ -n "$OMPI_COMM_WORLD_SIZE" ]; then
     export NTASKS=$OMPI_COMM_WORLD_SIZE
     export NODEID=$OMPI_COMM_WORLD_RANK
     : ${MASTER_ADDR:=$(echo "${OMPI_MCA_orte_hnp_uri:-127.0.0.1}" | sed -e 's/.*tcp:\/\///' -e 's/[,:].*//')}
     export MASTER_ADDR
-    export LOG_PATH=logs/ompi/$NODEID
+    export LOG_PATH=${LOG_PATH:-logs/ompi/$NODEID}
 else
     export NTASKS=1
     export NODEID=0
     export MASTER_ADDR=127.0.0.1
-    export LOG_PATH=logs/local
+    export LOG_PATH=${LOG_PATH:-logs/local}
 fi
 mkdir -p "$LOG_PATH"
 export MASTER_PORT=${MASTER_PORT:-41000}

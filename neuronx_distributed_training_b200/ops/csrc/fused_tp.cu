@@ -23,6 +23,7 @@
 
 #include "gemm_sm100.cuh"
 #include "tma_utils.h"
+#include <cstdlib>
 #include <set>
 
 namespace gemm100 {
@@ -384,6 +385,12 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // Device-resident epoch: incremented by a one-thread kernel in stream order right before every fused op, so that a
 // captured CUDA graph advances the cross-GPU protocol on every replay (a host-passed epoch would be baked in).
 __global__ void bump_epoch_kernel(uint32_t* epoch) { *epoch = *epoch + 1u; }
+// same, and clears the reduce-scatter arrival counters of this call (instead of a memset, so that the clear is an
+// ordinary kernel node in stream / graph order)
+__global__ void bump_epoch_clear_kernel(uint32_t* epoch, uint32_t* counters, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) counters[i] = 0u;
+  if (threadIdx.x == 0) *epoch = *epoch + 1u;
+}
 
 // All-peer barrier at the epoch held in `epoch_ptr`: every rank has finished everything it enqueued before this
 // kernel once the kernel completes on all ranks.  Placed at CUDA-graph boundaries, where the double-buffer parity of
@@ -542,7 +549,6 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   rs.out = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
   rs.epoch = (uint32_t)epoch;
   rs.epoch_ptr = reinterpret_cast<const uint32_t*>(epoch_ptr);
-  if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
   rs.rank = rank; rs.tp = tp; rs.rows_per_rank = rows_per_rank; rs.N = N;
   CUtensorMap ta, tb;
   make_operand_maps(a.data_ptr(), b.data_ptr(), M_total, N, K, true, b_kmajor, ta, tb);
@@ -556,7 +562,19 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   // while I am still computing, and what the others need from me is produced in ring order
   p.m_first = ((rank + 1) % tp) * (rows_per_rank / 128);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  C10_CUDA_CHECK(cudaMemsetAsync(rs.counter_local, 0, sizeof(uint32_t) * (rows_per_rank / 128), stream));
+  // NXDT_RS_CLEAR_KERNEL=1 (experiment for the graph-replay investigation, docs/ROUND2_PLAN.md): clear the counters
+  // with a kernel node instead of a memset node
+  static const bool clear_with_kernel = [] {
+    const char* e = std::getenv("NXDT_RS_CLEAR_KERNEL");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (epoch_ptr != 0 && clear_with_kernel) {
+    bump_epoch_clear_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr), rs.counter_local,
+                                                   rows_per_rank / 128);
+  } else {
+    if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
+    C10_CUDA_CHECK(cudaMemsetAsync(rs.counter_local, 0, sizeof(uint32_t) * (rows_per_rank / 128), stream));
+  }
   auto run = [&](auto kern) {
     set_smem(kern);
     kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, maps, p, rs);
