@@ -243,7 +243,8 @@ class _GroupedLinearFn(torch.autograd.Function):
             main_grad = getattr(w, "main_grad", None)
             if main_grad is not None:
                 grouped_wgrad(x, dy, offsets, main_grad, True)
-                w.grad_added_to_main_grad = True
+                from ..parallel.grad_hooks import mark_main_grad_written
+                mark_main_grad_written(w)
             else:
                 dw = grouped_wgrad(x, dy, offsets, torch.empty_like(w), False)
         return dx, dw, None, None

@@ -174,6 +174,9 @@ class DistributedOptimizer:
                 else:
                     p.main_grad.add_(p.grad.to(p.main_grad.dtype))
                 p.grad = None
+                cb = getattr(p, "_grad_ready_cb", None)
+                if cb is not None:
+                    cb(p)
         return hook
 
     # ------------------------------------------------------------------------------------------
@@ -198,8 +201,87 @@ class DistributedOptimizer:
             p.main_grad.copy_(flat[o:o + p.numel()].view(p.shape))
             o += p.numel()
 
+    # ---- data-parallel gradient reduction overlapped with the last micro-batch's backward -----------------
+    def enable_grad_reduce_overlap(self, bucket_mb: float = 256.0) -> bool:
+        """Split the flat gradient buffer into buckets (cut at the ZeRO-1 shard boundaries, so every bucket has ONE
+        owner) and reduce a bucket to its owner as soon as every parameter in it has its final gradient -- while
+        backward is still running (`bucket_size_collectives`, reference training_orchestrator.py:42).  The shard layout,
+        the optimizer state and the checkpoints are unchanged: the owner receives the sum in place with
+        ``dist.reduce`` (``all_reduce`` without ZeRO-1).  Buckets that hold parameters whose gradient needs another
+        reduction first (sequence-parallel norm weights: TP sum) or that are written more than once per backward (tied
+        weights) are reduced at step time."""
+        if self.dp_size <= 1 or self._fused_zero1 is not None:
+            return False
+        esize = self.grad_buffer.element_size()
+        per = max(64, int(bucket_mb * (1 << 20) / esize) // 64 * 64)
+        cuts = set(range(0, self.total, per)) | {self.total}
+        if self.zero1:
+            cuts |= {r * self.shard_size for r in range(self.dp_size + 1)}
+        cuts = sorted(cuts)
+        self._buckets = [(lo, hi, (lo // self.shard_size) if self.zero1 else None) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+        starts = [b[0] for b in self._buckets]
+        import bisect
+        self._bucket_params = [0] * len(self._buckets)
+        self._bucket_late = [False] * len(self._buckets)
+        for o, p_ in zip(self.offsets, self.params):
+            first = bisect.bisect_right(starts, o) - 1
+            last = bisect.bisect_right(starts, o + p_.numel() - 1) - 1
+            p_._grad_buckets = list(range(first, last + 1))
+            late = bool(getattr(p_, "sequence_parallel_enabled", False)) or bool(getattr(p_, "_multi_use", False)) \
+                or bool(getattr(p_, "kv_replica_sync", False))
+            for b in p_._grad_buckets:
+                self._bucket_params[b] += 1
+                self._bucket_late[b] = self._bucket_late[b] or late
+            p_._grad_ready_cb = self._on_grad_ready
+        self._overlap = True
+        self._armed = False
+        return True
+
+    def start_grad_sync_window(self) -> None:
+        """Call right before the backward of the LAST micro-batch of the step."""
+        if not getattr(self, "_overlap", False):
+            return
+        self._armed = True
+        self._pending = list(self._bucket_params)
+        self._launched = [False] * len(self._buckets)
+        self._handles = []
+
+    def _on_grad_ready(self, p) -> None:
+        if not getattr(self, "_armed", False):
+            return
+        for b in p._grad_buckets:
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and not self._bucket_late[b]:
+                self._launch_bucket(b)
+
+    def _launch_bucket(self, b: int) -> None:
+        lo, hi, owner = self._buckets[b]
+        t = self.grad_buffer[lo:hi]
+        scale = self.extra_grad_scale / (self.dp_size if self.average_over_dp else 1.0)
+        if scale != 1.0:
+            t.mul_(scale)
+        if owner is None:
+            h = dist.all_reduce(t, group=self.dp_group, async_op=True)
+        else:
+            dst = dist.get_global_rank(self.dp_group, owner) if self.dp_group is not None else owner
+            h = dist.reduce(t, dst=dst, group=self.dp_group, async_op=True)
+        self._handles.append(h)
+        self._launched[b] = True
+
+    def _finish_overlapped_reduce(self) -> torch.Tensor:
+        for b in range(len(self._buckets)):
+            if not self._launched[b]:
+                self._launch_bucket(b)
+        for h in self._handles:
+            h.wait()
+        self._armed = False
+        self._handles = []
+        return self.grad_buffer[self.shard_lo:self.shard_hi] if self.zero1 else self.grad_buffer
+
     def _reduce_over_dp(self) -> torch.Tensor:
         """Returns this rank's gradient shard (view) after the DP reduction."""
+        if getattr(self, "_armed", False):
+            return self._finish_overlapped_reduce()
         if self.extra_grad_scale != 1.0:
             self.grad_buffer.mul_(self.extra_grad_scale)
         if self.dp_size == 1:

@@ -23,6 +23,7 @@ import torch.nn.functional as F
 import torch.distributed as dist
 
 from . import state as ps
+from .grad_hooks import mark_main_grad_written
 from . import mappings as mp
 from .. import ops
 
@@ -106,7 +107,7 @@ def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, weight: torch.Tensor) -> Optio
     main_grad = getattr(weight, "main_grad", None)
     if main_grad is not None:
         ops.gemm_wgrad(dy2d, x2d, out=main_grad, accumulate=True)
-        weight.grad_added_to_main_grad = True
+        mark_main_grad_written(weight)
         return None
     return ops.gemm_wgrad(dy2d, x2d).to(weight.dtype)
 
@@ -116,7 +117,7 @@ def _wgrad_fused_gather(fused, dy2d: torch.Tensor, x_local2d: torch.Tensor, weig
     main_grad = getattr(weight, "main_grad", None)
     if main_grad is not None:
         fused.all_gather_wgrad(dy2d, x_local2d, main_grad, True)
-        weight.grad_added_to_main_grad = True
+        mark_main_grad_written(weight)
         return None
     out = torch.empty(weight.shape, dtype=weight.dtype, device=weight.device)
     return fused.all_gather_wgrad(dy2d, x_local2d, out, False)
@@ -624,7 +625,7 @@ class _VocabParallelEmbeddingFn(torch.autograd.Function):
             if main_grad is not None and main_grad.dtype == torch.float32 and g.dtype == torch.bfloat16:
                 ops._count()
                 ops.C().embedding_bwd_(main_grad, ids, g, ctx.vocab_start, seq_first)
-                weight.grad_added_to_main_grad = True
+                mark_main_grad_written(weight)
                 return None, None, None, None, None, None
             dw = torch.zeros(ctx.num_emb, g.shape[-1], dtype=torch.float32, device=g.device)
             ops._count()

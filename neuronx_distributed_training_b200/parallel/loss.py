@@ -18,6 +18,7 @@ import torch
 import torch.distributed as dist
 
 from . import state as ps
+from .grad_hooks import mark_main_grad_written
 from .. import ops
 
 
@@ -199,7 +200,7 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
                 # scale by the upstream scalar on the device: no host read of g_loss (a sync here would stall the
                 # launch queue once per micro-batch and forbid CUDA-graph capture), no [V, H] temporary
                 ctx.weight.main_grad.addcmul_(dw_acc, g_loss.to(dw_acc.dtype))
-                ctx.weight.grad_added_to_main_grad = True
+                mark_main_grad_written(ctx.weight)
             else:
                 gw = (dw_acc * g_loss).to(ctx.wdtype)
         return gh, gw, None, None, None, None, None

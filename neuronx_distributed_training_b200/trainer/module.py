@@ -152,6 +152,12 @@ class BaseModelModule:
             self.optimizer = ChainedOptimizer([o_dense, o_exp], [(), (ps.get_expert_model_parallel_group(),)])
         else:
             self.optimizer = DistributedOptimizer(groups, **common)
+        # overlap the data-parallel gradient reduction with the last micro-batch's backward (non-pipelined path);
+        # bucket size = the reference's `bucket_size_collectives` (MB)
+        if bool(ocfg.get("overlap_grad_reduce", False)) or os.environ.get("NXDT_OVERLAP_GRAD_REDUCE", "0") == "1":
+            if self.dims.pp == 1 and isinstance(self.optimizer, DistributedOptimizer):
+                if self.optimizer.enable_grad_reduce_overlap(float(self.cfg.get("bucket_size_collectives", 256) or 256)):
+                    log.info("data-parallel gradient reduction overlaps backward (%d buckets)", len(self.optimizer._buckets))
         sched = ocfg.get("sched", None)
         self.lr_scheduler = prepare_lr_scheduler(self.optimizer, sched, max_steps) if sched is not None else None
         return self.optimizer, self.lr_scheduler
@@ -185,7 +191,12 @@ class BaseModelModule:
             if is_training and self.use_mb_overlap and self.num_microbatches >= 2:
                 running = self._overlapped_microbatches(batch)
                 batch = {}          # nothing left for the sequential loop below
+            n_seen = 0
             for mb in (self.get_batch_iterator(batch) if batch else ()):
+                n_seen += 1
+                if is_training and n_seen == self.num_microbatches and self.optimizer is not None \
+                        and hasattr(self.optimizer, "start_grad_sync_window"):
+                    self.optimizer.start_grad_sync_window()      # DP reduction of finished buckets overlaps this backward
                 if is_training and self._graphed_microbatch(mb, running):
                     continue
                 with contextlib.nullcontext() if is_training else torch.no_grad():

@@ -81,3 +81,8 @@ def test_resume_with_a_different_data_parallel_size(tmp_path, dp_save, dp_resume
     assert len(saved) == 4 and len(resumed) == 4 and len(full) == 8
     for a, b in zip(full, saved + resumed):
         assert abs(a - b) < 2e-5, (full, saved, resumed)
+
+
+@pytest.mark.parametrize("dp", [2, 4])
+def test_overlapped_gradient_reduction_matches(dp):
+    run_dist("zero1_overlap.py", dp)
