@@ -103,6 +103,7 @@ class ResumableBatchSampler(Sampler):
         self.gbs, self.rank, self.size = global_batch_size, dp_rank, dp_size
         self.per_rank = global_batch_size // dp_size
         self.drop_last, self.shuffle, self.seed = drop_last, shuffle, seed
+        self.pad_to_global_batch = False      # with drop_last=False: fill the last batch with index -1 (padding samples)
 
     def __len__(self):
         n = (self.total - self.consumed % max(self.total, 1))
@@ -126,8 +127,12 @@ class ResumableBatchSampler(Sampler):
             i += self.gbs
         if not self.drop_last and i < self.total:
             rem = order[i:]
-            per = (len(rem) + self.size - 1) // self.size
-            yield rem[self.rank * per: (self.rank + 1) * per]
+            if self.pad_to_global_batch:
+                rem = rem + [-1] * (self.gbs - len(rem))
+                yield rem[self.rank * self.per_rank: (self.rank + 1) * self.per_rank]
+            else:
+                per = (len(rem) + self.size - 1) // self.size
+                yield rem[self.rank * per: (self.rank + 1) * per]
 
 
 def default_collate(samples: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:

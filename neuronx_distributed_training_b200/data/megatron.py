@@ -270,6 +270,12 @@ class GPTDataset(Dataset):
         return np.concatenate(parts)
 
     def __getitem__(self, idx: int) -> Dict[str, torch.Tensor]:
+        if idx < 0:
+            # padding sample (data.pad_samples_to_global_batch_size): a real sample with an all-zero loss mask, so the
+            # last partial validation batch has the global batch shape without contributing to the loss
+            out = self[0]
+            out["loss_mask"] = torch.zeros_like(out["loss_mask"])
+            return out
         text = torch.from_numpy(self._tokens(idx).astype(np.int64))
         need = self.seq_length + self.add_extra_token
         if text.numel() < need:                  # last partial sample when drop_last=False
@@ -312,6 +318,10 @@ class BlendableDataset(Dataset):
         return self.size
 
     def __getitem__(self, idx):
+        if idx < 0:
+            out = self[0]
+            out["loss_mask"] = torch.zeros_like(out["loss_mask"])
+            return out
         d = int(self.dataset_index[idx])
         return self.datasets[d][int(self.dataset_sample_index[idx]) % len(self.datasets[d])]
 
@@ -391,6 +401,7 @@ def get_tokenizer(cfg: Optional[Config]):
         import sentencepiece as spm
         sp = spm.SentencePieceProcessor()
         sp.Load(cfg.get("model"))
+        sp.legacy = bool(cfg.get("sentencepiece_legacy", False))      # NeMo's flag; special tokens are plain pieces here
         return sp
     from transformers import AutoTokenizer
     return AutoTokenizer.from_pretrained(cfg.get("type", cfg.get("model", None)), use_fast=bool(cfg.get("use_fast", True)))
@@ -441,12 +452,18 @@ class MegatronDataModule(BaseDataModule):
             no_seqlen_plus_one_input_tokens=bool(d.get("no_seqlen_plus_one_input_tokens", False)))
         return self._ds
 
-    def _loader(self, ds, consumed: int):
+    def _loader(self, ds, consumed: int, drop_last: bool = True, pad: bool = False):
         if ds is None:
             return None
         d = self.cfg.data
+        impl = str(d.get("data_impl", "mmap"))
+        if impl not in ("mmap", "lazy", "cached", "infer"):
+            raise ValueError(f"data.data_impl={impl!r}: only Megatron indexed datasets (.bin/.idx, memory-mapped) are supported")
+        # data.skip_warmup: the memory-mapped reader never pre-touches the file, so the flag has nothing to skip
         cls = MegatronRandomBatchSampler if str(d.get("dataloader_type", "single")) == "cyclic" else ResumableBatchSampler
-        sampler = cls(len(ds), consumed, self.global_batch_size, self.dp_rank, self.dp_size, drop_last=True, seed=self.seed)
+        sampler = cls(len(ds), consumed, self.global_batch_size, self.dp_rank, self.dp_size, drop_last=drop_last, seed=self.seed)
+        if pad and not drop_last and hasattr(sampler, "pad_to_global_batch"):
+            sampler.pad_to_global_batch = True
         return DataLoader(ds, batch_sampler=sampler, collate_fn=default_collate, num_workers=int(d.get("num_workers", 0)),
                           pin_memory=torch.cuda.is_available(), persistent_workers=int(d.get("num_workers", 0)) > 0)
 
@@ -454,7 +471,11 @@ class MegatronDataModule(BaseDataModule):
         return self._loader(self.build()[0], self.consumed_samples)
 
     def val_dataloader(self):
-        return self._loader(self.build()[1], 0)
+        d = self.cfg.data
+        # reference megatron/data_module.py:62-75: the last partial validation batch is dropped unless
+        # validation_drop_last is False, in which case it may be padded up to the global batch
+        return self._loader(self.build()[1], 0, drop_last=bool(d.get("validation_drop_last", True)),
+                            pad=bool(d.get("pad_samples_to_global_batch_size", False)))
 
     def test_dataloader(self):
         return self._loader(self.build()[2], 0)

@@ -112,6 +112,9 @@ class Trainer:
         # strip the "-vN" version suffix PTL appends (reference nlp_overrides.py:572-578)
         user_content = self.dump_checkpoint()
         model_sd = self.model.state_dict()
+        if em is not None and em.save_bf16:
+            # exp_manager.save_bf16: store the model weights in bf16 regardless of the training dtype
+            model_sd = {k: (v.to(torch.bfloat16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in model_sd.items()}
         opt = self.model.optimizer
         if em is not None and em.checkpoint_callback_params.use_master_weights_in_ckpt and opt.master is not None:
             user_content["master_weights_in_ckpt"] = True
@@ -224,6 +227,10 @@ class Trainer:
             self.validate()
         t_start = time.time()
         cb = self.exp_manager.checkpoint_callback if self.exp_manager else None
+        emc = self.exp_manager.cfg if self.exp_manager else None
+        if self.max_time is None and emc is not None and emc.max_time_per_run:
+            self.max_time = _parse_max_time(emc.max_time_per_run)       # NeMo's per-run wall-clock budget
+        first_step_pending = bool(emc is not None and emc.enable_recovery_time_instrumentation)
         # hang detection: top-level `neuron_rt_exec_timeout` (the reference's runtime timeout knob) or
         # NXDT_STEP_TIMEOUT, in seconds; 0 / unset = off
         timeout = float(os.environ.get("NXDT_STEP_TIMEOUT", model.cfg.get("neuron_rt_exec_timeout", 0) or 0) or 0)
@@ -248,6 +255,14 @@ class Trainer:
                     if self.ema is not None:
                         self.ema.update(self.global_step + 1)
                     n_batches += 1
+                    if first_step_pending:
+                        # time from process start-up (exp manager creation) to the end of the first step after a (re)start
+                        if torch.cuda.is_available():
+                            torch.cuda.synchronize()
+                        rec = time.time() - self.exp_manager.t_created
+                        log.info("recovery time: first training step finished %.2f s after start-up (resumed=%s)", rec, bool(ckpt_path))
+                        self.callback_metrics["recovery_time_s"] = rec
+                        first_step_pending = False
                     if self.watchdog is not None:
                         self.watchdog.pet()
                     self.global_step += 1

@@ -80,8 +80,8 @@ class ExpManagerConfig:
     step_timing_kwargs: Optional[dict] = None
     log_local_rank_0_only: bool = False
     log_global_rank_0_only: bool = False
-    log_parameter_norm: bool = False
-    log_gradient_norm: bool = False
+    log_parameter_norm: bool = True       # reference defaults (utils/exp_manager.py:52-53)
+    log_gradient_norm: bool = True
     enable_recovery_time_instrumentation: bool = False
     save_xser: bool = True
     load_xser: bool = True
@@ -359,12 +359,21 @@ class ExpManager:
             with open(os.path.join(self.log_dir, "cmd-args.log"), "a") as f:
                 f.write(" ".join(sys.argv) + "\n")
             self.loggers.append(JsonlLogger(os.path.join(self.log_dir, "metrics.jsonl")))
+            for src in (c.files_to_copy or []):          # keep the launch inputs next to the logs (NeMo behaviour)
+                try:
+                    import shutil
+                    shutil.copy(str(src), self.log_dir)
+                except OSError as e:
+                    log.warning("files_to_copy: could not copy %s (%s)", src, e)
             if c.create_tensorboard_logger:
                 self.loggers.append(TensorBoardLogger(self.log_dir, **(c.summary_writer_kwargs or {})))
             if c.create_wandb_logger:
                 self.loggers.append(WandbLogger(self.log_dir, **(c.wandb_logger_kwargs or {})))
             if c.create_mlflow_logger:
                 self.loggers.append(MLflowLogger(self.log_dir, **(c.mlflow_logger_kwargs or {})))
+        self.t_created = time.time()                   # reference point for recovery-time instrumentation
+        if c.seconds_to_sleep and rank != 0:
+            time.sleep(float(c.seconds_to_sleep))
         self.timing = TimingCallback() if c.log_step_timing else None
         self.checkpoint_callback = None
         if c.create_checkpoint_callback:

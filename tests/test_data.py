@@ -101,3 +101,22 @@ def test_ckpt_name_parsing():
     p = "/x/checkpoints/hf_llama3_8B--step=10-consumed_samples=10240.0.ckpt"
     assert consumed_samples_from_path(p) == 10240 and step_from_path(p) == 10
     assert consumed_samples_from_path(None) == 0
+
+
+def test_validation_padding_samples(tmp_path):
+    """data.validation_drop_last=False + pad_samples_to_global_batch_size: the last partial batch is filled with index -1,
+    which the dataset turns into a sample that carries no loss."""
+    from neuronx_distributed_training_b200.data.base import ResumableBatchSampler
+    prefix, docs = _make_corpus(tmp_path)
+    indexed = MMapIndexedDataset(prefix)
+    ds = GPTDataset("valid", prefix, np.arange(len(docs), dtype=np.int32), indexed, num_samples=10, seq_length=16, seed=7)
+    pad = ds[-1]
+    assert pad["tokens"].shape == ds[0]["tokens"].shape and float(pad["loss_mask"].sum()) == 0.0
+    assert float(ds[0]["loss_mask"].sum()) > 0
+    s = ResumableBatchSampler(10, 0, 4, dp_rank=1, dp_size=2, drop_last=False)
+    s.pad_to_global_batch = True
+    batches = list(s)
+    assert batches == [[2, 3], [6, 7], [-1, -1]] and all(len(b) == 2 for b in batches)
+    s0 = ResumableBatchSampler(10, 0, 4, dp_rank=0, dp_size=2, drop_last=False)
+    s0.pad_to_global_batch = True
+    assert list(s0)[-1] == [8, 9]

@@ -118,3 +118,21 @@ def test_unknown_recompute_class_and_exp_manager_keys(tmp_path):
         HFLlamaModule(cfg, None).setup()
     with pytest.raises(ValueError):
         ExpManagerConfig.from_config(from_dict({"not_a_key": 1}))
+
+
+def test_exp_manager_small_options(tmp_path):
+    """files_to_copy, save_bf16, enable_recovery_time_instrumentation, max_time_per_run."""
+    src = tmp_path / "launch_note.txt"
+    src.write_text("hello")
+    cfg = _cfg(str(tmp_path / "run"), max_steps=2)
+    cfg.exp_manager["files_to_copy"] = [str(src)]
+    cfg.exp_manager["save_bf16"] = True
+    cfg.exp_manager["enable_recovery_time_instrumentation"] = True
+    cfg.exp_manager["max_time_per_run"] = "00:01:00:00"
+    tr, mod = _fit(cfg)
+    assert (tmp_path / "run" / "launch_note.txt").read_text() == "hello"
+    assert tr.max_time == 3600.0 and tr.callback_metrics["recovery_time_s"] > 0
+    from neuronx_distributed_training_b200.checkpoint import io as ckpt_io
+    ck = sorted(glob.glob(str(tmp_path / "run" / "checkpoints" / "*.ckpt")))[-1]
+    m, _, _ = ckpt_io.load_checkpoint(os.path.dirname(ck), os.path.basename(ck), optimizer=False)
+    assert all(v.dtype == torch.bfloat16 for v in m.values() if torch.is_tensor(v) and v.is_floating_point())
