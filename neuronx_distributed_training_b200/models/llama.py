@@ -355,6 +355,7 @@ class LlamaForCausalLM(nn.Module):
                                                 use_cpu_initialization=config.use_cpu_initialization)
             if config.tie_word_embeddings and with_embedding:
                 self.lm_head.weight = self.model.embed_tokens.weight
+                self.lm_head.weight._multi_use = True      # two gradient contributions per backward (embedding + head)
         else:
             self.lm_head = None
 

@@ -394,6 +394,9 @@ class GPTModel(nn.Module):
         self.cfg = cfg
         self.language_model = TransformerLanguageModel(cfg, device, layer_range, with_embedding, with_head)
         self.with_head = with_head
+        if with_head and self.language_model.output_layer is None and hasattr(self.language_model, "embedding"):
+            # tied output layer: the embedding weight receives two gradient contributions per backward
+            self.language_model.embedding.word_embeddings.weight._multi_use = True
 
     @property
     def lm_head(self):
@@ -407,7 +410,9 @@ class GPTModel(nn.Module):
         if not hasattr(lm, "embedding"):
             raise RuntimeError("tied embeddings are not supported across pipeline stages "
                                "(set share_embeddings_and_output_weights: False); reference known_issues.rst:14-24")
-        return lm.embedding.word_embeddings.weight
+        w = lm.embedding.word_embeddings.weight
+        w._multi_use = True                    # tied: written by the embedding backward AND the output-layer backward
+        return w
 
     def forward(self, input_ids=None, labels=None, position_ids=None, loss_mask=None, attention_mask=None,
                 hidden=None, seq_len=None, return_logits: bool = False):

@@ -484,6 +484,10 @@ class GQAQKVColumnParallelLinear(nn.Module):
                 g = dist.new_group(ranks=sub)
                 if ps.get_rank() in sub:
                     self._kv_replica_group = g
+        if self._kv_replica_group is not None:
+            # their gradients get one more reduction after backward: not eligible for an early data-parallel reduce
+            for p in ((self.weight_qkv,) if self.fuse_qkv else (self.weight_k, self.weight_v)):
+                p.kv_replica_sync = True
 
     def _sync_replica_grads(self, *params):
         """Sum KV gradients over the ranks that hold replicas of the same logical head."""
