@@ -101,6 +101,6 @@ class DPOBaseModel:
         ref_c = batch["reference_chosen_logps"].to(pi_c.dtype)
         ref_r = batch["reference_rejected_logps"].to(pi_c.dtype)
         loss, cr, rr = dpo_loss(pi_c, pi_r, ref_c, ref_r, beta, str(dcfg.get("loss_type", "sigmoid")))
-        module._logged["chosen_rewards"] = float(cr.mean())
-        module._logged["rejected_rewards"] = float(rr.mean())
+        module._logged["chosen_rewards"] = cr.mean().detach()      # read back only when metrics are logged
+        module._logged["rejected_rewards"] = rr.mean().detach()
         return loss, None

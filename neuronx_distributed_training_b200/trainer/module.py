@@ -344,7 +344,7 @@ class BaseModelModule:
                 m["gradient_norm"] = float(self.optimizer.grad_norm)
         if self.log_parameter_norm:
             m["parameter_norm"] = float(self.parameter_norm())
-        m.update(self._logged)
+        m.update({k: (float(v) if torch.is_tensor(v) else v) for k, v in self._logged.items()})
         m["throughput"] = self.throughput.get_throughput()
         m["throughput_peak"] = self.throughput.throughput_peak
         return m

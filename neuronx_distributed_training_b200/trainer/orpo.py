@@ -30,6 +30,6 @@ class ORPOBaseModel:
         beta = float(ocfg.get("beta", 0.1))
         logp_c, logp_r = sequence_logps(module.model, concatenated_inputs(batch), average=True)
         loss, cr, rr = orpo_loss(logp_c, logp_r, beta)
-        module._logged["chosen_rewards"] = float(cr.mean())
-        module._logged["rejected_rewards"] = float(rr.mean())
+        module._logged["chosen_rewards"] = cr.mean().detach()      # read back only when metrics are logged
+        module._logged["rejected_rewards"] = rr.mean().detach()
         return loss, None
