@@ -60,8 +60,11 @@ class FusedTP:
         self.push = os.environ.get("NXDT_AG_MODE", "pull") == "push"
         total = self.stage_off[1] + self.max_stage_bytes
         try:
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")     # newer torch enables every group implicitly and deprecates the call
+                symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:  # noqa: BLE001 - absent / no-op on newer torch
             pass
         self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
         self.buf.zero_()
