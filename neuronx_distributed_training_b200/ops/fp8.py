@@ -129,3 +129,54 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] 
     gq, gs = quantize_cols_transposed(dy)         # [N, M]
     xq, xs = quantize_cols_transposed(x)          # [K, M]
     return gemm(gq, gs, xq, xs, out=out, accumulate=accumulate, out_dtype=dy.dtype)
+
+
+# ================================================================================================================
+# MX (micro-scaling) variant: one power-of-two scale (E8M0 byte) per 1 x 32 block along the reduction dimension -- the
+# format `tcgen05.mma.kind::mxf8f6f4.block_scale` consumes.  Reference implementation + the scale-factor packing the
+# tensor core expects; the CUDA kernel for it is not written yet (docs/ROUND2_PLAN.md §4).
+# ================================================================================================================
+MX_BLOCK = 32
+
+
+def quantize_mx(x: torch.Tensor):
+    """x [R, C] (C % 32 == 0) -> (e4m3 bytes [R, C], E8M0 scale bytes [R, C/32]);  value = q * 2^(scale - 127).
+    The scale is the smallest power of two that brings the block's amax into the e4m3 range (OCP MX recipe)."""
+    R, C = x.shape
+    assert C % MX_BLOCK == 0
+    xb = x.float().reshape(R, C // MX_BLOCK, MX_BLOCK)
+    amax = xb.abs().amax(dim=-1)
+    # exponent e with amax / 2^e <= 448:  e = ceil(log2(amax / 448)); empty blocks get the neutral scale 2^0
+    e = torch.where(amax > 0, torch.ceil(torch.log2(amax / E4M3_MAX)), torch.zeros_like(amax)).clamp(-127, 127)
+    q = (xb / torch.exp2(e)[..., None]).to(torch.float8_e4m3fn)
+    return q.reshape(R, C).view(torch.uint8), (e + 127).to(torch.uint8)
+
+
+def dequantize_mx(q: torch.Tensor, scale_e8m0: torch.Tensor) -> torch.Tensor:
+    R, C = q.shape
+    s = torch.exp2(scale_e8m0.float() - 127.0)
+    return (q.view(torch.float8_e4m3fn).float().reshape(R, C // MX_BLOCK, MX_BLOCK) * s[..., None]).reshape(R, C)
+
+
+def gemm_mx_reference(a_q, a_s, b_q, b_s, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """(A_q . B_q^T) with both operands MX-quantised along K."""
+    return (dequantize_mx(a_q, a_s) @ dequantize_mx(b_q, b_s).t()).to(out_dtype)
+
+
+def pack_mx_scales(scale_e8m0: torch.Tensor) -> torch.Tensor:
+    """Scale bytes [R, KB] (KB = K/32 blocks) -> the tensor-core layout: tiles of 128 rows x 4 k-blocks, 512 bytes each,
+    byte offset inside a tile = (r % 32) * 16 + (r // 32) * 4 + (kb % 4)   (one 16-byte line per TMEM lane, four
+    32-bit words = the four 32-row groups, the byte inside a word = the k-block, selected by the MMA's scale-factor id).
+    Returns [ceil(R/128), ceil(KB/4), 512] uint8 (rows / blocks beyond the matrix are the neutral scale 127)."""
+    R, KB = scale_e8m0.shape
+    rt, kt = (R + 127) // 128, (KB + 3) // 4
+    padded = torch.full((rt * 128, kt * 4), 127, dtype=torch.uint8, device=scale_e8m0.device)
+    padded[:R, :KB] = scale_e8m0
+    t = padded.reshape(rt, 4, 32, kt, 4)                  # [row tile, r // 32, r % 32, k tile, kb % 4]
+    return t.permute(0, 3, 2, 1, 4).reshape(rt, kt, 512).contiguous()
+
+
+def unpack_mx_scales(packed: torch.Tensor, R: int, KB: int) -> torch.Tensor:
+    rt, kt, _ = packed.shape
+    t = packed.reshape(rt, kt, 32, 4, 4).permute(0, 3, 2, 1, 4).reshape(rt * 128, kt * 4)
+    return t[:R, :KB].contiguous()

@@ -105,3 +105,26 @@ def test_small_llama_in_fp8_gradients_track_the_unquantised_model_and_it_trains(
     for n, g in grads["ref"].items():
         assert _rel(grads["fp8"][n], g) < 0.12, (n, _rel(grads["fp8"][n], g))    # e4m3 has 3 mantissa bits
         assert abs(grads["fp8"][n].norm() / g.norm() - 1.0) < 0.05, n
+
+
+def test_mx_block_scaled_reference_and_scale_packing():
+    torch.manual_seed(3)
+    x = torch.randn(200, 256) * torch.logspace(-3, 3, 256)[None, :]       # magnitudes vary along K: per-32 blocks matter
+    q, s = fp8.quantize_mx(x)
+    assert q.shape == (200, 256) and s.shape == (200, 8) and s.dtype == torch.uint8
+    assert _rel(fp8.dequantize_mx(q, s), x) < 0.04
+    qr, sr = fp8.quantize_rows(x)                                           # one scale per row loses the small columns
+    small = slice(0, 64)
+    assert _rel(fp8.dequantize_mx(q, s)[:, small], x[:, small]) < 0.05 < _rel(fp8.dequantize(qr, sr)[:, small], x[:, small])
+    w = torch.randn(96, 256) * 0.1
+    wq, ws = fp8.quantize_mx(w)
+    assert _rel(fp8.gemm_mx_reference(q, s, wq, ws, torch.float32), x @ w.t()) < 0.05
+    # hardware scale layout: 128 rows x 4 k-blocks per 512-byte tile, offset (r % 32) * 16 + (r // 32) * 4 + kb % 4
+    packed = fp8.pack_mx_scales(s)
+    assert packed.shape == (2, 2, 512)
+    for (r, kb) in [(0, 0), (5, 3), (37, 1), (127, 7), (128, 4), (199, 6)]:
+        tile = packed[r // 128, kb // 4]
+        rr = r % 128
+        assert int(tile[(rr % 32) * 16 + (rr // 32) * 4 + kb % 4]) == int(s[r, kb])
+    assert torch.equal(fp8.unpack_mx_scales(packed, 200, 8), s)
+    assert int(packed[1, 0, (100 % 32) * 16 + (100 // 32) * 4]) == 127     # row 228 does not exist: neutral scale
