@@ -10,6 +10,11 @@ synthetic tokens, random-init weights.  The global batch is fixed (strong scalin
 One optimizer step = ``global_batch`` sequences; every timed step includes forward, backward, grad-norm
 clipping, the AdamW update and the LR schedule.
 
+Other named configs: ``--model llama2_7b --tp 2 --pp 2`` on 8 GPUs (BASELINE config 3: TP2 x PP2 x DP2, 1F1B, ZeRO-1),
+``--model llama3_70b`` on 8 GPUs (config 5).  Experiment switches (all default off): ``NXDT_CUDA_GRAPH=1`` (graph replay of
+the micro-batch), ``NXDT_MB_OVERLAP=1`` (two micro-batches on two streams, NCCL TP path), ``NXDT_FUSED_TP=0`` (NCCL TP
+path), ``NXDT_OVERLAP_GRAD_REDUCE=1`` (data-parallel reduction during backward), ``NXDT_FP8=1`` (e4m3 linear GEMMs).
+
 ``--impl reference`` would run the unmodified reference from baseline/_ref; it cannot be imported here
 (needs torch_xla / neuronx_distributed / nemo / lightning) so that arm reports unavailable.
 ``--impl baseline`` runs this framework with every hot op on the library path (NCCL + cuBLAS + SDPA).
