@@ -26,6 +26,7 @@ import torch.distributed as dist
 from .. import ops
 from ..parallel import state as ps
 from ..parallel.layers import param_is_tp_duplicate
+from ..parallel.grad_hooks import ordered_main_grad_update
 
 
 @dataclass
@@ -155,24 +156,13 @@ class DistributedOptimizer:
                 p.data = self.param_buffer[o:o + p.numel()].view(p.shape)
                 p.main_grad = self.grad_buffer[o:o + p.numel()].view(p.shape)
 
-    multi_stream = False        # set by the trainer module when micro-batches are issued on several CUDA streams
-    _last_hook_event = None     # then: orders the read-modify-write of main_grad across those streams
-
     @staticmethod
     def _make_hook():
         def hook(p):
             if p.grad is not None:
-                if p.grad.is_cuda and DistributedOptimizer.multi_stream:
-                    cur = torch.cuda.current_stream(p.grad.device)
-                    prev = DistributedOptimizer._last_hook_event
-                    if prev is not None:
-                        cur.wait_event(prev)
-                    p.main_grad.add_(p.grad.to(p.main_grad.dtype))
-                    ev = torch.cuda.Event()
-                    ev.record(cur)
-                    DistributedOptimizer._last_hook_event = ev
-                else:
-                    p.main_grad.add_(p.grad.to(p.main_grad.dtype))
+                g = p.grad
+                # ordered across streams when micro-batches run on several of them (parallel/grad_hooks.py)
+                ordered_main_grad_update(g.device, lambda: p.main_grad.add_(g.to(p.main_grad.dtype)))
                 p.grad = None
                 cb = getattr(p, "_grad_ready_cb", None)
                 if cb is not None:

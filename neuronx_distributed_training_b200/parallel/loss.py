@@ -18,7 +18,7 @@ import torch
 import torch.distributed as dist
 
 from . import state as ps
-from .grad_hooks import mark_main_grad_written
+from .grad_hooks import mark_main_grad_written, ordered_main_grad_update
 from .. import ops
 
 
@@ -199,7 +199,8 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
             if ctx.dw_is_main:
                 # scale by the upstream scalar on the device: no host read of g_loss (a sync here would stall the
                 # launch queue once per micro-batch and forbid CUDA-graph capture), no [V, H] temporary
-                ctx.weight.main_grad.addcmul_(dw_acc, g_loss.to(dw_acc.dtype))
+                w = ctx.weight
+                ordered_main_grad_update(dw_acc.device, lambda: w.main_grad.addcmul_(dw_acc, g_loss.to(dw_acc.dtype)))
                 mark_main_grad_written(ctx.weight)
             else:
                 gw = (dw_acc * g_loss).to(ctx.wdtype)

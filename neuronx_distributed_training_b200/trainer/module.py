@@ -221,14 +221,15 @@ class BaseModelModule:
 
     def _overlapped_microbatches(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """Forward + backward of the micro-batches, two at a time on two side streams.  Both streams share the flat
-        ``main_grad`` buffer: the wgrad GEMMs add into it with element-wise atomic TMA reductions, the small
-        read-modify-write accumulations are ordered by ``DistributedOptimizer.multi_stream``; per-stream scratch in the
+        ``main_grad`` buffer: the wgrad GEMMs add into it with element-wise atomic TMA reductions, the
+        read-modify-write accumulations are ordered by ``parallel.grad_hooks.ordered_main_grad_update``; per-stream scratch in the
         fused LM-head / cross-entropy keeps the two micro-batches apart.  Requires NCCL tensor parallelism (the fused
         TP kernels own every SM and one symmetric workspace, so they cannot run two at a time)."""
         from ..parallel import fused as fused_mod
         if fused_mod._FTP_CACHE:
             raise RuntimeError("microbatch_overlap needs the NCCL tensor-parallel path (do not call enable_fused_tp)")
-        DistributedOptimizer.multi_stream = True
+        from ..parallel.grad_hooks import set_multi_stream
+        set_multi_stream(True)
         main = torch.cuda.current_stream()
         if self._mb_streams is None:
             self._mb_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
