@@ -279,6 +279,7 @@ struct RsArgs {
   uint32_t epoch;
   const uint32_t* epoch_ptr;
   int rank, tp, rows_per_rank, N, num_n_blocks;
+  int self_reset;                      // 1: the last reducer of a row-block zeroes its arrival counter (no host-side clear)
 };
 
 struct RsMaps {
@@ -378,6 +379,17 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
     __syncthreads();
+    if (rs.self_reset && threadIdx.x == 0) {
+      // counter_local[512 + rb] counts the reducers that are done with row-block rb; the last one re-arms both counters.
+      // Safe: arrivals of the next call that uses this parity are only sent after my next handshake, i.e. after this
+      // kernel has completed.
+      const uint32_t done = atomicAdd(rs.counter_local + 512 + rb, 1u);
+      if (done == (uint32_t)(n_chunks - 1)) {
+        rs.counter_local[512 + rb] = 0u;
+        __threadfence();
+        rs.counter_local[rb] = 0u;
+      }
+    }
   }
   dbg_stamp(3);
 }
@@ -568,7 +580,16 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
     const char* e = std::getenv("NXDT_RS_CLEAR_KERNEL");
     return e != nullptr && e[0] == '1';
   }();
-  if (epoch_ptr != 0 && clear_with_kernel) {
+  // NXDT_RS_SELF_RESET=1 (second experiment): no clear at all, the kernel re-arms its counters itself
+  static const bool self_reset = [] {
+    const char* e = std::getenv("NXDT_RS_SELF_RESET");
+    return e != nullptr && e[0] == '1';
+  }();
+  rs.self_reset = self_reset ? 1 : 0;
+  TORCH_CHECK(!self_reset || rows_per_rank / 128 <= 512, "self-resetting counters support up to 512 row-blocks per rank");
+  if (self_reset) {
+    if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
+  } else if (epoch_ptr != 0 && clear_with_kernel) {
     bump_epoch_clear_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr), rs.counter_local,
                                                    rows_per_rank / 128);
   } else {

@@ -32,6 +32,7 @@ class World:
         self.slab = [[{}, {}] for _ in range(tp)]                     # slab[owner][par][(src, rb, nt)] = epoch
         self.slab_reading = [[{}, {}] for _ in range(tp)]               # slab_reading[owner][par][rb] = epoch being reduced
         self.errors = []
+        self.done = {}
 
 
 def kernel_ag(w, r, epoch, par):
@@ -60,6 +61,9 @@ def kernel_ag(w, r, epoch, par):
                     yield
             yield
     return [comm()] + [gemm(c) for c in range(N_CTA)]
+
+
+SELF_RESET = {"on": False}     # protocol variant: no host-side clear, the last reducer of a row-block re-arms its counter
 
 
 def kernel_rs(w, r, epoch, par):
@@ -101,6 +105,12 @@ def kernel_rs(w, r, epoch, par):
                         w.errors.append(f"rank {r} call {epoch}: slab tile ({src},{rb},{nt}) = {w.slab[r][par].get((src, rb, nt))}")
             yield
             w.slab_reading[r][par].pop(rb, None)
+            if SELF_RESET["on"]:
+                key = (r, par, rb)
+                w.done[key] = w.done.get(key, 0) + 1
+                if w.done[key] == NTILE:                                 # every reducer of this row-block has consumed it
+                    w.done[key] = 0
+                    w.counter[r][par][rb] = 0
     return [cta(c) for c in range(N_CTA)]
 
 
@@ -135,7 +145,8 @@ def rank_program(w, r, ops, replays, boundary_barriers):
                 w.xstage[r][par] = epoch                              # staging copy (stream order, before the kernel)
                 yield kernel_ag(w, r, epoch, par)
             else:
-                w.counter[r][par] = [0] * BLOCKS                      # memset (stream order, before the kernel)
+                if not SELF_RESET["on"]:
+                    w.counter[r][par] = [0] * BLOCKS                  # memset (stream order, before the kernel)
                 yield kernel_rs(w, r, epoch, par)
 
 
@@ -179,6 +190,18 @@ def test_protocol_has_no_lost_signal_or_stale_read(ops, boundary_barriers):
     for seed in range(60):
         errors = run(ops, replays, boundary_barriers, seed)
         assert not errors, errors[:3]
+
+
+@pytest.mark.parametrize("ops", [("ag", "rs"), ("rs", "rs", "rs"), ("ag", "rs", "agw", "rs", "ag")])
+def test_self_resetting_counters_variant(ops):
+    """NXDT_RS_SELF_RESET: arrivals may even precede the owner's kernel start, nothing is ever wiped."""
+    SELF_RESET["on"] = True
+    try:
+        for seed in range(60):
+            assert not run(ops, 3 if len(ops) % 2 == 0 else 1, False, seed)
+            assert not run(ops, 3, True, seed)
+    finally:
+        SELF_RESET["on"] = False
 
 
 def test_three_ranks():
