@@ -321,6 +321,37 @@ class BaseModelModule:
             dist.all_reduce(loss, group=ppg)
         return loss
 
+    @torch.no_grad()
+    def predict_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0) -> Dict[str, torch.Tensor]:
+        """Greedy next-token predictions and per-token log-probs of the labels for one batch (non-pipelined models)."""
+        if self.dims.pp > 1:
+            raise NotImplementedError("predict_step is implemented for pipeline_model_parallel_size == 1")
+        from ..parallel.loss import from_parallel_logits_to_logprobs
+        batch = get_batch_on_this_context_parallel_rank(self.to_device(batch))
+        self.model.eval()
+        try:
+            with self.autocast_ctx():
+                _, logits = self.model(input_ids=batch["input_ids"], labels=None)          # [B, S, V/TP]
+        finally:
+            self.model.train()
+        tp_group = ps.get_tensor_model_parallel_group()
+        local_max, local_arg = logits.float().max(dim=-1)
+        vocab_start = ps.get_tensor_model_parallel_rank() * logits.shape[-1]
+        if ps.group_size(tp_group) > 1:
+            gmax = local_max.clone()
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=tp_group)
+            cand = torch.where(local_max == gmax, local_arg + vocab_start, torch.full_like(local_arg, 1 << 40))
+            dist.all_reduce(cand, op=dist.ReduceOp.MIN, group=tp_group)
+            pred = cand
+        else:
+            pred = local_arg
+        out = {"predictions": pred}
+        if "labels" in batch and batch["labels"] is not None:
+            labels = batch["labels"]
+            shifted = torch.cat([labels[:, 1:], labels.new_full((labels.shape[0], 1), -100)], dim=1)
+            out["logprobs"] = from_parallel_logits_to_logprobs(logits, shifted)
+        return out
+
     # ---- metrics -------------------------------------------------------------------------------------
     @torch.no_grad()
     def parameter_norm(self) -> torch.Tensor:

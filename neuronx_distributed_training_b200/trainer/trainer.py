@@ -200,6 +200,66 @@ class Trainer:
         log.info("validation: val_loss=%.5f (%d batches)", val, len(losses))
         return val
 
+    # ---- test / predict (the evaluation and prediction loops of the reference trainer, nlp_overrides.py:264-533) -----
+    def _attach(self, model, datamodule, ckpt_path: Optional[str]):
+        """Set a model / data module up outside ``fit`` (weights from ``ckpt_path`` when given)."""
+        self.model, self.datamodule = model, datamodule
+        model.trainer = self
+        if datamodule is not None:
+            datamodule.setup(ckpt_path)
+        model.setup("test")
+        if getattr(model, "optimizer", None) is None:
+            model.configure_optimizers(self.max_steps if self.max_steps > 0 else None)
+        if ckpt_path:
+            self.restore(ckpt_path, weight_init_only=True)
+
+    def test(self, model=None, datamodule=None, ckpt_path: Optional[str] = None) -> Optional[float]:
+        """Mean loss over ``test_dataloader`` (``limit_test_batches`` applies); logged as ``test_loss``."""
+        if model is not None:
+            self._attach(model, datamodule, ckpt_path)
+        loader = self.datamodule.test_dataloader() if self.datamodule is not None and hasattr(self.datamodule, "test_dataloader") else None
+        if loader is None:
+            return None
+        try:
+            n_total = len(loader)
+        except TypeError:
+            n_total = None
+        n = self._limit(self.limit_test_batches, n_total)
+        losses = []
+        for i, batch in enumerate(loader):
+            if i >= n:
+                break
+            with nvtx_range("test_step"):
+                losses.append(self.model.validation_step(batch, i))
+        if not losses:
+            return None
+        val = float(torch.stack([l.detach().float() for l in losses]).mean())
+        self.callback_metrics["test_loss"] = val
+        if self.exp_manager:
+            self.exp_manager.log_metrics({"test_loss": val}, self.global_step)
+        log.info("test: test_loss=%.5f (%d batches)", val, len(losses))
+        return val
+
+    def predict(self, model=None, datamodule=None, ckpt_path: Optional[str] = None, dataloader=None) -> list:
+        """Runs ``model.predict_step(batch, idx)`` over a dataloader (``predict_dataloader`` of the data module, else its
+        test / validation loader) and returns the list of per-batch outputs."""
+        if model is not None:
+            self._attach(model, datamodule, ckpt_path)
+        loader = dataloader
+        if loader is None and self.datamodule is not None:
+            for name in ("predict_dataloader", "test_dataloader", "val_dataloader"):
+                fn = getattr(self.datamodule, name, None)
+                loader = fn() if fn is not None else None
+                if loader is not None:
+                    break
+        if loader is None:
+            return []
+        outs = []
+        for i, batch in enumerate(loader):
+            with nvtx_range("predict_step"):
+                outs.append(self.model.predict_step(batch, i))
+        return outs
+
     # ---- fit -----------------------------------------------------------------------------------------------
     def fit(self, model, datamodule, ckpt_path: Optional[str] = None):
         self.model, self.datamodule = model, datamodule

@@ -136,3 +136,33 @@ def test_exp_manager_small_options(tmp_path):
     ck = sorted(glob.glob(str(tmp_path / "run" / "checkpoints" / "*.ckpt")))[-1]
     m, _, _ = ckpt_io.load_checkpoint(os.path.dirname(ck), os.path.basename(ck), optimizer=False)
     assert all(v.dtype == torch.bfloat16 for v in m.values() if torch.is_tensor(v) and v.is_floating_point())
+
+
+def test_trainer_test_and_predict_loops(tmp_path):
+    """Trainer.test / Trainer.predict (the reference's evaluation and prediction loops) on a trained checkpoint."""
+    from neuronx_distributed_training_b200.trainer import Trainer
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    from neuronx_distributed_training_b200.data import SyntheticDataModule
+    cfg = _cfg(str(tmp_path / "run"), max_steps=2)
+    tr, mod = _fit(cfg)
+    ck = sorted(glob.glob(str(tmp_path / "run" / "checkpoints" / "*.ckpt")))[-1]
+    # a fresh trainer + module evaluates the saved weights
+    cfg2 = process_config(_cfg(str(tmp_path / "eval"), max_steps=2), 1)
+    cfg2.trainer["limit_test_batches"] = 2
+    tr2 = Trainer(**cfg2.trainer.to_dict())
+    mod2 = HFLlamaModule(cfg2, tr2)
+    dm2 = SyntheticDataModule(cfg2, tr2)
+    if not hasattr(dm2, "test_dataloader") or dm2.test_dataloader() is None:
+        dm2.test_dataloader = dm2.val_dataloader
+    loss = tr2.test(mod2, dm2, ckpt_path=ck)
+    assert loss is not None and loss == loss and "test_loss" in tr2.callback_metrics
+    for (n, a), (_, b) in zip(mod.local_named_parameters(), mod2.local_named_parameters()):
+        assert torch.equal(a.detach(), b.detach()), n                   # weights came from the checkpoint
+    batch = next(iter(dm2.val_dataloader()))
+    outs = tr2.predict(dataloader=[batch])
+    assert len(outs) == 1 and outs[0]["predictions"].shape == batch["input_ids"].shape
+    assert outs[0]["logprobs"].shape == batch["input_ids"].shape and (outs[0]["logprobs"] <= 0).all()
+    # greedy predictions agree with the argmax of the full logits
+    with torch.no_grad():
+        _, logits = mod2.model(input_ids=batch["input_ids"], labels=None)
+    assert torch.equal(outs[0]["predictions"], logits.float().argmax(-1))
