@@ -120,3 +120,32 @@ def test_validation_padding_samples(tmp_path):
     s0 = ResumableBatchSampler(10, 0, 4, dp_rank=0, dp_size=2, drop_last=False)
     s0.pad_to_global_batch = True
     assert list(s0)[-1] == [8, 9]
+
+
+def test_preprocess_tool_roundtrip(tmp_path, monkeypatch):
+    """tools/preprocess_data.py: jsonl -> Megatron .bin/.idx (readable by GPTDataset) and -> HF arrow blocks."""
+    import importlib.util
+    import json as _json
+    spec = importlib.util.spec_from_file_location("preprocess_data", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "preprocess_data.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+
+    class Tok:
+        eos_token_id, vocab_size = 2, 200
+
+        def encode(self, text, add_special_tokens=False):
+            return [3 + (ord(c) % 100) for c in text]
+    monkeypatch.setattr(tool, "load_tokenizer", lambda args: Tok())
+    src = tmp_path / "corpus.jsonl"
+    texts = ["hello world " * (i + 1) for i in range(12)]
+    src.write_text("\n".join(_json.dumps({"text": t}) for t in texts))
+    info = tool.main(["--input", str(src), "--format", "megatron", "--output-prefix", str(tmp_path / "out" / "corpus"), "--append-eod"])
+    assert info["documents"] == 12 and info["tokens"] == sum(len(t) + 1 for t in texts)
+    indexed = MMapIndexedDataset(str(tmp_path / "out" / "corpus"))
+    assert len(indexed) == 12 and list(indexed[0]) == Tok().encode(texts[0]) + [2]
+    ds = GPTDataset("train", str(tmp_path / "out" / "corpus"), np.arange(12, dtype=np.int32), indexed, num_samples=8, seq_length=16, seed=1)
+    assert ds[0]["tokens"].shape[0] == 16
+    datasets = pytest.importorskip("datasets")
+    info = tool.main(["--input", str(src), "--format", "hf", "--output-dir", str(tmp_path / "arrow"), "--seq-length", "32"])
+    arrow = datasets.load_from_disk(str(tmp_path / "arrow"))
+    assert len(arrow) == info["sequences"] > 0 and len(arrow[0]["input_ids"]) == 32 and arrow[0]["labels"] == arrow[0]["input_ids"]
