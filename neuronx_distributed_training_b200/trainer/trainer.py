@@ -49,7 +49,7 @@ class Trainer:
                  log_every_n_steps: int = 10, val_check_interval: Any = None, check_val_every_n_epoch: Any = None,
                  num_sanity_val_steps: int = 0, limit_val_batches: Any = 1.0, limit_test_batches: Any = 1.0,
                  gradient_clip_val: Optional[float] = None, max_time: Any = None, accumulate_grad_batches: int = 1,
-                 enable_progress_bar: bool = False, profiler: Any = None, **ignored):
+                 enable_progress_bar: bool = False, profiler: Any = None, callbacks: Optional[list] = None, **ignored):
         if accumulate_grad_batches not in (None, 1):
             raise ValueError("accumulate_grad_batches>1 is not supported; gradient accumulation is expressed "
                              "through global_batch_size / micro_batch_size")
@@ -64,6 +64,10 @@ class Trainer:
         self.num_sanity_val_steps = int(num_sanity_val_steps or 0)
         self.gradient_clip_val = gradient_clip_val
         self.max_time = _parse_max_time(max_time)
+        # user callbacks: objects with any of the PTL-style hooks on_fit_start / on_train_start / on_train_batch_end /
+        # on_validation_end / on_save_checkpoint / on_train_end (each receives the trainer first)
+        self.callbacks = list(callbacks or [])
+        self.enable_progress_bar = bool(enable_progress_bar)
         self.ignored_args = ignored           # Neuron-only knobs (lnc, sequential_move_factor, ...)
         self.profiler_cfg = profiler          # {start_step, end_step, dir} -> torch.profiler trace of those steps
         self.profiler: Optional[StepProfiler] = None
@@ -81,6 +85,12 @@ class Trainer:
         self.callback_metrics: Dict[str, float] = {}
         self.step_timer = DeviceStepTimer()
         self.last_step_ms = []
+
+    def _call(self, hook: str, *args) -> None:
+        for cb in self.callbacks:
+            fn = getattr(cb, hook, None)
+            if fn is not None:
+                fn(self, *args)
 
     # ---- signals ---------------------------------------------------------------------------------------
     def _install_signal_handlers(self):
@@ -274,7 +284,9 @@ class Trainer:
         if ckpt_path:
             self.restore(ckpt_path, weight_init_only=weight_init_only and
                          not os.path.dirname(ckpt_path.rstrip("/")).startswith(str(self.log_dir or "\0")))
+        self._call("on_fit_start", model)
         model.on_train_start(self)
+        self._call("on_train_start", model)
         if self.profiler_cfg:
             pc = dict(self.profiler_cfg) if not hasattr(self.profiler_cfg, "to_dict") else self.profiler_cfg.to_dict()
             self.profiler = StepProfiler(pc.get("start_step", 3), pc.get("end_step", 5),
@@ -330,11 +342,14 @@ class Trainer:
                     datamodule.consumed_samples = datamodule.compute_consumed_samples(self.steps_since_resume)
                     if self.global_step % self.log_every_n_steps == 0:
                         self._log(loss)
+                    self._call("on_train_batch_end", model, loss, batch, batch_idx)
                     vci = self.val_check_interval
                     if vci and isinstance(vci, int) and self.global_step % vci == 0:
                         self.validate()
+                        self._call("on_validation_end", model)
                     if cb is not None and cb.should_save(self.global_step):
                         cb.save(self, self._ckpt_metrics())
+                        self._call("on_save_checkpoint", model)
                     if self.watchdog is not None:
                         self.watchdog.pet()          # validation / checkpointing are not part of the step budget
                     if self.max_time is not None and time.time() - t_start > self.max_time:
@@ -356,6 +371,7 @@ class Trainer:
             if self.watchdog is not None:
                 self.watchdog.stop()
             model.on_train_end(self)
+            self._call("on_train_end", model)
             ckpt_io.finalize_checkpoint()
             if self.exp_manager:
                 self.exp_manager.close()
@@ -376,6 +392,10 @@ class Trainer:
         self.callback_metrics.update({"reduced_train_loss": m["reduced_train_loss"]})
         if self.exp_manager:
             self.exp_manager.log_metrics(m, self.global_step)
+        if self.enable_progress_bar and ps.get_rank() == 0 and self.max_steps > 0:
+            done = int(30 * self.global_step / self.max_steps)
+            print(f"\r[{'#' * done}{'.' * (30 - done)}] {self.global_step}/{self.max_steps} loss {m['reduced_train_loss']:.4f}",
+                  end="" if self.global_step < self.max_steps else "\n", flush=True)
         if ps.get_rank() == 0:
             log.info("step %d | %s", self.global_step,
                      " | ".join(f"{k}={v:.6g}" for k, v in m.items() if k != "global_step"))

@@ -166,3 +166,36 @@ def test_trainer_test_and_predict_loops(tmp_path):
     with torch.no_grad():
         _, logits = mod2.model(input_ids=batch["input_ids"], labels=None)
     assert torch.equal(outs[0]["predictions"], logits.float().argmax(-1))
+
+
+def test_user_callbacks_and_progress_bar(tmp_path, capsys):
+    from neuronx_distributed_training_b200.trainer import Trainer
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    from neuronx_distributed_training_b200.data import SyntheticDataModule
+    from neuronx_distributed_training_b200.utils.exp_manager import exp_manager
+    events = []
+
+    class Recorder:
+        def on_fit_start(self, trainer, module):
+            events.append("fit_start")
+
+        def on_train_batch_end(self, trainer, module, loss, batch, batch_idx):
+            events.append(("batch", trainer.global_step, float(loss) == float(loss)))
+
+        def on_validation_end(self, trainer, module):
+            events.append("val")
+
+        def on_save_checkpoint(self, trainer, module):
+            events.append("save")
+
+        def on_train_end(self, trainer, module):
+            events.append("end")
+
+    cfg = process_config(_cfg(str(tmp_path / "run"), max_steps=4), 1)
+    tr = Trainer(callbacks=[Recorder()], enable_progress_bar=True, **cfg.trainer.to_dict())
+    em = exp_manager(tr, cfg.exp_manager)
+    tr.fit(HFLlamaModule(cfg, tr), SyntheticDataModule(cfg, tr), ckpt_path=em.resume_from_checkpoint)
+    assert events[0] == "fit_start" and events[-1] == "end"
+    assert [e[1] for e in events if isinstance(e, tuple)] == [1, 2, 3, 4]
+    assert events.count("val") == 2 and events.count("save") == 2          # val_check_interval = every_n_train_steps = 2
+    assert "4/4" in capsys.readouterr().out
