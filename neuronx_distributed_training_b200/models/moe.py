@@ -199,7 +199,9 @@ class MoE(nn.Module):
         self.normalize = normalize_top_k_affinities
         self.sp = sequence_parallel_enabled and ps.get_tensor_model_parallel_size() > 1
         self.return_router_logits = return_router_logits
-        self.token_shuffle_group_size = token_shuffle_group_size
+        self.token_shuffle_group_size = int(token_shuffle_group_size or 1)
+        # created here (model construction happens on every rank at the same point): groups of consecutive DP ranks
+        self._shuffle_group, self._shuffle_ranks = ps.get_token_shuffle_group(self.token_shuffle_group_size)
 
     # ---- expert-parallel exchange -------------------------------------------------------------------
     @staticmethod
@@ -237,6 +239,15 @@ class MoE(nn.Module):
         shape = hidden.shape
         x = hidden.reshape(-1, shape[-1])
         T = x.shape[0]
+        # token shuffling (reference X19 `token_shuffle_group_size`): tokens are randomly exchanged inside a group of DP
+        # ranks before routing, so that a rank whose sequences favour a few experts does not overflow their capacity
+        unshuffle = None
+        G = len(self._shuffle_ranks)
+        if self._shuffle_group is not None and G > 1 and T % G == 0:
+            perm = torch.randperm(T, device=x.device)
+            counts = [T // G] * G
+            x = _A2A.apply(x.index_select(0, perm), counts, counts, self._shuffle_group)
+            unshuffle = (perm, counts)
         E, k = self.router.num_experts, self.router.top_k
         logits, aff, idx = self.router(x)
         w = aff.gather(-1, idx)                                   # [T,k]
@@ -283,7 +294,12 @@ class MoE(nn.Module):
             ys = self.expert_mlps.forward_sorted(xs, counts)
         out = torch.zeros_like(x, dtype=torch.float32)
         out.index_add_(0, st, ys.float() * sw.unsqueeze(-1).float())
-        out = out.to(x.dtype).view(shape)
+        out = out.to(x.dtype)
+        if unshuffle is not None:
+            perm, counts = unshuffle
+            back = _A2A.apply(out, counts, counts, self._shuffle_group)       # tokens return to their home rank ...
+            out = torch.empty_like(back).index_copy(0, perm, back)            # ... and to their original position
+        out = out.view(shape)
         # experts are TP-sharded on the FFN dim => partial sums over TP
         if self.sp:
             out = mp.reduce_scatter_to_sequence_parallel_region(out, tp_group)

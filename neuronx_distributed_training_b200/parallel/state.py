@@ -150,7 +150,32 @@ def initialize_model_parallel(tensor_model_parallel_size: int = 1, pipeline_mode
         _GROUPS[kind], _GROUP_RANKS[kind] = mine
 
 
+_SHUFFLE_GROUPS: Dict[int, Tuple[object, List[int]]] = {}
+
+
+def get_token_shuffle_group(size: int):
+    """Process group of ``size`` consecutive data-parallel ranks (MoE ``token_shuffle_group_size``), created on first
+    use.  Every rank of the world must call this at the same point (groups are created collectively)."""
+    size = int(size)
+    if size <= 1 or not dist.is_initialized() or _G.world_size == 1:
+        return None, []
+    if size in _SHUFFLE_GROUPS:
+        return _SHUFFLE_GROUPS[size]
+    if _G.dp % size != 0:
+        raise ValueError(f"token_shuffle_group_size {size} must divide the data-parallel size {_G.dp}")
+    mine = (None, [])
+    for ranks in enumerate_groups(_G.world_size, _G.tp, _G.pp, _G.cp, _G.ep)["dp"]:
+        for i in range(0, len(ranks), size):
+            sub = ranks[i:i + size]
+            g = dist.new_group(ranks=sub)
+            if _G.rank in sub:
+                mine = (g, sub)
+    _SHUFFLE_GROUPS[size] = mine
+    return mine
+
+
 def destroy_model_parallel() -> None:
+    _SHUFFLE_GROUPS.clear()
     global _G
     _GROUPS.clear()
     _GROUP_RANKS.clear()

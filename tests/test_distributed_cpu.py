@@ -86,3 +86,7 @@ def test_resume_with_a_different_data_parallel_size(tmp_path, dp_save, dp_resume
 @pytest.mark.parametrize("dp", [2, 4])
 def test_overlapped_gradient_reduction_matches(dp):
     run_dist("zero1_overlap.py", dp)
+
+
+def test_moe_token_shuffling_is_transparent():
+    run_dist("moe_shuffle.py", 2)
