@@ -178,8 +178,17 @@ class BaseModelModule:
             yield {key: (v[k * mbs:(k + 1) * mbs] if torch.is_tensor(v) else v) for key, v in batch.items()}
 
     def model_fwd_calc_loss(self, batch: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, Any]:
+        extra = {"return_logits": True} if self.save_logits and self.dims.pp == 1 else {}
         out = self.model(input_ids=batch["input_ids"], labels=batch["labels"],
-                         attention_mask=batch.get("attention_mask"), loss_mask=batch.get("loss_mask"))
+                         attention_mask=batch.get("attention_mask"), loss_mask=batch.get("loss_mask"), **extra)
+        if self.save_logits and out[1] is not None:
+            # model.save_logits (reference base.py:68,381): the (vocab-parallel) logits of the latest micro-batch stay
+            # available for numerics comparisons; dumped next to the logs when NXDT_DUMP_LOGITS_DIR is set
+            self.last_logits = out[1].detach()
+            dump = os.environ.get("NXDT_DUMP_LOGITS_DIR")
+            if dump:
+                os.makedirs(dump, exist_ok=True)
+                torch.save(self.last_logits.cpu(), os.path.join(dump, f"logits_rank{ps.get_rank()}.pt"))
         return out[0], out[1]
 
     def forward_backward_step(self, batch: Dict[str, torch.Tensor], is_training: bool = True) -> torch.Tensor:

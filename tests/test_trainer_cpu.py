@@ -199,3 +199,14 @@ def test_user_callbacks_and_progress_bar(tmp_path, capsys):
     assert [e[1] for e in events if isinstance(e, tuple)] == [1, 2, 3, 4]
     assert events.count("val") == 2 and events.count("save") == 2          # val_check_interval = every_n_train_steps = 2
     assert "4/4" in capsys.readouterr().out
+
+
+def test_save_logits_keeps_the_vocab_parallel_logits(tmp_path, monkeypatch):
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    monkeypatch.setenv("NXDT_DUMP_LOGITS_DIR", str(tmp_path / "dump"))
+    cfg = process_config(_cfg(str(tmp_path / "x"), save_logits=True), 1)
+    mod = HFLlamaModule(cfg, None); mod.setup(); mod.configure_optimizers(10)
+    ids = torch.randint(0, 128, (2, 32))
+    loss = mod.training_step({"input_ids": ids, "labels": ids.clone()})
+    assert mod.last_logits.shape == (1, 32, 128) and float(loss) == float(loss)      # latest micro-batch, [B, S, V]
+    assert torch.equal(torch.load(tmp_path / "dump" / "logits_rank0.pt"), mod.last_logits.cpu())
