@@ -60,6 +60,7 @@ class LlamaConfig:
     kv_shared_group_size: int = 1        # = distributed_strategy.kv_replicator
     use_flash_attention: bool = True
     use_ring_attention: bool = False
+    use_ulysses_attention: bool = False     # all-to-all context parallelism instead of the ring (parallel/ulysses_attention.py)
     fused_linear_ce: bool = True
     ce_chunk_tokens: int = 2048
     torch_dtype: str = "bfloat16"
@@ -239,14 +240,16 @@ class LlamaAttention(nn.Module):
         self.o_proj = RowParallelLinear(self.num_heads * self.head_dim, config.hidden_size, bias=config.attention_bias,
                                         input_is_parallel=True, init_method=init, **kw)
         self.core_attn = CoreAttention(config)
-        self.use_ring = config.use_ring_attention and ps.get_context_model_parallel_size() > 1
-        if ps.get_context_model_parallel_size() > 1 and not config.use_ring_attention:
+        cp = ps.get_context_model_parallel_size()
+        self.use_ulysses = bool(config.use_ulysses_attention) and cp > 1
+        self.use_ring = config.use_ring_attention and cp > 1 and not self.use_ulysses
+        if cp > 1 and not (config.use_ring_attention or config.use_ulysses_attention):
             raise ValueError("context parallelism requires model.fusions.ring_attention=True "
-                             "(reference modeling_llama.py:280-288)")
+                             "(reference modeling_llama.py:280-288) or model.fusions.ulysses_attention=True")
 
     def forward(self, hidden: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
         # hidden: [S_local, B, H]
-        if self.qkv_mode == "gqa" and self.config.fuse_qkv and not self.use_ring and \
+        if self.qkv_mode == "gqa" and self.config.fuse_qkv and not self.use_ring and not self.use_ulysses and \
                 type(self.qkv_proj).__name__ == "GQAQKVColumnParallelLinear":
             # one GEMM, then one fused kernel: split + RoPE + [S,B]->[B,S] layout, no intermediate copies
             packed = self.qkv_proj.forward_packed(hidden)
@@ -266,7 +269,10 @@ class LlamaAttention(nn.Module):
         k = k.reshape(S, B, self.local_kv_heads, self.head_dim).transpose(0, 1)
         v = v.reshape(S, B, self.local_kv_heads, self.head_dim).transpose(0, 1)
         q, k = ops.rope(q, k, cos, sin)
-        if self.use_ring:
+        if self.use_ulysses:
+            from ..parallel.ulysses_attention import ulysses_attention
+            o = ulysses_attention(q.contiguous(), k.contiguous(), v.contiguous(), self.core_attn)
+        elif self.use_ring:
             from ..parallel.ring_attention import ring_attention
             o = ring_attention(q, k, v, scale=self.core_attn.scale)
         else:

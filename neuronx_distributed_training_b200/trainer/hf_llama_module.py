@@ -105,6 +105,7 @@ class HFLlamaModule(BaseHfModel):
         hf.kv_shared_group_size = int(ds.get("kv_replicator", 1) or 1)
         hf.use_flash_attention = bool(fus.get("flash_attention", True))
         hf.use_ring_attention = bool(fus.get("ring_attention", False))
+        hf.use_ulysses_attention = bool(fus.get("ulysses_attention", False))
         hf.fused_linear_ce = bool(fus.get("linear_cross_entropy", True)) and not self.save_logits
         hf.ce_chunk_tokens = int(m.get("ce_chunk_tokens", 2048))
         hf.use_cpu_initialization = bool(m.get("use_cpu_initialization", False)) and not torch.cuda.is_available() \

@@ -47,6 +47,11 @@ def test_ring_attention_context_parallel(cp):
     run_dist("ring_attention.py", cp, {"CP": str(cp)})
 
 
+@pytest.mark.parametrize("cp", [2, 4])
+def test_ulysses_attention_context_parallel(cp):
+    run_dist("ulysses_attention.py", cp, {"CP": str(cp)})
+
+
 def test_moe_expert_parallel_matches_single_process():
     run_dist("moe_ep.py", 2, {"EP": "2"})
 
