@@ -39,7 +39,7 @@ void zero1_adam_push(std::vector<int64_t> grads, std::vector<int64_t> params, st
                      const at::Tensor& clip, bool sr, int64_t seed, at::Tensor done_ctr);
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
-             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr);
+             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr, std::vector<int64_t> aflag_peer);
 void tp_barrier(int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t rank, int64_t tp, int64_t epoch_ptr);
 void grouped_gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, const at::Tensor& block_expert, bool b_kmajor);
 void grouped_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor& out, const at::Tensor& offsets, bool accumulate);

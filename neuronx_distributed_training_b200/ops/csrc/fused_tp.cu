@@ -93,7 +93,7 @@ struct AgGate {
   __device__ __forceinline__ void before_first_store() const {}
   __device__ __forceinline__ const CUtensorMap* out_map(int) const { return nullptr; }
   __device__ __forceinline__ int out_row(int m_blk) const { return m_blk * BLOCK_M; }
-  __device__ __forceinline__ void tile_done(int) const {}
+  __device__ __forceinline__ void tile_done(int, int) const {}
 };
 
 __device__ __forceinline__ void send_handshake(uint32_t* const* hs_peer, int rank, int tp, uint32_t epoch) {
@@ -193,7 +193,7 @@ __device__ void comm_cta_pull(const CommArgs& a, uint8_t* smem_raw) {
     const int src_rank = blk / blocks_per_rank;
     if (src_rank == a.rank) continue;
     if (!((waited_rank_mask >> src_rank) & 1)) {
-      spin_until_ge_sys(a.hs_local + src_rank, a.epoch, 100);
+      spin_until_ge_sys(a.hs_local + src_rank, a.epoch, 100, 0x100u | (uint32_t)a.rank);
       waited_rank_mask |= 1 << src_rank;
     }
     if (!stamped) { dbg_stamp(1); stamped = true; }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ag_only_kernel(const CommArgs 
   const int bpr = comm.rows_per_rank / 128;
   for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < bpr * comm.tp; blk += gridDim.x * blockDim.x) {
     if (blk / bpr == comm.rank) continue;
-    spin_until_ge_sys(comm.flags + blk, comm.epoch, 200);
+    spin_until_ge_sys(comm.flags + blk, comm.epoch, 200, 0x200u | (uint32_t)comm.rank);
   }
 }
 
@@ -280,6 +280,11 @@ struct RsArgs {
   const uint32_t* epoch_ptr;
   int rank, tp, rows_per_rank, N, num_n_blocks;
   int self_reset;                      // 1: the last reducer of a row-block zeroes its arrival counter (no host-side clear)
+  // Arrival FLAGS instead of counters (aflag_peer[0] != nullptr): one epoch-valued word per (row-block, source rank,
+  // n-tile) in the owner's workspace.  Nothing is ever cleared or counted, a word only grows, so the protocol needs no
+  // memset in front of the kernel and a reducer can start on a 256-column chunk as soon as ITS tp tiles have landed.
+  uint32_t* aflag_peer[MAX_TP];
+  const uint32_t* aflag_local;
 };
 
 struct RsMaps {
@@ -294,7 +299,7 @@ struct RsGate {
   __device__ __forceinline__ void before_first_store() const {
     if (threadIdx.x == 64) {
       for (int p = 0; p < a.tp; ++p)
-        spin_until_ge_sys(a.hs_local + p, a.epoch, 100);
+        spin_until_ge_sys(a.hs_local + p, a.epoch, 100, 0x300u | (uint32_t)a.rank);
       dbg_stamp(1);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -307,10 +312,13 @@ struct RsGate {
     const int d = m_blk / bpr;
     return a.rank * a.rows_per_rank + (m_blk - d * bpr) * 128;
   }
-  __device__ __forceinline__ void tile_done(int m_blk) const {
+  __device__ __forceinline__ void tile_done(int m_blk, int n_blk) const {
     const int bpr = a.rows_per_rank / 128;
     const int d = m_blk / bpr;
-    red_add_release_sys(a.counter_peer[d] + (m_blk - d * bpr), 1u);
+    if (a.aflag_peer[0] != nullptr)
+      st_release_sys(a.aflag_peer[d] + ((size_t)(m_blk - d * bpr) * a.tp + a.rank) * a.num_n_blocks + n_blk, a.epoch);
+    else
+      red_add_release_sys(a.counter_peer[d] + (m_blk - d * bpr), 1u);
   }
 };
 
@@ -333,8 +341,14 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t target = (uint32_t)(rs.tp * rs.num_n_blocks);
   for (int item = blockIdx.x; item < bpr * n_chunks; item += gridDim.x) {
     const int rb = item / n_chunks, nc = item - rb * n_chunks;
-    if (threadIdx.x == 0) {
-      spin_until_ge_sys(rs.counter_local + rb, target, 200);
+    if (rs.aflag_local != nullptr) {
+      static_assert(BLOCK_N == 256, "one reduce chunk == one n-tile");
+      // the tp partial tiles (rb, nc): one lane per source rank
+      if ((int)threadIdx.x < rs.tp)
+        spin_until_ge_sys(rs.aflag_local + ((size_t)rb * rs.tp + threadIdx.x) * rs.num_n_blocks + nc, rs.epoch, 200,
+                          0x600u | (uint32_t)rs.rank);
+    } else if (threadIdx.x == 0) {
+      spin_until_ge_sys(rs.counter_local + rb, target, 200, 0x400u | (uint32_t)rs.rank);
     }
     __syncthreads();
     // 128 rows x 32 sixteen-byte columns per item; every thread keeps 4 independent outputs in flight and issues all
@@ -412,7 +426,7 @@ __global__ void tp_barrier_kernel(const RsArgs a) {
   const int t = threadIdx.x;
   if (t < a.tp) {
     st_release_sys(a.hs_peer[t] + a.rank, epoch);
-    spin_until_ge_sys(a.hs_local + t, epoch, 100);
+    spin_until_ge_sys(a.hs_local + t, epoch, 100, 0x500u | (uint32_t)a.rank);
   }
 }
 
@@ -539,7 +553,7 @@ void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_p
 // out[rows_per_rank, N] = reduce_scatter_rows( a[M_total, K] * op(b) )
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
-             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr) {
+             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr, std::vector<int64_t> aflag_peer) {
   using namespace fused;
   TORCH_CHECK(a.is_cuda() && a.is_contiguous() && b.is_contiguous() && out.is_contiguous());
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16);
@@ -587,7 +601,16 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   }();
   rs.self_reset = self_reset ? 1 : 0;
   TORCH_CHECK(!self_reset || rows_per_rank / 128 <= 512, "self-resetting counters support up to 512 row-blocks per rank");
-  if (self_reset) {
+  const bool arrive_flags = !aflag_peer.empty();
+  for (int d = 0; d < MAX_TP; ++d) rs.aflag_peer[d] = nullptr;
+  rs.aflag_local = nullptr;
+  if (arrive_flags) {
+    TORCH_CHECK(epoch_ptr != 0 || epoch > 0, "arrival flags need a protocol epoch");
+    fill_ptrs(aflag_peer, tp, (void**)rs.aflag_peer);
+    rs.aflag_local = rs.aflag_peer[rank];
+    rs.self_reset = 0;
+  }
+  if (self_reset || arrive_flags) {
     if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
   } else if (epoch_ptr != 0 && clear_with_kernel) {
     bump_epoch_clear_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr), rs.counter_local,

@@ -56,7 +56,7 @@ struct NoGate {
   __device__ __forceinline__ void before_first_store() const {}
   __device__ __forceinline__ const CUtensorMap* out_map(int /*m_blk*/) const { return nullptr; }
   __device__ __forceinline__ int out_row(int m_blk) const { return m_blk * BLOCK_M; }
-  __device__ __forceinline__ void tile_done(int /*m_blk*/) const {}
+  __device__ __forceinline__ void tile_done(int /*m_blk*/, int /*n_blk*/) const {}
 };
 
 // Grouped (per-expert) GEMMs specialise this trait.  A grouped gate provides
@@ -233,7 +233,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
     constexpr int NCHUNK = BLOCK_N / COLS_PER_CHUNK;
     uint32_t acc = 0, acc_phase = 0, cbuf = 0;
     bool first_store = true;
-    int prev_tile_m = -1;
+    int prev_tile_m = -1, prev_tile_n = -1;
     for (int t = cta_first_tile; t < p.num_tiles; t += cta_tile_stride) {
       int m_blk, n_blk;
       tile_coords(p, t, m_blk, n_blk);
@@ -333,9 +333,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
             tma_store_wait<NCHUNK>();
             fence_proxy_async_all();
             __threadfence_system();
-            gate.tile_done(prev_tile_m);    // red.release.sys on the owner's arrival counter
+            gate.tile_done(prev_tile_m, prev_tile_n);    // publish the tile to the owner rank
           }
           prev_tile_m = m_blk;
+          prev_tile_n = n_blk;
         }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -346,7 +347,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
         if (prev_tile_m >= 0) {
           fence_proxy_async_all();
           __threadfence_system();
-          gate.tile_done(prev_tile_m);
+          gate.tile_done(prev_tile_m, prev_tile_n);
         }
       }
     }

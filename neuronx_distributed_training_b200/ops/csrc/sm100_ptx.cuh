@@ -313,13 +313,15 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 
 // Bounded spin on a cross-GPU flag: a lost signal becomes a trap (CUDA error on the host) instead of a silent hang.
 // `ge` semantics: wait until (int)(*p - target) >= 0 (flags are monotonically increasing epochs / counters).
-__device__ __forceinline__ void spin_until_ge_sys(const uint32_t* p, uint32_t target, int sleep_ns = 100) {
+// `tag` identifies the wait site in the message: (site << 8) | rank.
+__device__ __forceinline__ void spin_until_ge_sys(const uint32_t* p, uint32_t target, int sleep_ns = 100, uint32_t tag = 0) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(p) - target) < 0) {
     __nanosleep(sleep_ns);
     if (clock64() - t0 > 40000000000ll) {   // ~20 s at 2 GHz
-      printf("[nxdt] cross-GPU wait timed out: flag %p = %u, waiting for >= %u (block %d)\n", (const void*)p,
-             ld_acquire_sys(p), target, (int)blockIdx.x);
+      printf("[nxdt] cross-GPU wait timed out: flag %p = %u, waiting for >= %u (block %d, site 0x%x, next words %u %u %u)\n",
+             (const void*)p, ld_acquire_sys(p), target, (int)blockIdx.x, tag, ld_acquire_sys(p + 1), ld_acquire_sys(p + 2),
+             ld_acquire_sys(p + 3));
       __trap();
     }
   }

@@ -8,6 +8,8 @@ run() { name=$1; t=$2; shift 2; timeout "$t" "$@" > gpurun_out/r2n2_$name.log 2>
 run graph_ag_rs 60 $TR --master-port 29701 tests/gpu_checks/check_fused_graph.py --pattern ag,rs --replays 40
 NXDT_RS_CLEAR_KERNEL=1 run graph_ag_rs_clearkernel 60 $TR --master-port 29702 tests/gpu_checks/check_fused_graph.py --pattern ag,rs --replays 40
 NXDT_RS_SELF_RESET=1 run graph_ag_rs_selfreset 60 $TR --master-port 29705 tests/gpu_checks/check_fused_graph.py --pattern ag,rs --replays 40
+NXDT_RS_ARRIVE_FLAGS=1 run graph_ag_rs_flags 60 $TR --master-port 29707 tests/gpu_checks/check_fused_graph.py --pattern ag,rs --replays 40
+NXDT_RS_ARRIVE_FLAGS=1 run eager_flags_check 120 $TR --master-port 29708 tests/gpu_checks/check_fused_tp.py
 NXDT_RS_SELF_RESET=1 run eager_selfreset_check 120 $TR --master-port 29706 tests/gpu_checks/check_fused_tp.py
 run graph_rs_only 60 $TR --master-port 29703 tests/gpu_checks/check_fused_graph.py --pattern rs,rs --replays 40
 run graph_ag_only 60 $TR --master-port 29704 tests/gpu_checks/check_fused_graph.py --pattern ag,ag --replays 40
