@@ -1,7 +1,7 @@
 """Generation metrics: ROUGE-1/2/L (F-measure) and exact match, dependency-free."""
 import re
 from collections import Counter
-from typing import Dict, List
+from typing import List
 
 
 def _tok(s: str) -> List[str]:

@@ -13,7 +13,7 @@ import glob
 import json
 import os
 import re
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 

@@ -18,9 +18,7 @@ avoids the fork-doubles-host-memory problem the reference documents (known_issue
 """
 from __future__ import annotations
 
-import io
 import os
-import pickle
 import shutil
 import struct
 import threading
@@ -29,7 +27,6 @@ from concurrent.futures import ThreadPoolExecutor, Future
 from typing import Any, Dict, List, Optional, Tuple
 
 import torch
-import torch.distributed as dist
 
 from ..parallel import state as ps
 from . import storage

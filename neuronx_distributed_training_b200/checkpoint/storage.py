@@ -12,7 +12,7 @@ from __future__ import annotations
 import hashlib
 import os
 import shutil
-from typing import Callable, Dict, Iterable, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 
 def split_url(url: str) -> Tuple[str, str, str]:

@@ -18,7 +18,6 @@ import torch
 from torch.utils.data import DataLoader, Dataset, DistributedSampler
 
 from ..config import Config
-from ..parallel import state as ps
 from .base import BaseDataModule, default_collate
 
 log = logging.getLogger("nxdt")

@@ -7,13 +7,12 @@ Batches stay on (pinned) host memory; the trainer issues the H2D copies on a sid
 """
 from __future__ import annotations
 
-import os
 from typing import Any, Dict, Iterator, List, Optional
 
 import torch
-from torch.utils.data import DataLoader, Dataset, DistributedSampler, Sampler
+from torch.utils.data import DataLoader, Dataset, Sampler
 
-from ..config import Config, ParallelDims, batch_arithmetic
+from ..config import Config
 from ..parallel import state as ps
 from ..utils.exp_manager import consumed_samples_from_path
 

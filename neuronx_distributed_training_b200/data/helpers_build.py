@@ -1,12 +1,10 @@
 """Build / load the C++ index-builder extension (``data/csrc/helpers.cpp``) in-tree with g++ + pybind11."""
 from __future__ import annotations
 
-import glob
 import importlib.machinery
 import importlib.util
 import os
 import subprocess
-import sys
 import sysconfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -9,14 +9,12 @@ src/.../models/hf_models/modeling_mixtral.py:123-154,342-374,451-454,537-547,872
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import torch
 import torch.nn as nn
 
-from ..parallel import state as ps
-from .llama import (LlamaConfig, LlamaAttention, LlamaMLP, LlamaRMSNorm, LlamaModel, LlamaForCausalLM,
-                    LlamaRotaryEmbedding)
+from .llama import LlamaConfig, LlamaAttention, LlamaMLP, LlamaRMSNorm, LlamaModel, LlamaForCausalLM
 from .moe import RouterTopK, RouterSinkhorn, ExpertMLPs, MoE, load_balancing_loss_func
 
 

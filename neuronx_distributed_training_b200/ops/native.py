@@ -9,8 +9,6 @@ import glob
 import importlib.machinery
 import importlib.util
 import os
-import subprocess
-import sys
 from typing import List, Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -14,7 +14,6 @@ Design (B200-first, not a translation):
 """
 from __future__ import annotations
 
-import math
 from typing import Callable, Optional, Tuple
 
 import torch

@@ -7,7 +7,7 @@ hf_models/llama_model.py:94-103, lightning_modules/model/base.py:374-381, utils/
 from __future__ import annotations
 
 import logging
-from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
 
 import torch
 import torch.nn as nn

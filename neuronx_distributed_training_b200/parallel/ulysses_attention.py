@@ -13,7 +13,7 @@ Selected by ``model.fusions.ulysses_attention: true`` (with ``ring_attention`` t
 from __future__ import annotations
 
 import math
-from typing import Callable, Optional
+from typing import Callable
 
 import torch
 import torch.distributed as dist

@@ -11,11 +11,10 @@ transfer of microbatch *k* overlaps the compute of microbatch *k+1*.
 from __future__ import annotations
 
 import contextlib
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
-import torch.nn as nn
 
 from ..parallel import state as ps
 

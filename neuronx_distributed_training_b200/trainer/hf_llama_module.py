@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import logging
 import os
-from typing import Any, Dict, List, Optional
+from typing import Optional
 
 import torch
 import torch.nn as nn
@@ -16,9 +16,7 @@ import torch.nn as nn
 from ..config import Config
 from ..models import llama as llama_mod
 from ..models.llama import LlamaConfig, LlamaForCausalLM, LlamaDecoderLayer
-from ..parallel import state as ps
 from ..parallel.model import initialize_parallel_model
-from ..utils.activation_checkpoint import apply_activation_checkpointing
 from .module import BaseModelModule, get_param_groups_by_weight_decay
 
 log = logging.getLogger("nxdt")

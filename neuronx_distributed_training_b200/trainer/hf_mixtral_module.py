@@ -1,7 +1,6 @@
 """HF-Mixtral task module (reference hf_models/mixtral_model.py:24-96)."""
 from __future__ import annotations
 
-import torch
 
 from ..config import Config
 from ..models import mixtral as mixtral_mod

@@ -8,7 +8,7 @@ rejected options (distributed fused adam, amp O2, grad-accumulation fusion, bias
 from __future__ import annotations
 
 import logging
-from typing import Any, Dict
+from typing import Dict
 
 import torch
 

@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import contextlib
 import logging
-import math
 import os
 from typing import Any, Dict, List, Optional, Tuple
 

@@ -19,10 +19,8 @@ import time
 from typing import Any, Dict, Optional
 
 import torch
-import torch.distributed as dist
 
 from ..checkpoint import io as ckpt_io
-from ..config import Config
 from ..parallel import state as ps
 from ..utils.exp_manager import ExpManager, consumed_samples_from_path, step_from_path
 from ..utils.throughput import DeviceStepTimer

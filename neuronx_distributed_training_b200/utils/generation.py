@@ -2,7 +2,7 @@
 The training models have no KV cache; evaluation prompts are short, so every step re-runs the prefix."""
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import torch
 

@@ -5,7 +5,6 @@ from __future__ import annotations
 
 import contextlib
 import os
-from typing import Optional
 
 import torch
 

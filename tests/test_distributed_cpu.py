@@ -6,7 +6,8 @@ import sys
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_PORT = [29600]
+# a separate port range per pytest-xdist worker (gw0, gw1, ...) so that `-n 4` runs do not collide
+_PORT = [29600 + 200 * int((os.environ.get("PYTEST_XDIST_WORKER", "gw0")[2:] or 0))]
 
 
 def run_dist(script, nproc, env=None, timeout=600):
