@@ -15,7 +15,8 @@ _TRIED = False
 def build(force: bool = False) -> str:
     import shutil
     from torch.utils import cpp_extension
-    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(_SRC):
+    deps = [_SRC, os.path.join(os.path.dirname(_SRC), "parallel_io.h")]
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(d) for d in deps):
         return _SO
     bdir = os.path.join(_HERE, "_build")
     os.makedirs(bdir, exist_ok=True)
