@@ -17,9 +17,10 @@ elif [ -n "$OMPI_COMM_WORLD_SIZE" ]; then
     export MASTER_ADDR
     export LOG_PATH=${LOG_PATH:-logs/ompi/$NODEID}
 else
-    export NTASKS=1
-    export NODEID=0
-    export MASTER_ADDR=127.0.0.1
+    # single node by default; a manual multi-node launch presets NTASKS / NODEID / MASTER_ADDR on every node
+    export NTASKS=${NTASKS:-1}
+    export NODEID=${NODEID:-0}
+    export MASTER_ADDR=${MASTER_ADDR:-127.0.0.1}
     export LOG_PATH=${LOG_PATH:-logs/local}
 fi
 mkdir -p "$LOG_PATH"

@@ -48,6 +48,8 @@ class TensorReference:
         return f"TensorReference({self.tid})"
 
 
+EXTRA_FILES_KEY = "_extra_files"      # user_content[EXTRA_FILES_KEY] = {file name: text}: written next to user_content.pt
+
 def _native_io():
     try:
         from . import native_io
@@ -268,7 +270,15 @@ def save_checkpoint(checkpoint_dir: str, tag: str, model: Optional[Dict[str, Any
         _save_object(optimizer, os.path.join(root, "optim", shard_file_name(dp_rank, tp_rank, pp_rank)),
                      use_xser, async_save)
     if user_content is not None and rank == 0:
+        # small side files (e.g. the PEFT adapter_config.json) travel as {"file name": text} under a reserved key
+        extra = user_content.pop(EXTRA_FILES_KEY, None) if isinstance(user_content, dict) else None
         torch.save(user_content, os.path.join(root, "user_content.pt"))
+        for name, text in (extra or {}).items():
+            with open(os.path.join(root, os.path.basename(name)), "w") as f:
+                f.write(text)
+        if extra and not _publish:          # staging for an object store: tell the uploader which side files exist
+            with open(os.path.join(root, ".extra_files"), "w") as f:
+                f.write("\n".join(os.path.basename(n) for n in extra) + "\n")
 
     def finish():
         # marker files: written once every rank's writes are durable
@@ -354,7 +364,12 @@ def _save_checkpoint_remote(url_dir, tag, model, optimizer, user_content, use_xs
                 f.write(tag + "\n")
             with open(os.path.join(local_root, "done"), "w") as f:
                 f.write(str(time.time()) + "\n")
-            for name in ("user_content.pt", "checkpoint", "done"):       # 'done' strictly last
+            extra_names = []
+            if os.path.exists(os.path.join(local_root, ".extra_files")):
+                with open(os.path.join(local_root, ".extra_files")) as f:
+                    extra_names = [l.strip() for l in f if l.strip()]
+                os.remove(os.path.join(local_root, ".extra_files"))
+            for name in (*extra_names, "user_content.pt", "checkpoint", "done"):       # 'done' strictly last
                 lp = os.path.join(local_root, name)
                 if os.path.exists(lp):
                     store.upload_file(lp, storage.join_url(root_url, name))

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn
@@ -48,6 +48,14 @@ class LoraConfig:
     @property
     def scaling(self) -> float:
         return float(self.lora_alpha) / float(self.lora_rank)
+
+    def to_adapter_config(self, base_model_name_or_path: Optional[str] = None) -> Dict[str, object]:
+        """The ``adapter_config.json`` that ``save_lora_config_adapter`` stores next to the adapter weights
+        (HF-PEFT field names, so the adapter can be described to other tooling)."""
+        return {"peft_type": "LORA", "task_type": "CAUSAL_LM", "r": int(self.lora_rank), "lora_alpha": float(self.lora_alpha),
+                "lora_dropout": float(self.lora_dropout), "bias": str(self.lora_bias),
+                "target_modules": list(self.target_modules), "base_model_name_or_path": base_model_name_or_path,
+                "fan_in_fan_out": False, "inference_mode": False}
 
 
 class LoraAdapter(nn.Module):

@@ -396,6 +396,19 @@ class BaseModelModule:
     def on_train_end(self, trainer):
         pass
 
+    def extra_checkpoint_files(self) -> Dict[str, str]:
+        """Small text files stored in the checkpoint directory next to ``user_content.pt``: with PEFT and
+        ``save_lora_config_adapter`` the LoRA description as ``adapter_config.json``."""
+        a = self.cfg.get("model_alignment_strategy", None)
+        peft = a.get("peft", None) if a is not None else None
+        if peft is None or not bool(peft.get("save_lora_config_adapter", True)):
+            return {}
+        import json
+        from ..models.lora import LoraConfig
+        base = self.config.get("model_config", None)
+        return {"adapter_config.json": json.dumps(LoraConfig.from_config(peft).to_adapter_config(str(base) if base else None),
+                                                  indent=2)}
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
         a = self.cfg.get("model_alignment_strategy", None)
         peft = a.get("peft", None) if a is not None else None

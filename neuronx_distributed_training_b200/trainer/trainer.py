@@ -123,6 +123,9 @@ class Trainer:
         if em is not None and em.save_bf16:
             # exp_manager.save_bf16: store the model weights in bf16 regardless of the training dtype
             model_sd = {k: (v.to(torch.bfloat16) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in model_sd.items()}
+        extra = self.model.extra_checkpoint_files() if hasattr(self.model, "extra_checkpoint_files") else None
+        if extra:
+            user_content[ckpt_io.EXTRA_FILES_KEY] = extra
         opt = self.model.optimizer
         if em is not None and em.checkpoint_callback_params.use_master_weights_in_ckpt and opt.master is not None:
             user_content["master_weights_in_ckpt"] = True

@@ -48,6 +48,20 @@ def test_save_load_roundtrip_through_object_store(fake_s3, async_save, use_xser)
     assert not ckpt.has_checkpoint(url, "step_3")
 
 
+def test_extra_text_files_reach_the_object_store(fake_s3):
+    """user_content["_extra_files"] (the PEFT adapter_config.json) is stored as plain files beside user_content.pt"""
+    m, o, uc = _state()
+    uc[ckpt.EXTRA_FILES_KEY] = {"adapter_config.json": '{"peft_type": "LORA"}'}
+    url = "s3://my-bucket/run2/checkpoints"
+    ckpt.save_checkpoint(url, "step_1", m, o, uc)
+    ckpt.finalize_checkpoint()
+    keys = storage.get_store(url).list(url + "/step_1")
+    assert any(k.endswith("/adapter_config.json") for k in keys), keys
+    assert not any(k.endswith(".extra_files") for k in keys)
+    _, _, uc2 = ckpt.load_checkpoint(url, "step_1", model=True, optimizer=True)
+    assert ckpt.EXTRA_FILES_KEY not in uc2 and uc2["note"] == "x"
+
+
 def test_incomplete_remote_checkpoint_is_rejected(fake_s3):
     m, o, uc = _state()
     url = "s3://b/ck"

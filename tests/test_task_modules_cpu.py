@@ -143,3 +143,12 @@ def test_lora_sft_trains_only_the_adapters(tmp_path):
             assert torch.equal(p_.detach(), base_before[n]), n                     # frozen base
     sd = mod.state_dict()
     assert sd and all(("adapter" in k or "lora" in k.lower()) for k in sd), list(sd)[:4]   # adapter-only checkpoint by default
+    # save_lora_config_adapter (default on): the adapter description is stored next to the adapter weights
+    ck = str(tmp_path / "manual" / "lora--step=6-consumed_samples=0.ckpt")
+    tr.save_checkpoint(ck)
+    with open(os.path.join(ck, "adapter_config.json")) as f:
+        ac = json.load(f)
+    assert ac["peft_type"] == "LORA" and ac["r"] == 4 and ac["lora_alpha"] == 8 and ac["target_modules"] == peft["target_modules"]
+    assert os.path.exists(os.path.join(ck, "done")) and os.path.exists(os.path.join(ck, "user_content.pt"))
+    uc = torch.load(os.path.join(ck, "user_content.pt"), weights_only=False)
+    assert "_extra_files" not in uc
