@@ -103,4 +103,6 @@ class DPOBaseModel:
         loss, cr, rr = dpo_loss(pi_c, pi_r, ref_c, ref_r, beta, str(dcfg.get("loss_type", "sigmoid")))
         module._logged["chosen_rewards"] = cr.mean().detach()      # read back only when metrics are logged
         module._logged["rejected_rewards"] = rr.mean().detach()
+        module._logged["reward_margin"] = (cr - rr).mean().detach()
+        module._logged["reward_accuracy"] = (cr > rr).float().mean().detach()
         return loss, None
