@@ -184,14 +184,10 @@ def main():
     module = HFLlamaModule(cfg, None)
     module.setup("fit")
     module.configure_optimizers(100000)
-    if args.impl == "native" and tp > 1 and os.environ.get("NXDT_FUSED_TP", "1") != "0" \
-            and os.environ.get("NXDT_MB_OVERLAP", "0") != "1":      # the two-stream overlap mode needs NCCL TP
-        try:
-            from neuronx_distributed_training_b200.parallel.fused import enable_fused_tp
-            enable_fused_tp(module.model)
-        except Exception as e:  # noqa
-            if rank == 0:
-                print(f"[bench] fused TP kernels not enabled: {e}", file=sys.stderr)
+    # the fused TP kernels are attached by module.setup() itself (model.fusions.fused_tp: auto; NXDT_FUSED_TP=0 or the
+    # library baseline arm select the NCCL path)
+    if rank == 0 and tp > 1:
+        print(f"[bench] fused TP kernels on {getattr(module, 'fused_tp_layers', 0)} linears", file=sys.stderr)
     hf = module.hf_config
     tokens_per_step = args.global_batch * args.seq_len
 

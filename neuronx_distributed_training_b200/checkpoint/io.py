@@ -27,6 +27,7 @@ from concurrent.futures import ThreadPoolExecutor, Future
 from typing import Any, Dict, List, Optional, Tuple
 
 import torch
+import torch.distributed as dist
 
 from ..parallel import state as ps
 from . import storage
@@ -443,7 +444,14 @@ def load_checkpoint(checkpoint_dir: str, tag: str, model: bool = True, optimizer
     tp_rank, pp_rank = ps.get_tensor_model_parallel_rank(), ps.get_pipeline_model_parallel_rank()
     m = o = None
     if model:
-        m = _load_object(os.path.join(root, "model", shard_file_name(0, tp_rank, pp_rank)), map_location)
+        mpath = os.path.join(root, "model", shard_file_name(0, tp_rank, pp_rank))
+        if _broadcast_load_enabled():
+            # every data-parallel replica needs the same model shard: ONE rank per (tp, pp) reads it and the others
+            # receive it over the data-parallel group, instead of dp_size readers hammering the same files
+            # (reference docs/general/features.rst: "load only on 1 data-parallel rank and broadcast")
+            m = _broadcast_over_dp(_load_object(mpath, map_location) if dp_rank == 0 else None)
+        else:
+            m = _load_object(mpath, map_location)
     if optimizer:
         p = os.path.join(root, "optim", shard_file_name(dp_rank, tp_rank, pp_rank))
         if not os.path.exists(p):
@@ -453,6 +461,60 @@ def load_checkpoint(checkpoint_dir: str, tag: str, model: bool = True, optimizer
     uc_path = os.path.join(root, "user_content.pt")
     uc = torch.load(uc_path, map_location="cpu", weights_only=False) if os.path.exists(uc_path) else None
     return m, o, uc
+
+
+def _dp_load_group():
+    return ps.get_data_parallel_group() if ps.get_context_model_parallel_size() == 1 else ps.get_data_context_parallel_group()
+
+
+def _broadcast_load_enabled() -> bool:
+    """On by default whenever there is more than one data-parallel replica (``NXDT_CKPT_LOAD_BROADCAST=0`` turns it off)."""
+    if os.environ.get("NXDT_CKPT_LOAD_BROADCAST", "1") == "0" or not dist.is_initialized():
+        return False
+    return ps.group_size(_dp_load_group()) > 1
+
+
+def _broadcast_over_dp(obj):
+    """``obj`` (a nested dict / list of tensors and plain values) is given on data-parallel rank 0 and ``None`` elsewhere;
+    returns it on every rank of the data-parallel group.  The structure travels as one pickled skeleton, the tensors
+    one by one (through the GPU when the group's backend is NCCL)."""
+    group = _dp_load_group()
+    src = dist.get_global_rank(group, 0)
+    is_src = dist.get_rank() == src
+    tensors: List[torch.Tensor] = []
+
+    def strip(x):
+        if torch.is_tensor(x):
+            tensors.append(x)
+            return ("__tensor__", len(tensors) - 1, tuple(x.shape), x.dtype)
+        if isinstance(x, dict):
+            return {k: strip(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return type(x)(strip(v) for v in x)
+        return x
+
+    box = [strip(obj) if is_src else None]
+    dist.broadcast_object_list(box, src=src, group=group)
+    skeleton = box[0]
+    use_cuda = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    received: Dict[int, torch.Tensor] = {}
+
+    def fill(x):
+        if isinstance(x, tuple) and len(x) == 4 and x[0] == "__tensor__":
+            _, idx, shape, dtype = x
+            if idx not in received:
+                t = tensors[idx].to(dev).contiguous() if is_src else torch.empty(shape, dtype=dtype, device=dev)
+                dist.broadcast(t, src=src, group=group)
+                received[idx] = tensors[idx] if is_src else t
+            return received[idx]
+        if isinstance(x, dict):
+            return {k: fill(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return type(x)(fill(v) for v in x)
+        return x
+
+    return fill(skeleton)
 
 
 def remove_checkpoint(path: str, async_remove: bool = True) -> None:

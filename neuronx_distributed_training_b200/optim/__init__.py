@@ -18,6 +18,12 @@ _OPTIMIZERS = {
 
 
 def register_optimizer(name, algorithm, **extra):
+    """Make ``model.optim.name: <name>`` available.  ``algorithm`` is the name of a built-in update rule (``adamw``,
+    ``adam``, ``sgd``, ``adamax``, ``adagrad``, ``rmsprop``, ``novograd``) or a callable
+    ``fn(param32, grad32, state, group, step)`` that updates the flat fp32 parameter view in place; ``state`` holds two
+    persistent buffers (``exp_avg``, ``exp_avg_sq``) and ``group`` the YAML hyper-parameters (``lr``, ``weight_decay``,
+    ``betas``, ``eps``, ...).  Either way the update runs inside the flat ``DistributedOptimizer``, i.e. with ZeRO-1
+    sharding, fp32 master weights / gradient accumulation, global-norm clipping and checkpointing for free."""
     _OPTIMIZERS[name] = (algorithm, extra)
 
 

@@ -57,7 +57,7 @@ class DistributedOptimizer:
                  max_grad_norm: Optional[float] = 1.0, stochastic_rounding: bool = False,
                  state_dtype: torch.dtype = torch.float32, dp_group=None, grad_sync_groups: Optional[dict] = None,
                  average_over_dp: bool = True, extra_grad_scale: float = 1.0, **unused):
-        self.algorithm = algorithm.lower()
+        self.algorithm = algorithm if callable(algorithm) else algorithm.lower()
         self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, momentum=momentum)
         self.param_groups: List[Dict[str, Any]] = []
         for g in param_groups:
@@ -140,7 +140,8 @@ class DistributedOptimizer:
         need_master = self.master_weights and pdtype != torch.float32
         self.master = self.param_buffer[self.shard_lo:self.shard_hi].float() if need_master else None
         self.exp_avg = torch.zeros(n, dtype=self.state_dtype, device=dev)
-        two_buffers = self.algorithm in ("adamw", "adam", "adamax", "adagrad", "rmsprop")
+        # a callable algorithm is a user-registered update rule (optim.register_optimizer): it gets both state buffers
+        two_buffers = callable(self.algorithm) or self.algorithm in ("adamw", "adam", "adamax", "adagrad", "rmsprop")
         self.exp_avg_sq = torch.zeros(n, dtype=self.state_dtype, device=dev) if two_buffers else None
         # NovoGrad keeps ONE second-moment scalar per tensor (layer-wise normalisation)
         self.layer_v = torch.zeros(len(self.params), dtype=torch.float32, device=dev) if self.algorithm == "novograd" else None
@@ -350,7 +351,17 @@ class DistributedOptimizer:
     def _update(self, p, g, lo, hi, group, clip):
         lr, wd = float(group["lr"]), float(group["weight_decay"])
         master = self.master[lo:hi] if self.master is not None else None
-        if self.algorithm in ("adamw", "adam"):
+        if callable(self.algorithm):
+            # user-registered element-wise update rule on the flat fp32 views of this rank's shard:
+            #   fn(param32, grad32, state, group, step) updates param32 in place; state["exp_avg"] / state["exp_avg_sq"]
+            #   are two persistent buffers of the same shape (checkpointed and ZeRO-1-sharded like Adam's moments)
+            p32 = master if master is not None else p.float()
+            gg = g.float() * (clip if clip is not None else 1.0)
+            self.algorithm(p32, gg, {"exp_avg": self.exp_avg[lo:hi], "exp_avg_sq": self.exp_avg_sq[lo:hi]}, group,
+                           self.step_count)
+            if master is not None or p32.data_ptr() != p.data_ptr():
+                p.copy_(p32)
+        elif self.algorithm in ("adamw", "adam"):
             b1, b2 = group["betas"]
             scale = clip
             if self.algorithm == "adam" and wd != 0.0:
@@ -454,7 +465,7 @@ class DistributedOptimizer:
     def state_dict(self) -> Dict[str, Any]:
         """This rank's shard (every DP rank saves its own under ZeRO-1)."""
         sd = {
-            "step": self.step_count, "algorithm": self.algorithm, "zero1": self.zero1,
+            "step": self.step_count, "algorithm": self.algorithm if isinstance(self.algorithm, str) else getattr(self.algorithm, "__name__", "custom"), "zero1": self.zero1,
             "dp_size": self.dp_size if self.zero1 else 1, "dp_rank": self.dp_rank if self.zero1 else 0,
             "total": self.total, "shard_lo": self.shard_lo, "shard_hi": self.shard_hi,
             "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "master": self.master,

@@ -96,6 +96,11 @@ class HFLlamaModule(BaseHfModel):
                 setattr(hf, attr, type(getattr(hf, attr))(m[yaml_key]) if getattr(hf, attr) is not None else m[yaml_key])
         if m.get("hidden_size", None) is not None and m.get("head_dim", None) is None:
             hf.head_dim = hf.hidden_size // hf.num_attention_heads
+        if bool(getattr(hf, "tie_word_embeddings", False)) and self.dims.pp > 1:
+            # embedding and LM head land on different stages: the reference fails with "shared weight has None grad"
+            # (docs/general/known_issues.rst); reject the combination up front instead
+            raise ValueError("tie_word_embeddings is not supported with pipeline parallelism; set "
+                             "model.tie_word_embeddings: false (the head then gets its own weight) or use PP=1")
         fus = m.get("fusions", Config({})) or Config({})
         hf.sequence_parallel_enabled = self.sequence_parallel
         hf.qkv_linear = bool(m.get("qkv_linear", True))

@@ -116,6 +116,40 @@ class BaseModelModule:
             ops.fp8.set_enabled(bool(fus.get("fp8_gemm", True)))
         if self.model is None:
             self.model = self.build_model()
+            self._maybe_enable_fused_tp()
+
+    def _maybe_enable_fused_tp(self) -> int:
+        """Attach the fused AG->GEMM / GEMM->RS / AG-wgrad kernels (parallel/fused.py) to the sequence-parallel linears.
+        ``model.fusions.fused_tp``: ``auto`` (default: on for CUDA runs with TP > 1 and sequence parallelism, quietly
+        off when the workspace cannot be set up), ``true`` (errors are fatal), ``false``.  ``NXDT_FUSED_TP=0|1`` overrides."""
+        fus = self.config.get("fusions", Config({})) if "fusions" in self.config else Config({})
+        want = fus.get("fused_tp", "auto")
+        env = os.environ.get("NXDT_FUSED_TP")
+        if env is not None:
+            want = env != "0"
+        if isinstance(want, str):
+            want = {"true": True, "false": False}.get(want.lower(), "auto")
+        self.fused_tp_layers = 0
+        if want is False or self.device.type != "cuda" or self.dims.tp < 2 or not self.sequence_parallel:
+            return 0
+        if ops.get_backend() == "torch" or self.use_mb_overlap:      # library baseline / two-stream mode: NCCL TP path
+            return 0
+        if self.use_cuda_graph and want == "auto" and os.environ.get("NXDT_CUDA_GRAPH_WITH_FUSED_TP", "0") != "1":
+            log.info("cuda_graph requested: tensor-parallel collectives stay on NCCL (graph replay of the fused kernels is "
+                     "not validated yet, docs/ROUND2_PLAN.md)")
+            return 0
+        try:
+            from ..parallel.fused import enable_fused_tp
+            seq = int(self.config.get("encoder_seq_length", None) or self.cfg.data.get("seq_length", 8192))
+            self.fused_tp_layers = enable_fused_tp(self.model, seq_len=max(1, seq // self.dims.cp),
+                                                   micro_batch=self.micro_batch_size)
+            if ps.get_rank() == 0:
+                log.info("fused tensor-parallel kernels attached to %d linears", self.fused_tp_layers)
+        except Exception as e:  # noqa: BLE001 - e.g. no peer access between the GPUs of the TP group
+            if want is True:
+                raise
+            log.warning("fused tensor-parallel kernels not enabled (%s); using the NCCL path", e)
+        return self.fused_tp_layers
 
     def local_named_parameters(self):
         m = self.model

@@ -53,6 +53,10 @@ def test_ulysses_attention_context_parallel(cp):
     run_dist("ulysses_attention.py", cp, {"CP": str(cp)})
 
 
+def test_checkpoint_load_reads_once_per_model_shard_and_broadcasts(tmp_path):
+    run_dist("ckpt_broadcast_load.py", 2, {"WORKDIR": str(tmp_path)})
+
+
 def test_moe_expert_parallel_matches_single_process():
     run_dist("moe_ep.py", 2, {"EP": "2"})
 

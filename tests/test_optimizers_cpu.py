@@ -77,3 +77,42 @@ def test_novograd_layerwise_second_moment():
 def test_unknown_optimizer_name():
     with pytest.raises(KeyError):
         get_optimizer("adafactor")
+
+
+def test_user_registered_update_rule_runs_inside_the_flat_optimizer():
+    """optim.register_optimizer(name, callable): a custom element-wise rule (here: Lion) gets ZeRO-style flat buffers,
+    clipping and state checkpointing from DistributedOptimizer and matches a hand-written reference."""
+    from neuronx_distributed_training_b200 import optim
+    from neuronx_distributed_training_b200.optim.distributed import DistributedOptimizer
+
+    def lion(p32, g32, state, group, step):
+        b1, b2 = group["betas"]
+        m = state["exp_avg"]
+        upd = (m * b1 + g32 * (1 - b1)).sign_()
+        p32.mul_(1 - group["lr"] * group["weight_decay"]).add_(upd, alpha=-group["lr"])
+        m.mul_(b2).add_(g32, alpha=1 - b2)
+
+    optim.register_optimizer("lion", lion)
+    algo, _ = optim.get_optimizer("lion")
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(7, 5)); b = torch.nn.Parameter(torch.randn(5))
+    ref_w, ref_b = w.detach().clone(), b.detach().clone()
+    ref_m = [torch.zeros_like(ref_w), torch.zeros_like(ref_b)]
+    opt = DistributedOptimizer([{"params": [w, b]}], lr=1e-2, betas=(0.9, 0.99), weight_decay=0.1, algorithm=algo,
+                               zero1=False, master_weights=False, fp32_grad_acc=False, max_grad_norm=None)
+    for step in range(4):
+        gs = [torch.randn(7, 5), torch.randn(5)]
+        for p_, g_ in zip(opt.params, gs):
+            if getattr(p_, "main_grad", None) is not None:
+                p_.main_grad.copy_(g_)
+            else:
+                p_.grad = g_.clone()
+        opt.step()
+        for r, m, g_ in zip((ref_w, ref_b), ref_m, gs):
+            upd = (m * 0.9 + g_ * 0.1).sign()
+            r.mul_(1 - 1e-2 * 0.1).add_(upd, alpha=-1e-2)
+            m.mul_(0.99).add_(g_, alpha=0.01)
+    assert torch.allclose(opt.params[0].detach().view(7, 5), ref_w, atol=1e-6)
+    assert torch.allclose(opt.params[1].detach(), ref_b, atol=1e-6)
+    sd = opt.state_dict()
+    assert sd["algorithm"] == "lion"
