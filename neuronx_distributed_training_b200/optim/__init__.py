@@ -14,6 +14,7 @@ _OPTIMIZERS = {
     "adagrad": ("adagrad", {}),
     "rmsprop": ("rmsprop", {}),
     "novograd": ("novograd", {}),
+    "adafactor": ("adafactor", {}),
 }
 
 

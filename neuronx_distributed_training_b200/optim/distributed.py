@@ -16,6 +16,7 @@ The clip coefficient stays on the device (no host sync in the step).
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -56,9 +57,13 @@ class DistributedOptimizer:
                  zero1: bool = True, master_weights: bool = True, fp32_grad_acc: bool = True,
                  max_grad_norm: Optional[float] = 1.0, stochastic_rounding: bool = False,
                  state_dtype: torch.dtype = torch.float32, dp_group=None, grad_sync_groups: Optional[dict] = None,
-                 average_over_dp: bool = True, extra_grad_scale: float = 1.0, **unused):
+                 average_over_dp: bool = True, extra_grad_scale: float = 1.0,
+                 extra_defaults: Optional[Dict[str, Any]] = None, **unused):
         self.algorithm = algorithm if callable(algorithm) else algorithm.lower()
         self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, momentum=momentum)
+        # algorithm-specific hyper-parameters from the YAML (rmsprop alpha, novograd grad_averaging, adafactor
+        # clip_threshold / decay_rate / beta1 / scale_parameter, custom rules' own keys): visible as group[...]
+        self.defaults.update(extra_defaults or {})
         self.param_groups: List[Dict[str, Any]] = []
         for g in param_groups:
             g = dict(g)
@@ -99,6 +104,7 @@ class DistributedOptimizer:
         # contiguous segments per (group, tp_dup)
         entries.sort(key=lambda e: (e[0], e[1]))
         self.params: List[torch.nn.Parameter] = [e[2] for e in entries]
+        self.param_group_idx: List[int] = [e[0] for e in entries]
         dev = self.params[0].device
         pdtype = self.params[0].dtype
         for p in self.params:
@@ -141,10 +147,13 @@ class DistributedOptimizer:
         self.master = self.param_buffer[self.shard_lo:self.shard_hi].float() if need_master else None
         self.exp_avg = torch.zeros(n, dtype=self.state_dtype, device=dev)
         # a callable algorithm is a user-registered update rule (optim.register_optimizer): it gets both state buffers
-        two_buffers = callable(self.algorithm) or self.algorithm in ("adamw", "adam", "adamax", "adagrad", "rmsprop")
+        two_buffers = callable(self.algorithm) or self.algorithm in ("adamw", "adam", "adamax", "adagrad", "rmsprop", "adafactor")
         self.exp_avg_sq = torch.zeros(n, dtype=self.state_dtype, device=dev) if two_buffers else None
         # NovoGrad keeps ONE second-moment scalar per tensor (layer-wise normalisation)
         self.layer_v = torch.zeros(len(self.params), dtype=torch.float32, device=dev) if self.algorithm == "novograd" else None
+        self.af_rc = None
+        if self.algorithm == "adafactor":
+            self._adafactor_setup()
         self.state = {"step": 0}
 
     def rebind_buffers(self, new_param_buffer: torch.Tensor, new_grad_buffer: torch.Tensor) -> None:
@@ -341,9 +350,12 @@ class DistributedOptimizer:
         pshard = self.param_buffer[self.shard_lo:self.shard_hi]
         if self.algorithm == "novograd":
             self._novograd_layer_moments(gshard, clip)
-        for s, lo, hi in self._seg_ranges():
-            g = self.param_groups[s.group_idx]
-            self._update(pshard[lo:hi], gshard[lo:hi], lo, hi, g, clip)
+        if self.algorithm == "adafactor":
+            self._adafactor_step(gshard, pshard, clip)
+        else:
+            for s, lo, hi in self._seg_ranges():
+                g = self.param_groups[s.group_idx]
+                self._update(pshard[lo:hi], gshard[lo:hi], lo, hi, g, clip)
         if self.zero1:
             dist.all_gather_into_tensor(self.param_buffer, pshard, group=self.dp_group)
         self._gshard = None
@@ -461,6 +473,112 @@ class DistributedOptimizer:
             denom[lo:hi] = d[i]
         self._novograd_denom = denom
 
+    # ---- Adafactor (Shazeer & Stern 2018; hyper-parameter names of the NeMo / HF implementations) -------------
+    # Second moments of a >= 2-D tensor [..., r, c] are kept FACTORED: a row vector R [..., r] and a column vector
+    # C [..., c].  Under ZeRO-1 a rank owns an arbitrary contiguous piece of the flattened tensor, so every rank adds the
+    # row / column sums of its piece into one small vector that is all-reduced over the data-parallel group; R and C end
+    # up replicated (they are tiny), everything element-wise stays sharded.  1-D tensors use the ordinary second moment
+    # (``exp_avg_sq``); the optional first moment (``beta1``) lives in ``exp_avg``.  Like every TP implementation, the
+    # statistics of a tensor-parallel weight are those of the local shard.
+    def _adafactor_setup(self) -> None:
+        self._af_meta = []          # per param: (factored, batch, rows, cols, offset of R in af_rc, offset of C)
+        off = 0
+        for p in self.params:
+            shp = tuple(p.shape)
+            if len(shp) >= 2:
+                r, c = int(shp[-2]), int(shp[-1])
+                b = p.numel() // (r * c)
+                self._af_meta.append((True, b, r, c, off, off + b * r))
+                off += b * (r + c)
+            else:
+                self._af_meta.append((False, 1, 1, int(p.numel()), -1, -1))
+        self.af_rc = torch.zeros(max(off, 1), dtype=torch.float32, device=self.device)
+
+    def _af_pieces(self):
+        """(param index, lo, hi in shard-local coordinates, offset of the piece inside its tensor)"""
+        out = []
+        for i, (o, p) in enumerate(zip(self.offsets, self.params)):
+            lo, hi = max(o, self.shard_lo), min(o + p.numel(), self.shard_hi)
+            if lo < hi:
+                out.append((i, lo - self.shard_lo, hi - self.shard_lo, lo - o))
+        return out
+
+    def _adafactor_step(self, gshard: torch.Tensor, pshard: torch.Tensor, clip) -> None:
+        CH = 1 << 22                                             # elements per index_add chunk (bounds temporaries)
+        t = self.step_count
+        hp = self.param_groups[0]
+        decay_rate = float(hp.get("decay_rate", -0.8))
+        beta2t = 1.0 - math.pow(t, decay_rate)
+        eps = hp.get("eps", None)
+        eps1, eps2 = (float(eps[0]), float(eps[1])) if isinstance(eps, (tuple, list)) else (1e-30, 1e-3)
+        clip_threshold = float(hp.get("clip_threshold", 1.0))
+        beta1 = hp.get("beta1", None)
+        scale_parameter = bool(hp.get("scale_parameter", True))
+        pieces = self._af_pieces()
+        g32 = gshard.float() if gshard.dtype != torch.float32 else gshard.clone()
+        if clip is not None:
+            g32.mul_(clip)
+        # 1. row / column sums of g^2 + eps1 for the factored tensors
+        part = torch.zeros_like(self.af_rc)
+        for i, lo, hi, toff in pieces:
+            fact, b, r, c, ro, co = self._af_meta[i]
+            if not fact:
+                continue
+            for a in range(lo, hi, CH):
+                e = min(hi, a + CH)
+                idx = torch.arange(toff + (a - lo), toff + (e - lo), device=self.device)
+                upd = g32[a:e].pow(2).add_(eps1)
+                part.index_add_(0, ro + idx // c, upd)                               # row id = b * r + i
+                part.index_add_(0, co + (idx // (r * c)) * c + idx % c, upd)         # column id = b * c + j
+        if self.zero1:
+            dist.all_reduce(part, group=self.dp_group)
+        for i, (fact, b, r, c, ro, co) in enumerate(self._af_meta):
+            if fact:
+                part[ro:ro + b * r].div_(c)          # mean over the columns
+                part[co:co + b * c].div_(r)          # mean over the rows
+        self.af_rc.mul_(beta2t).add_(part, alpha=1.0 - beta2t)
+        # 2. the unclipped update u (in place of g32) and the per-tensor sums of u^2 and p^2
+        p32 = self.master if self.master is not None else pshard.float()
+        stats = torch.zeros(2 * len(self.params), dtype=torch.float32, device=self.device)
+        for i, lo, hi, toff in pieces:
+            fact, b, r, c, ro, co = self._af_meta[i]
+            if fact:
+                R = self.af_rc[ro:ro + b * r].view(b, r)
+                rfac = (R / R.mean(dim=1, keepdim=True)).rsqrt_().reshape(-1)
+                cfac = self.af_rc[co:co + b * c].rsqrt()
+                for a in range(lo, hi, CH):
+                    e = min(hi, a + CH)
+                    idx = torch.arange(toff + (a - lo), toff + (e - lo), device=self.device)
+                    g32[a:e].mul_(rfac[idx // c]).mul_(cfac[(idx // (r * c)) * c + idx % c])
+            else:
+                v = self.exp_avg_sq[lo:hi]
+                v.mul_(beta2t).add_(g32[lo:hi].pow(2).add_(eps1), alpha=1.0 - beta2t)
+                g32[lo:hi].mul_(v.float().rsqrt())
+            stats[2 * i] = g32[lo:hi].pow(2).sum()
+            stats[2 * i + 1] = p32[lo:hi].float().pow(2).sum()
+        if self.zero1:
+            dist.all_reduce(stats, group=self.dp_group)
+        # 3. RMS clipping of the update, parameter-scaled learning rate, optional momentum, decoupled weight decay
+        for i, lo, hi, toff in pieces:
+            grp = self.param_groups[self.param_group_idx[i]]
+            n = float(self.params[i].numel())
+            rms_u = (stats[2 * i] / n).sqrt()
+            lr_t = float(grp["lr"])
+            if scale_parameter:
+                lr_t = lr_t * torch.clamp((stats[2 * i + 1] / n).sqrt(), min=eps2)
+            u = g32[lo:hi]
+            u.div_(torch.clamp(rms_u / clip_threshold, min=1.0)).mul_(lr_t)
+            if beta1 is not None:
+                m = self.exp_avg[lo:hi]
+                m.mul_(float(beta1)).add_(u, alpha=1.0 - float(beta1))
+                u = m.float()
+            wd = float(grp["weight_decay"])
+            if wd != 0.0:
+                p32[lo:hi].mul_(1.0 - wd * lr_t)
+            p32[lo:hi].sub_(u)
+        if self.master is not None or p32.data_ptr() != pshard.data_ptr():
+            pshard.copy_(p32)
+
     # ------------------------------------------------------------------------------------------
     def state_dict(self) -> Dict[str, Any]:
         """This rank's shard (every DP rank saves its own under ZeRO-1)."""
@@ -474,6 +592,8 @@ class DistributedOptimizer:
         }
         if self.layer_v is not None:
             sd["layer_v"] = self.layer_v
+        if self.af_rc is not None:
+            sd["adafactor_rc"] = self.af_rc          # replicated over the data-parallel group
         return sd
 
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
@@ -487,6 +607,8 @@ class DistributedOptimizer:
             self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         if self.layer_v is not None and sd.get("layer_v") is not None:
             self.layer_v.copy_(sd["layer_v"])
+        if self.af_rc is not None and sd.get("adafactor_rc") is not None:
+            self.af_rc.copy_(sd["adafactor_rc"])
         if self.master is not None:
             if sd.get("master") is not None:
                 self.master.copy_(sd["master"])

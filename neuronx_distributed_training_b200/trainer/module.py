@@ -163,8 +163,12 @@ class BaseModelModule:
         groups = self.setup_optimizer_param_groups()
         clip = self.cfg.trainer.get("gradient_clip_val", None)
         pol = self.precision
+        eps = ocfg.get("eps", 1e-8)
+        eps = tuple(float(e) for e in eps) if isinstance(eps, (list, tuple)) else float(eps)     # adafactor: (eps1, eps2)
+        known = {"name", "lr", "betas", "eps", "weight_decay", "momentum", "sched", "overlap_grad_reduce", "capturable"}
+        extras = {k: ocfg[k] for k in ocfg.keys() if k not in known} if hasattr(ocfg, "keys") else {}
         common = dict(lr=float(ocfg.get("lr", 1e-4)), betas=tuple(ocfg.get("betas", (0.9, 0.999))),
-                      eps=float(ocfg.get("eps", 1e-8)), weight_decay=float(ocfg.get("weight_decay", 0.01)),
+                      eps=eps, weight_decay=float(ocfg.get("weight_decay", 0.01)), extra_defaults=extras,
                       algorithm=algo, momentum=float(ocfg.get("momentum", 0.0)), zero1=self.zero1,
                       master_weights=pol.master_weights, fp32_grad_acc=pol.fp32_grad_acc, max_grad_norm=clip,
                       stochastic_rounding=pol.stochastic_rounding, state_dtype=pol.optimizer_state_dtype)

@@ -33,6 +33,11 @@ def test_zero1_matches_adamw():
     run_dist("zero1.py", 2)
 
 
+def test_zero1_adafactor_matches_unsharded_reference():
+    pytest.importorskip("transformers")
+    run_dist("zero1_adafactor.py", 2)
+
+
 @pytest.mark.parametrize("pp,vpp,tp,nmb", [(2, 1, 1, 4), (4, 1, 1, 6), (2, 2, 1, 4), (2, 1, 2, 3), (4, 2, 1, 8)])
 def test_pipeline_matches_unpipelined(pp, vpp, tp, nmb):
     run_dist("pipeline.py", pp * tp, {"PP": str(pp), "VPP": str(vpp), "TP": str(tp), "NMB": str(nmb)})

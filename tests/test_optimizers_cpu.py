@@ -76,7 +76,7 @@ def test_novograd_layerwise_second_moment():
 
 def test_unknown_optimizer_name():
     with pytest.raises(KeyError):
-        get_optimizer("adafactor")
+        get_optimizer("lamb_8bit")
 
 
 def test_user_registered_update_rule_runs_inside_the_flat_optimizer():
@@ -116,3 +116,34 @@ def test_user_registered_update_rule_runs_inside_the_flat_optimizer():
     assert torch.allclose(opt.params[1].detach(), ref_b, atol=1e-6)
     sd = opt.state_dict()
     assert sd["algorithm"] == "lion"
+
+
+@pytest.mark.parametrize("beta1,scale_parameter,wd", [(None, True, 0.0), (0.9, False, 0.05), (None, False, 0.0)])
+def test_adafactor_matches_the_reference_implementation(beta1, scale_parameter, wd):
+    """Factored second moments inside the flat optimizer == transformers.optimization.Adafactor tensor by tensor
+    (2-D, 3-D "stacked experts" and 1-D parameters; update clipping, parameter scaling, momentum, weight decay)."""
+    hf_optim = pytest.importorskip("transformers.optimization")
+    from neuronx_distributed_training_b200.optim.distributed import DistributedOptimizer
+    from neuronx_distributed_training_b200 import optim
+    torch.manual_seed(0)
+    shapes = [(12, 7), (3, 5, 4), (9,), (6, 6)]
+    ours = [torch.nn.Parameter(torch.randn(*s)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    algo, _ = optim.get_optimizer("adafactor")
+    opt = DistributedOptimizer([{"params": ours}], lr=1e-2, weight_decay=wd, algorithm=algo, zero1=False, master_weights=False,
+                               fp32_grad_acc=False, max_grad_norm=None, eps=(1e-30, 1e-3),
+                               extra_defaults={"beta1": beta1, "scale_parameter": scale_parameter, "clip_threshold": 1.0,
+                                               "decay_rate": -0.8})
+    ropt = hf_optim.Adafactor(ref, lr=1e-2, eps=(1e-30, 1e-3), clip_threshold=1.0, decay_rate=-0.8, beta1=beta1,
+                              weight_decay=wd, scale_parameter=scale_parameter, relative_step=False, warmup_init=False)
+    for step in range(5):
+        for p_, r_ in zip(opt.params, ref):
+            g = torch.randn(*r_.shape) * (3.0 if step == 2 else 0.3)          # step 2 triggers the RMS clipping
+            r_.grad = g.clone()
+            p_.main_grad.copy_(g)
+        opt.step()
+        ropt.step()
+        for p_, r_ in zip(opt.params, ref):
+            assert torch.allclose(p_.detach(), r_.detach(), atol=2e-6, rtol=1e-5), (step, tuple(r_.shape))
+    sd = opt.state_dict()
+    assert "adafactor_rc" in sd
