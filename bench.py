@@ -13,7 +13,8 @@ clipping, the AdamW update and the LR schedule.
 Other named configs: ``--model llama2_7b --tp 2 --pp 2`` on 8 GPUs (BASELINE config 3: TP2 x PP2 x DP2, 1F1B, ZeRO-1),
 ``--model llama3_70b`` on 8 GPUs (config 5).  Experiment switches (all default off): ``NXDT_CUDA_GRAPH=1`` (graph replay of
 the micro-batch), ``NXDT_MB_OVERLAP=1`` (two micro-batches on two streams, NCCL TP path), ``NXDT_FUSED_TP=0`` (NCCL TP
-path), ``NXDT_OVERLAP_GRAD_REDUCE=1`` (data-parallel reduction during backward), ``NXDT_FP8=1`` (e4m3 linear GEMMs).
+path), ``NXDT_OVERLAP_GRAD_REDUCE=1`` (data-parallel reduction during backward), ``NXDT_FP8=1`` (e4m3 linear GEMMs),
+``NXDT_KEEP_GATHERED=1`` (column linears keep the gathered input for wgrad: one all-gather less per linear).
 
 ``--impl reference`` would run the unmodified reference from baseline/_ref; it cannot be imported here
 (needs torch_xla / neuronx_distributed / nemo / lightning) so that arm reports unavailable.
@@ -120,6 +121,11 @@ class ClockSampler:
         load = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "samples": len(sm), "power_w_max": max(power)}
+
+
+def _keep_gathered():
+    from neuronx_distributed_training_b200.parallel.layers import keep_gathered_input
+    return keep_gathered_input()
 
 
 def main():
@@ -269,7 +275,9 @@ def main():
                        "recompute": recompute, "l2_policy": "inputs larger than L2 (weights+activations >> 126 MB per step)",
                        "peak_mem_gb": round(mem_gb, 1), "final_loss": float(loss),
                        "cuda_graph": getattr(module, "_mb_graph", None) is not None,
-                       "microbatch_overlap": bool(getattr(module, "use_mb_overlap", False))},
+                       "microbatch_overlap": bool(getattr(module, "use_mb_overlap", False)),
+                       "fused_tp_layers": int(getattr(module, "fused_tp_layers", 0)),
+                       "keep_gathered_input": bool(_keep_gathered())},
             "clocks": clocks, "gpu_launches": launches,
         }
         if not args.no_e2e:

@@ -14,6 +14,7 @@ Design (B200-first, not a translation):
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -122,6 +123,21 @@ def _wgrad_fused_gather(fused, dy2d: torch.Tensor, x_local2d: torch.Tensor, weig
     return fused.all_gather_wgrad(dy2d, x_local2d, out, False)
 
 
+# Keep the all-gathered input of a sequence-parallel column linear for the weight gradient instead of gathering it a
+# second time in backward (the Megatron default, which trades NVLink traffic for activation memory).  On a B200 node the
+# trade goes the other way at large TP: the layer is communication-bound and 180 GB leave room for [tokens, hidden] per
+# column linear.  ``model.fusions.keep_gathered_input`` / ``NXDT_KEEP_GATHERED=1``.
+_KEEP_GATHERED = {"on": os.environ.get("NXDT_KEEP_GATHERED", "0") == "1"}
+
+
+def set_keep_gathered_input(flag: bool) -> None:
+    _KEEP_GATHERED["on"] = bool(flag)
+
+
+def keep_gathered_input() -> bool:
+    return _KEEP_GATHERED["on"]
+
+
 class _ColumnParallelLinearFn(torch.autograd.Function):
     """Y = AG_seq(X) @ W^T (+b).  Backward: dX = RS_seq(dY @ W) (or all-reduce without SP),
     dW = AG_seq(X)^T dY."""
@@ -137,12 +153,21 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
             fused.ok(x2d.shape[0], x2d.shape[1], weight.shape[0])
         ctx.can_fuse = can_fuse
         use_fused = can_fuse and fused.prefer_ag_gemm(x2d.shape[0], x2d.shape[1], weight.shape[0])
+        kept = None
+        keep = _KEEP_GATHERED["on"] and weight.requires_grad
         if sequence_parallel and tp > 1:
             if use_fused:
-                y2d = fused.all_gather_gemm(x2d, weight)
+                if keep:
+                    # the gathered view lives in the double-buffered symmetric workspace: copy it out
+                    y2d, xg = fused.all_gather_gemm(x2d, weight, return_gathered=True)
+                    kept = xg.clone()
+                else:
+                    y2d = fused.all_gather_gemm(x2d, weight)
             else:
                 total_x = mp.all_gather_dim0(x2d, group)
                 y2d = ops.gemm_nt(total_x, weight)
+                if keep:
+                    kept = total_x
                 del total_x
             out_shape = (x.shape[0] * tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
         else:
@@ -150,7 +175,8 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
             out_shape = tuple(x.shape[:-1]) + (weight.shape[0],)
         if bias is not None:
             y2d = y2d + bias
-        ctx.save_for_backward(x, weight)
+        ctx.kept = kept is not None
+        ctx.save_for_backward(kept if kept is not None else x, weight)
         return y2d.view(out_shape)
 
     @staticmethod
@@ -163,8 +189,10 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         need_dw = ctx.needs_input_grad[1]
         handle = None
         total_x = x2d
-        fused_wgrad = ctx.can_fuse and need_dw and ctx.fused.prefer_ag_wgrad(x2d.shape[0], x2d.shape[1], dy2d.shape[1])
-        if ctx.sp and tp > 1 and need_dw:
+        kept = getattr(ctx, "kept", False)          # x2d IS the gathered input: nothing to gather, plain wgrad GEMM
+        fused_wgrad = (not kept) and ctx.can_fuse and need_dw and \
+            ctx.fused.prefer_ag_wgrad(x2d.shape[0], x2d.shape[1], dy2d.shape[1])
+        if ctx.sp and tp > 1 and need_dw and not kept:
             if fused_wgrad:
                 pass   # the gather is fused into the K loop of the wgrad GEMM below
             else:

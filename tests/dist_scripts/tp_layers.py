@@ -16,7 +16,9 @@ w1 = torch.randn(I, H, generator=g) * 0.1       # column weight (stride 2: gate|
 w2 = torch.randn(H, I // 2, generator=g) * 0.1  # row weight
 gy = torch.randn(S, B, H, generator=g)
 
-for sp in (False, True):
+from neuronx_distributed_training_b200.parallel import layers as _layers
+for sp, keep in ((False, False), (True, False), (True, True)):
+    _layers.set_keep_gathered_input(keep)       # keep=True: the gathered input is saved for wgrad (no second all-gather)
     col = ColumnParallelLinear(H, I, bias=False, stride=2, sequence_parallel_enabled=sp)
     row = RowParallelLinear(I // 2, H, bias=False, sequence_parallel_enabled=sp)
     with torch.no_grad():
@@ -36,9 +38,10 @@ for sp in (False, True):
     yr = (F.silu(gr) * ur) @ w2r.t()
     yr.backward(gy)
     check(f"y sp={sp}", y, yr.chunk(tp, 0)[tpr] if sp else yr)
-    check(f"dx sp={sp}", x_in.grad, xr.grad.chunk(tp, 0)[tpr] if sp else xr.grad)
-    check(f"dw1 sp={sp}", col.weight.grad, shard_master_weight(w1r.grad, 0, tp, tpr, stride=2))
+    check(f"dx sp={sp} keep={keep}", x_in.grad, xr.grad.chunk(tp, 0)[tpr] if sp else xr.grad)
+    check(f"dw1 sp={sp} keep={keep}", col.weight.grad, shard_master_weight(w1r.grad, 0, tp, tpr, stride=2))
     check(f"dw2 sp={sp}", row.weight.grad, shard_master_weight(w2r.grad, 1, tp, tpr))
+_layers.set_keep_gathered_input(False)
 
 # ---- GQA QKV with KV replication --------------------------------------------------------------------------
 nh, nkv, hd = 2 * tp, max(1, tp // 2), 4

@@ -14,9 +14,9 @@ NXDT_RS_SELF_RESET=1 run eager_selfreset_check 120 $TR --master-port 29706 tests
 run graph_rs_only 60 $TR --master-port 29703 tests/gpu_checks/check_fused_graph.py --pattern rs,rs --replays 40
 run graph_ag_only 60 $TR --master-port 29704 tests/gpu_checks/check_fused_graph.py --pattern ag,ag --replays 40
 port=29711
-for mode in default overlap; do
+for mode in default overlap keepgather; do
   port=$((port + 1))
-  env $( [ $mode = overlap ] && echo NXDT_MB_OVERLAP=1 ) timeout 200 $TR --master-port $port bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2n2_bench_$mode.log 2>&1
+  env $( [ $mode = overlap ] && echo NXDT_MB_OVERLAP=1 ) $( [ $mode = keepgather ] && echo NXDT_KEEP_GATHERED=1 ) timeout 200 $TR --master-port $port bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2n2_bench_$mode.log 2>&1
   echo "== bench $mode exit $?"; grep -h '^{"metric"' gpurun_out/r2n2_bench_$mode.log | python -c "
 import sys, json
 for l in sys.stdin:
