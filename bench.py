@@ -163,6 +163,23 @@ def main():
         # footprint needs no recompute.
         # (the library-path arm keeps whole-MLP recomputation: its unfused ops hold more activations)
         recompute = ("swiglu" if args.impl == "native" else "mlp") if world == 1 else "none"
+        if world > 1:
+            # larger models (config 5: Llama-3-70B at TP 8 keeps 8.8 B parameters + fp32 AdamW state per GPU): take the
+            # lightest recompute policy whose estimated footprint fits (utils/perf_estimate.py, calibrated on the 8B runs)
+            import json as _json
+            from neuronx_distributed_training_b200.utils.perf_estimate import estimate_memory_gib
+            cpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "neuronx_distributed_training_b200", "models",
+                                 "configs", args.model + ".json")
+            if os.path.exists(cpath):
+                c = _json.load(open(cpath))
+                for cand in ("none", "swiglu", "mlp", "full"):
+                    est = estimate_memory_gib(
+                        c["hidden_size"], args.layers or c["num_hidden_layers"], args.seq_len, c["vocab_size"], c["intermediate_size"],
+                        c["num_attention_heads"], c.get("num_key_value_heads"), c.get("head_dim"), tp=tp, pp=pp, dp=dp,
+                        recompute=None if cand == "none" else cand)
+                    recompute = cand
+                    if est["total"] <= (165.0 if args.impl == "native" else 150.0):
+                        break
     gran, rec_list = {"none": (None, None), "mlp": ("selective", ["CoreAttention", "LlamaMLP"]),
                       "mlp_only": ("selective", ["LlamaMLP"]),
                       "swiglu": ("selective", ["ActivationMultiplyMLP"]),

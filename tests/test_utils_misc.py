@@ -134,3 +134,26 @@ def test_trainer_starts_the_watchdog_from_the_config_key(tmp_path):
     cfg["neuron_rt_exec_timeout"] = 600
     tr, _ = _fit(cfg)
     assert tr.watchdog is not None and not tr.watchdog.fired and tr.global_step == 2
+
+
+def test_memory_estimate_matches_the_measured_llama3_8b_footprints():
+    """utils/perf_estimate.estimate_memory_gib against the peak memory bench.py measured on B200 (profiles/bench_results.jsonl)."""
+    from neuronx_distributed_training_b200.utils.perf_estimate import estimate_memory_gib, fits_b200, llama_param_count
+    dims = dict(hidden_size=4096, num_layers=32, seq_len=8192, vocab_size=128256, intermediate_size=14336, num_heads=32,
+                num_kv_heads=8)
+    assert abs(llama_param_count(4096, 32, 128256, 14336, 32, 8) / 1e9 - 8.03) < 0.01
+    measured = [(dict(tp=1, recompute="swiglu"), 164.3), (dict(tp=1, recompute="mlp"), 150.8), (dict(tp=2), 85.8),
+                (dict(tp=4), 43.0), (dict(tp=8), 21.6)]
+    for kw, gib in measured:
+        est = estimate_memory_gib(**dims, **kw)
+        assert abs(est["total"] - gib) / gib < 0.06, (kw, est["total"], gib)
+    # lighter recompute policies keep more: none > swiglu > mlp > full
+    totals = [estimate_memory_gib(**dims, tp=1, recompute=r)["total"] for r in (None, "swiglu", "mlp", "full")]
+    assert totals == sorted(totals, reverse=True) and len(set(totals)) == 4
+    d70 = dict(hidden_size=8192, num_layers=80, seq_len=8192, vocab_size=128256, intermediate_size=28672, num_heads=64, num_kv_heads=8)
+    assert fits_b200(estimate_memory_gib(**d70, tp=8, recompute="mlp"))
+    assert estimate_memory_gib(**d70, tp=8, recompute="mlp", state_bytes=2)["optimizer"] < estimate_memory_gib(**d70, tp=8)["optimizer"]
+    # ZeRO-1 divides only the optimizer state; pipeline stages multiply the live activations
+    a, b = estimate_memory_gib(**dims, tp=2, dp=1), estimate_memory_gib(**dims, tp=2, dp=4)
+    assert abs(b["optimizer"] * 4 - a["optimizer"]) < 1e-6 and b["weights"] == a["weights"]
+    assert estimate_memory_gib(**dims, tp=2, pp=2)["activations"] > 0.9 * a["activations"]
