@@ -11,6 +11,10 @@
 //               softmax in the exp2 domain with LAZY rescaling (O in TMEM is only rescaled when a row maximum
 //               grows by more than 2^8; otherwise the stale maximum is kept, which is exact after the final 1/l
 //               normalisation), P written as bf16 into the 128B-swizzled K-major layout the PV MMA reads.
+// SPLIT = 2 (NXDT_FLASH_SPLIT=2, preview): EIGHT softmax warps; warps w and w+4 share a TMEM lane quadrant (the same 32
+// query rows) and each takes 64 of the 128 score columns, so every scheduler has two softmax warps to interleave and a
+// thread's serial chain per block halves.  The row maximum is exchanged through shared memory once per block (parity
+// double-buffered), the row sums once at the end; O rescaling, the P tile and the epilogue are split by columns too.
 // TMEM columns: [0,128) S even, [128,256) S odd, [256,384) O.
 // Output: O [B,S,Hq,D] bf16 and LSE [B,Hq,S] fp32 (natural log), which the backward kernels consume.
 #include <torch/extension.h>
@@ -30,8 +34,10 @@ constexpr int D = 128;           // head dim
 constexpr int TILE_BYTES = 128 * 128 * 2;     // one [128 x 128] bf16 tile = two 16 KB swizzle chunks
 constexpr int CHUNK_BYTES = 128 * 64 * 2;     // [128 rows x 64 cols] bf16
 constexpr int KV_STAGES = 2;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = TILE_BYTES /*Q / O staging*/ + 2 * KV_STAGES * TILE_BYTES /*K,V*/ + TILE_BYTES /*P*/ + 1024 + 256;
+constexpr int NUM_THREADS = 192;                 // SPLIT = 1; 64 + 128 * SPLIT in general
+constexpr int XCHG_BYTES = 3 * 2 * 128 * 4;       // [2 parities][2 halves][128 rows] row maxima + [2][128] row sums
+constexpr int SMEM_BYTES = TILE_BYTES /*Q / O staging*/ + 2 * KV_STAGES * TILE_BYTES /*K,V*/ + TILE_BYTES /*P*/ + 1024 + 256
+                           + XCHG_BYTES;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
 struct Params {
@@ -52,7 +58,15 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kk) {
   return make_smem_desc_sw128(tile_addr + kk * (16 * 128), CHUNK_BYTES, 1024);
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int SPLIT>
+__device__ __forceinline__ void softmax_bar(int id) {
+  // named barrier over the softmax warps only (the producer / MMA warps never join it)
+  if constexpr (SPLIT == 1) asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+  else asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(64 + 128 * SPLIT, 1)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -73,6 +87,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   uint64_t* p_full = bars + 13;            // 1
   uint64_t* pv_done = bars + 14;           // 1
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  float* xchg_max = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][2][128]
+  float* xchg_sum = xchg_max + 2 * 2 * 128;                                             // [2][128]
 
   // heavy (late) query blocks first: better tail behaviour under causal masking
   const int q_blk = p.num_q_blocks - 1 - (int)blockIdx.x;
@@ -91,7 +107,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4 * SPLIT);
     }
     mbar_init(p_full, 1);
     mbar_init(pv_done, 1);
@@ -163,7 +179,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       __syncwarp();
     }
   } else {
-    const uint32_t q = warp_idx & 3;
+    constexpr int COLS = BN / SPLIT;                 // score columns handled by this thread
+    constexpr int OCOLS = D / SPLIT;                 // output columns handled by this thread
+    const uint32_t q = warp_idx & 3;                 // TMEM lane quadrant: warps w and w + 4 share it
+    const uint32_t half = (warp_idx - 2) >> 2;       // which column slice (always 0 when SPLIT == 1)
     const uint32_t row = q * 32 + lane;
     const uint32_t lane_off = (q * 32u) << 16;
     const int q_pos = q0 + (int)row;
@@ -172,13 +191,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       const int j = j_lo + i, st = i & 1;
       mbar_wait(&s_full[st], (i >> 1) & 1);
       tcgen05_fence_after();
-      float s[BN];
+      float s[COLS];
       {
         uint32_t* sr = reinterpret_cast<uint32_t*>(s);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < COLS / 32; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_off + st * BN + c * 32, v);
+          tmem_ld_32x32b_x32(tmem_base + lane_off + st * BN + half * COLS + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int t = 0; t < 32; ++t) sr[c * 32 + t] = v[t];
@@ -188,11 +207,11 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
-      const int k0 = j * BN;
-      const bool need_mask = (p.causal && j == q_blk) || (p.window > 0 && k0 <= q_pos - p.window);
+      const int k0 = j * BN + (int)half * COLS;
+      const bool need_mask = (p.causal && j == q_blk) || (p.window > 0 && j * BN <= q_pos - p.window);
       float mx = -INFINITY;
 #pragma unroll
-      for (int t = 0; t < BN; ++t) {
+      for (int t = 0; t < COLS; ++t) {
         float v = s[t] * p.scale_log2;
         if (need_mask) {
           const int kpos = k0 + t;
@@ -200,6 +219,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         }
         s[t] = v;
         mx = fmaxf(mx, v);
+      }
+      if constexpr (SPLIT > 1) {
+        // row maximum over both column slices; buffers alternate with the block parity so that a fast thread writing
+        // block i+1 cannot overwrite what its partner still has to read for block i
+        float* xm = xchg_max + (i & 1) * 256;
+        xm[half * 128 + row] = mx;
+        softmax_bar<SPLIT>(2);
+        mx = fmaxf(mx, xm[(half ^ 1u) * 128 + row]);
       }
       const float m_new = fmaxf(m_used, mx);
       // PV_{i-1} must have retired before P is overwritten / O is touched
@@ -212,13 +239,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         if (i > 0) {
           tcgen05_fence_after();
 #pragma unroll
-          for (int c = 0; c < D / 16; ++c) {
+          for (int c = 0; c < OCOLS / 16; ++c) {
             uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_o + lane_off + c * 16, v);
+            tmem_ld_32x32b_x16(tmem_o + lane_off + half * OCOLS + c * 16, v);
             tmem_ld_wait();
 #pragma unroll
             for (int t = 0; t < 16; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * alpha);
-            tmem_st_32x32b_x16(tmem_o + lane_off + c * 16, v);
+            tmem_st_32x32b_x16(tmem_o + lane_off + half * OCOLS + c * 16, v);
           }
           tmem_st_wait();
           tcgen05_fence_before();
@@ -229,33 +256,39 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       float rs = 0.f;
       uint8_t* prow = sP + row * 128;
 #pragma unroll
-      for (int c16 = 0; c16 < BN / 8; ++c16) {
+      for (int c8 = 0; c8 < COLS / 8; ++c8) {
         float e[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          e[t] = exp2f(s[c16 * 8 + t] - m_exp);
+          e[t] = exp2f(s[c8 * 8 + t] - m_exp);
           rs += e[t];
         }
         uint4 o;
         o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
         o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+        const int c16 = (int)half * (COLS / 8) + c8;      // 16-byte column group of the full 128-column P row
         const int chunk = c16 >> 3, j16 = c16 & 7;
         *reinterpret_cast<uint4*>(prow + chunk * CHUNK_BYTES + ((j16 ^ (row & 7)) * 16)) = o;
       }
       l += rs;
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      softmax_bar<SPLIT>(1);
       if (threadIdx.x == 64) mbar_arrive(p_full);
     }
     // ---------------- epilogue: O / l -> bf16 -> smem (Q buffer is free now) -> TMA store; LSE ----------------
+    if constexpr (SPLIT > 1) {
+      xchg_sum[half * 128 + row] = l;
+      softmax_bar<SPLIT>(2);
+      l += xchg_sum[(half ^ 1u) * 128 + row];
+    }
     mbar_wait(pv_done, (n_blocks - 1) & 1);
     tcgen05_fence_after();
     const float inv_l = 1.f / l;
     uint8_t* orow = sQ + row * 128;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < OCOLS / 32; ++c) {
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+      tmem_ld_32x32b_x32(tmem_o + lane_off + half * OCOLS + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int t8 = 0; t8 < 4; ++t8) {
@@ -264,15 +297,15 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         o.y = pack_bf16x2(__uint_as_float(v[t8 * 8 + 2]) * inv_l, __uint_as_float(v[t8 * 8 + 3]) * inv_l);
         o.z = pack_bf16x2(__uint_as_float(v[t8 * 8 + 4]) * inv_l, __uint_as_float(v[t8 * 8 + 5]) * inv_l);
         o.w = pack_bf16x2(__uint_as_float(v[t8 * 8 + 6]) * inv_l, __uint_as_float(v[t8 * 8 + 7]) * inv_l);
-        const int c16 = c * 4 + t8;                       // 16-byte column group 0..15
+        const int c16 = (int)half * (OCOLS / 8) + c * 4 + t8;      // 16-byte column group 0..15
         const int chunk = c16 >> 3, j16 = c16 & 7;
         *reinterpret_cast<uint4*>(orow + chunk * CHUNK_BYTES + ((j16 ^ (row & 7)) * 16)) = o;
       }
     }
-    p.lse[((size_t)batch * p.Hq + head) * p.S + q_pos] = (m_used + log2f(l)) * 0.6931471805599453f;
+    if (half == 0) p.lse[((size_t)batch * p.Hq + head) * p.S + q_pos] = (m_used + log2f(l)) * 0.6931471805599453f;
     tcgen05_fence_before();
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    softmax_bar<SPLIT>(1);
     if (threadIdx.x == 64) {
       tma_store_2d(&tma_o, sQ, head * D, row_base + q0);
       tma_store_2d(&tma_o, sQ + CHUNK_BYTES, head * D + 64, row_base + q0);
@@ -319,11 +352,18 @@ std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k,
   p.lse = lse.data_ptr<float>();
   static bool once = false;
   if (!once) {
-    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     once = true;
   }
+  // NXDT_FLASH_SPLIT=2: the eight-softmax-warp variant (preview until its numerics have been checked on hardware)
+  static const int split = [] {
+    const char* e = std::getenv("NXDT_FLASH_SPLIT");
+    return (e != nullptr && e[0] == '2') ? 2 : 1;
+  }();
   dim3 grid(p.num_q_blocks, Hq, B);
-  flash_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  if (split == 2) flash_fwd_kernel<2><<<grid, 64 + 128 * 2, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  else flash_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, lse};
 }

@@ -11,6 +11,7 @@ run() {  # name, timeout, command...
 run pytest_gpu 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu
 run flash_bwd 120 python tests/gpu_checks/check_flash_bwd.py
 run flash_fwd 120 python tests/gpu_checks/check_flash.py
+NXDT_FLASH_SPLIT=2 run flash_fwd_split2 120 python tests/gpu_checks/check_flash.py      # eight-softmax-warp variant
 run fp8 180 python tests/gpu_checks/check_fp8.py
 run smoke 120 python -c "import __graft_entry__ as g; g.smoke()"
 NXDT_FLASH_BWD_PREVIEW=1 run bench_flash_native 200 python bench.py --steps 2 --warmup 3 --layers 8 --no-e2e
