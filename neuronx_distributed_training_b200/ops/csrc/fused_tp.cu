@@ -285,6 +285,10 @@ struct RsArgs {
   // memset in front of the kernel and a reducer can start on a 256-column chunk as soon as ITS tp tiles have landed.
   uint32_t* aflag_peer[MAX_TP];
   const uint32_t* aflag_local;
+  // Blocked staging layout (NXDT_RS_BLOCKED=1, needs N % 64 == 0): a slab is [row-block][64-column chunk] blocks of
+  // 16 KB, each the raw 128B-swizzled shared-memory image of a [128 x 64] bf16 chunk, written with one contiguous bulk
+  // copy over NVLink; the reduce phase applies the same XOR when it reads.
+  int blocked;
 };
 
 struct RsMaps {
@@ -311,6 +315,13 @@ struct RsGate {
     const int bpr = a.rows_per_rank / 128;
     const int d = m_blk / bpr;
     return a.rank * a.rows_per_rank + (m_blk - d * bpr) * 128;
+  }
+  __device__ __forceinline__ uint8_t* peer_chunk(int m_blk, int cn) const {
+    if (!a.blocked) return nullptr;
+    const int bpr = a.rows_per_rank / 128;
+    const int d = m_blk / bpr;
+    const size_t blk = ((size_t)a.rank * bpr + (m_blk - d * bpr)) * (size_t)(a.N / 64) + (size_t)(cn / 64);
+    return reinterpret_cast<uint8_t*>(a.stage_peer[d]) + blk * 16384;
   }
   __device__ __forceinline__ void tile_done(int m_blk, int n_blk) const {
     const int bpr = a.rows_per_rank / 128;
@@ -363,8 +374,17 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool ok = u < 128 * 32 && col < rs.N;
 #pragma unroll
         for (int sl = 0; sl < MAX_TP; ++sl)
-          if (ok && sl < rs.tp)
-            v[i][sl] = __ldcg(reinterpret_cast<const uint4*>(rs.stage_local + ((size_t)sl * rs.rows_per_rank + rb * 128 + r) * rs.N + col));
+          if (ok && sl < rs.tp) {
+            if (rs.blocked) {
+              const int unit = u & 31;                              // 16-byte unit within the 256 columns of this item
+              const size_t blk = ((size_t)sl * bpr + rb) * (size_t)(rs.N / 64) + (size_t)(nc * 4 + (unit >> 3));
+              const uint8_t* src = reinterpret_cast<const uint8_t*>(rs.stage_local) + blk * 16384 + r * 128 +
+                                   (((unit & 7) ^ (r & 7)) * 16);
+              v[i][sl] = __ldcg(reinterpret_cast<const uint4*>(src));
+            } else {
+              v[i][sl] = __ldcg(reinterpret_cast<const uint4*>(rs.stage_local + ((size_t)sl * rs.rows_per_rank + rb * 128 + r) * rs.N + col));
+            }
+          }
       }
 #pragma unroll
       for (int i = 0; i < ILP; ++i) {
@@ -601,6 +621,11 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   }();
   rs.self_reset = self_reset ? 1 : 0;
   TORCH_CHECK(!self_reset || rows_per_rank / 128 <= 512, "self-resetting counters support up to 512 row-blocks per rank");
+  static const bool blocked_env = [] {
+    const char* e = std::getenv("NXDT_RS_BLOCKED");
+    return e != nullptr && e[0] == '1';
+  }();
+  rs.blocked = (blocked_env && N % 64 == 0) ? 1 : 0;
   const bool arrive_flags = !aflag_peer.empty();
   for (int d = 0; d < MAX_TP; ++d) rs.aflag_peer[d] = nullptr;
   rs.aflag_local = nullptr;

@@ -316,10 +316,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* __restrict__ tma_a,
         if (issuer) {
           const int cn = n_blk * BLOCK_N + c * COLS_PER_CHUNK;
           if (cn < p.N) {
-            if constexpr (OUT == OUT_F32_ADD || OUT == OUT_BF16_ADD)
+            if constexpr (OUT == OUT_F32_ADD || OUT == OUT_BF16_ADD) {
               tma_reduce_add_2d(cmap, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
-            else
+            } else if constexpr (OUT == OUT_BF16_PEER) {
+              // blocked staging layout (gate returns a destination): the [128 x 64] chunk leaves as ONE contiguous 16 KB
+              // bulk copy, swizzle and all, instead of 128 separate 128-byte rows of a 2-D box; the owner un-swizzles
+              uint8_t* dst = gate.peer_chunk(m_blk, cn);
+              if (dst != nullptr) bulk_s2g(dst, smem_c + cbuf * C_STAGE_BYTES, C_STAGE_BYTES);
+              else tma_store_2d(cmap, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
+            } else {
               tma_store_2d(cmap, smem_c + cbuf * C_STAGE_BYTES, cn, cm);
+            }
           }
           tma_store_commit();
         }

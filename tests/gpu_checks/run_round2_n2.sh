@@ -10,6 +10,8 @@ NXDT_RS_CLEAR_KERNEL=1 run graph_ag_rs_clearkernel 60 $TR --master-port 29702 te
 NXDT_RS_SELF_RESET=1 run graph_ag_rs_selfreset 60 $TR --master-port 29705 tests/gpu_checks/check_fused_graph.py --pattern ag,rs --replays 40
 NXDT_RS_ARRIVE_FLAGS=1 run graph_ag_rs_flags 60 $TR --master-port 29707 tests/gpu_checks/check_fused_graph.py --pattern ag,rs --replays 40
 NXDT_RS_ARRIVE_FLAGS=1 run eager_flags_check 120 $TR --master-port 29708 tests/gpu_checks/check_fused_tp.py
+NXDT_RS_BLOCKED=1 run eager_blocked_check 120 $TR --master-port 29709 tests/gpu_checks/check_fused_tp.py     # 16 KB contiguous peer writes
+NXDT_RS_BLOCKED=1 NXDT_RS_ARRIVE_FLAGS=1 run eager_blocked_flags_check 120 $TR --master-port 29710 tests/gpu_checks/check_fused_tp.py
 NXDT_RS_SELF_RESET=1 run eager_selfreset_check 120 $TR --master-port 29706 tests/gpu_checks/check_fused_tp.py
 run graph_rs_only 60 $TR --master-port 29703 tests/gpu_checks/check_fused_graph.py --pattern rs,rs --replays 40
 run graph_ag_only 60 $TR --master-port 29704 tests/gpu_checks/check_fused_graph.py --pattern ag,ag --replays 40
