@@ -295,7 +295,12 @@ struct RsMaps {
   CUtensorMap m[MAX_TP];   // one store map per destination rank: its staging buffer [tp * rows_per_rank, N]
 };
 
-struct RsGate {
+// EXP = false: the validated default protocol (arrival counters cleared in front of the kernel, 2-D TMA stores into the
+// row-major staging slab).  EXP = true: the experimental switches (self-resetting counters, arrival flags, blocked slab
+// layout) are compiled in and selected at run time; keeping them out of the default instantiation keeps its code
+// generation identical to the measured kernel.
+template <bool EXP>
+struct RsGateT {
   RsArgs a;
   const CUtensorMap* maps;
   __device__ __forceinline__ void wait_m(int) const {}
@@ -317,6 +322,7 @@ struct RsGate {
     return a.rank * a.rows_per_rank + (m_blk - d * bpr) * 128;
   }
   __device__ __forceinline__ uint8_t* peer_chunk(int m_blk, int cn) const {
+    if constexpr (!EXP) return nullptr;
     if (!a.blocked) return nullptr;
     const int bpr = a.rows_per_rank / 128;
     const int d = m_blk / bpr;
@@ -326,17 +332,18 @@ struct RsGate {
   __device__ __forceinline__ void tile_done(int m_blk, int n_blk) const {
     const int bpr = a.rows_per_rank / 128;
     const int d = m_blk / bpr;
-    if (a.aflag_peer[0] != nullptr)
+    if (EXP && a.aflag_peer[0] != nullptr)
       st_release_sys(a.aflag_peer[d] + ((size_t)(m_blk - d * bpr) * a.tp + a.rank) * a.num_n_blocks + n_blk, a.epoch);
     else
       red_add_release_sys(a.counter_peer[d] + (m_blk - d * bpr), 1u);
   }
 };
 
-template <bool B_MN>
+template <bool B_MN, bool EXP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ RsMaps maps, const Params p, const RsArgs rs_in) {
+  using RsGate = RsGateT<EXP>;
   extern __shared__ uint8_t smem_raw[];
   RsArgs rs = rs_in;
   if (rs.epoch_ptr != nullptr) rs.epoch = ld_acquire_gpu(rs.epoch_ptr);
@@ -352,7 +359,7 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t target = (uint32_t)(rs.tp * rs.num_n_blocks);
   for (int item = blockIdx.x; item < bpr * n_chunks; item += gridDim.x) {
     const int rb = item / n_chunks, nc = item - rb * n_chunks;
-    if (rs.aflag_local != nullptr) {
+    if (EXP && rs.aflag_local != nullptr) {
       static_assert(BLOCK_N == 256, "one reduce chunk == one n-tile");
       // the tp partial tiles (rb, nc): one lane per source rank
       if ((int)threadIdx.x < rs.tp)
@@ -375,7 +382,7 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
         for (int sl = 0; sl < MAX_TP; ++sl)
           if (ok && sl < rs.tp) {
-            if (rs.blocked) {
+            if (EXP && rs.blocked) {
               const int unit = u & 31;                              // 16-byte unit within the 256 columns of this item
               const size_t blk = ((size_t)sl * bpr + rb) * (size_t)(rs.N / 64) + (size_t)(nc * 4 + (unit >> 3));
               const uint8_t* src = reinterpret_cast<const uint8_t*>(rs.stage_local) + blk * 16384 + r * 128 +
@@ -413,7 +420,7 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
     __syncthreads();
-    if (rs.self_reset && threadIdx.x == 0) {
+    if (EXP && rs.self_reset && threadIdx.x == 0) {
       // counter_local[512 + rb] counts the reducers that are done with row-block rb; the last one re-arms both counters.
       // Safe: arrivals of the next call that uses this parity are only sent after my next handshake, i.e. after this
       // kernel has completed.
@@ -648,7 +655,12 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
     set_smem(kern);
     kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, maps, p, rs);
   };
-  if (b_kmajor) run(gemm_rs_kernel<false>); else run(gemm_rs_kernel<true>);
+  const bool experimental = rs.self_reset || rs.blocked || arrive_flags;
+  if (experimental) {
+    if (b_kmajor) run(gemm_rs_kernel<false, true>); else run(gemm_rs_kernel<true, true>);
+  } else {
+    if (b_kmajor) run(gemm_rs_kernel<false, false>); else run(gemm_rs_kernel<true, false>);
+  }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
