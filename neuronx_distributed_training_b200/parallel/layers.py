@@ -155,7 +155,19 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         use_fused = can_fuse and fused.prefer_ag_gemm(x2d.shape[0], x2d.shape[1], weight.shape[0])
         kept = None
         keep = _KEEP_GATHERED["on"] and weight.requires_grad
-        if sequence_parallel and tp > 1:
+        # fp8 linears (model.fusions.fp8_gemm): quantise the LOCAL rows, all-gather e4m3 bytes + one fp32 scale per row
+        # (half the NVLink traffic of the bf16 gather, and no rank re-quantises rows it does not own), then the fp8 GEMM.
+        # Per-row scales make this bit-identical to gather-then-quantise.  The bf16 fused kernels stand aside.
+        fp8_gather = ops.fp8.enabled() and sequence_parallel and tp > 1 and x2d.dtype in (torch.bfloat16, torch.float32) \
+            and os.environ.get("NXDT_FP8_GATHER", "1") != "0"
+        if fp8_gather:
+            xq, xs = ops.fp8.quantize_rows(x2d.contiguous())
+            total_q = mp.all_gather_dim0(xq, group)
+            total_s = mp.all_gather_dim0(xs, group)
+            wq, ws = ops.fp8._cached(weight, "rows")
+            y2d = ops.fp8.gemm(total_q, total_s, wq, ws, out_dtype=x2d.dtype)
+            out_shape = (x.shape[0] * tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
+        elif sequence_parallel and tp > 1:
             if use_fused:
                 if keep:
                     # the gathered view lives in the double-buffered symmetric workspace: copy it out

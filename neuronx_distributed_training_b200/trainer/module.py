@@ -137,6 +137,10 @@ class BaseModelModule:
             return 0
         if ops.get_backend() == "torch" or self.use_mb_overlap:      # library baseline / two-stream mode: NCCL TP path
             return 0
+        if ops.fp8.enabled() and want == "auto":
+            # fp8 linears: e4m3 GEMMs + e4m3 all-gathers over NCCL (the fused kernels are bf16)
+            log.info("fp8_gemm: tensor-parallel collectives stay on NCCL (activations are gathered as e4m3 bytes)")
+            return 0
         if self.use_cuda_graph and want == "auto" and os.environ.get("NXDT_CUDA_GRAPH_WITH_FUSED_TP", "0") != "1":
             log.info("cuda_graph requested: tensor-parallel collectives stay on NCCL (graph replay of the fused kernels is "
                      "not validated yet, docs/ROUND2_PLAN.md)")

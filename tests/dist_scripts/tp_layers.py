@@ -107,4 +107,28 @@ r.backward()
 check("flce loss", ls / n, r)
 check("flce dh", h1.grad, h2.grad)
 check("flce dw", wl.grad, shard_master_weight(w2_.grad, 0, tp, tpr))
+
+# ---- fp8 linears: quantise-then-gather (e4m3 bytes + row scales over the wire) == gather-then-quantise, bit for bit ----
+from neuronx_distributed_training_b200 import ops
+ops.fp8.set_enabled(True)
+try:
+    col = ColumnParallelLinear(H, I, bias=False, stride=2, sequence_parallel_enabled=True)
+    with torch.no_grad():
+        col.weight.copy_(shard_master_weight(w1, 0, tp, tpr, stride=2))
+    outs = {}
+    for mode in ("1", "0"):
+        os.environ["NXDT_FP8_GATHER"] = mode
+        x_in = x_full.chunk(tp, 0)[tpr].clone().requires_grad_(True)
+        y = col(x_in)
+        y.backward(torch.ones_like(y))
+        outs[mode] = (y.detach().clone(), x_in.grad.clone(), col.weight.grad.clone())
+        col.weight.grad = None
+    for a, b, name in zip(outs["1"], outs["0"], ("y", "dx", "dw")):
+        assert torch.equal(a, b), f"fp8 gather mode changed {name}"
+    ref = x_full.reshape(-1, H) @ shard_master_weight(w1, 0, tp, tpr, stride=2).t()
+    rel = ((outs["1"][0].reshape(-1, ref.shape[1]) - ref).norm() / ref.norm()).item()
+    assert rel < 0.08, rel                      # e4m3 with per-row scales
+finally:
+    ops.fp8.set_enabled(False)
+    os.environ.pop("NXDT_FP8_GATHER", None)
 finish()
