@@ -294,6 +294,7 @@ def main():
                        "cuda_graph": getattr(module, "_mb_graph", None) is not None,
                        "microbatch_overlap": bool(getattr(module, "use_mb_overlap", False)),
                        "fused_tp_layers": int(getattr(module, "fused_tp_layers", 0)),
+                       "fused_zero1": bool(getattr(module, "fused_zero1", False)),
                        "keep_gathered_input": bool(_keep_gathered())},
             "clocks": clocks, "gpu_launches": launches,
         }

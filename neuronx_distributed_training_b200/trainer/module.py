@@ -202,9 +202,40 @@ class BaseModelModule:
             if self.dims.pp == 1 and isinstance(self.optimizer, DistributedOptimizer):
                 if self.optimizer.enable_grad_reduce_overlap(float(self.cfg.get("bucket_size_collectives", 256) or 256)):
                     log.info("data-parallel gradient reduction overlaps backward (%d buckets)", len(self.optimizer._buckets))
+        self._maybe_enable_fused_zero1(ocfg)
         sched = ocfg.get("sched", None)
         self.lr_scheduler = prepare_lr_scheduler(self.optimizer, sched, max_steps) if sched is not None else None
         return self.optimizer, self.lr_scheduler
+
+    def _maybe_enable_fused_zero1(self, ocfg) -> bool:
+        """ZeRO-1 step as two peer-memory kernels (gradient reduce-scatter by peer pulls -> AdamW on the shard -> parameter
+        all-gather by peer pushes, ``optim/fused_zero1.py``) instead of reduce_scatter + per-segment Adam + all_gather.
+        ``model.optim.fused_zero1: auto | true | false`` (``NXDT_FUSED_ZERO1=0|1``); needs AdamW with fp32 master weights and
+        state, a data-parallel group of 2..8 GPUs with peer access (one node), and no overlapped bucket reduction."""
+        want = ocfg.get("fused_zero1", "auto")
+        env = os.environ.get("NXDT_FUSED_ZERO1")
+        if env is not None:
+            want = env != "0"
+        if isinstance(want, str):
+            want = {"true": True, "false": False}.get(want.lower(), "auto")
+        self.fused_zero1 = False
+        opt = self.optimizer
+        if want is False or self.device.type != "cuda" or not isinstance(opt, DistributedOptimizer) or ops.get_backend() == "torch":
+            return False
+        if not opt.zero1 or not (2 <= opt.dp_size <= 8) or getattr(opt, "_buckets", None):
+            return False
+        if opt.master is None or opt.algorithm != "adamw" or opt.exp_avg.dtype != torch.float32:
+            return False
+        try:
+            from ..optim.fused_zero1 import enable_fused_zero1
+            self.fused_zero1 = bool(enable_fused_zero1(opt))
+            if self.fused_zero1 and ps.get_rank() == 0:
+                log.info("ZeRO-1 step runs as fused peer-memory kernels over the data-parallel group (%d GPUs)", opt.dp_size)
+        except Exception as e:  # noqa: BLE001 - e.g. the DP group spans nodes (no peer mapping)
+            if want is True:
+                raise
+            log.warning("fused ZeRO-1 step not enabled (%s); using NCCL reduce-scatter / all-gather", e)
+        return self.fused_zero1
 
     # ---- step ----------------------------------------------------------------------------------------
     def autocast_ctx(self):
