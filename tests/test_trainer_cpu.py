@@ -210,3 +210,68 @@ def test_save_logits_keeps_the_vocab_parallel_logits(tmp_path, monkeypatch):
     loss = mod.training_step({"input_ids": ids, "labels": ids.clone()})
     assert mod.last_logits.shape == (1, 32, 128) and float(loss) == float(loss)      # latest micro-batch, [B, S, V]
     assert torch.equal(torch.load(tmp_path / "dump" / "logits_rank0.pt"), mod.last_logits.cpu())
+
+
+def test_fused_kernel_attachment_policy(tmp_path, monkeypatch):
+    """Decision logic of BaseModelModule._maybe_enable_fused_tp / _maybe_enable_fused_zero1 with the GPU-only pieces stubbed:
+    auto / true / false, environment overrides, and the modes that keep tensor parallelism on NCCL (library baseline,
+    micro-batch overlap, CUDA graphs, fp8)."""
+    from neuronx_distributed_training_b200 import ops
+    from neuronx_distributed_training_b200.parallel import fused as fused_mod
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    cfg = _cfg(str(tmp_path / "run"))
+    process_config(cfg, 1)
+    mod = HFLlamaModule(cfg, None)
+    mod.setup()
+    assert mod.fused_tp_layers == 0                     # CPU, TP 1: nothing to attach
+    calls = []
+    monkeypatch.setattr(fused_mod, "enable_fused_tp", lambda model, seq_len=None, micro_batch=1: calls.append((seq_len, micro_batch)) or 7)
+    # pretend to be a CUDA rank of a TP=2 sequence-parallel job
+    mod.device = torch.device("cuda", 0)
+    mod.dims.tp, mod.sequence_parallel = 2, True
+    assert mod._maybe_enable_fused_tp() == 7 and calls[-1] == (32, 1)
+    monkeypatch.setenv("NXDT_FUSED_TP", "0")
+    assert mod._maybe_enable_fused_tp() == 0
+    monkeypatch.delenv("NXDT_FUSED_TP")
+    n = len(calls)
+    for attr, val in (("use_mb_overlap", True), ("use_cuda_graph", True)):
+        monkeypatch.setattr(mod, attr, val)
+        assert mod._maybe_enable_fused_tp() == 0 and len(calls) == n
+        monkeypatch.setattr(mod, attr, False)
+    ops.set_backend("torch")
+    try:
+        assert mod._maybe_enable_fused_tp() == 0 and len(calls) == n
+    finally:
+        ops.set_backend("auto")
+    ops.fp8.set_enabled(True)
+    try:
+        assert mod._maybe_enable_fused_tp() == 0 and len(calls) == n
+    finally:
+        ops.fp8.set_enabled(False)
+
+    def boom(*a, **k):
+        raise RuntimeError("no peer access")
+    monkeypatch.setattr(fused_mod, "enable_fused_tp", boom)
+    assert mod._maybe_enable_fused_tp() == 0            # auto: quiet fallback to NCCL
+    cfg.model.fusions["fused_tp"] = True
+    with pytest.raises(RuntimeError):
+        mod._maybe_enable_fused_tp()                    # explicit request: the error is fatal
+    cfg.model.fusions["fused_tp"] = False
+    assert mod._maybe_enable_fused_tp() == 0
+
+    # ZeRO-1: nothing on a single data-parallel rank; stubbed attach when the optimizer is sharded over 2..8 GPUs
+    mod.device = torch.device("cpu")
+    mod.configure_optimizers(10)
+    assert mod.fused_zero1 is False
+    from neuronx_distributed_training_b200.optim import fused_zero1 as fz
+    attached = []
+    monkeypatch.setattr(fz, "enable_fused_zero1", lambda opt: attached.append(opt) or True)
+    mod.device = torch.device("cuda", 0)
+    opt = mod.optimizer
+    monkeypatch.setattr(opt, "zero1", True); monkeypatch.setattr(opt, "dp_size", 4)
+    assert opt.master is None                           # fp32 run: no master copies -> not eligible
+    assert mod._maybe_enable_fused_zero1(cfg.model.optim) is False and not attached
+    monkeypatch.setattr(opt, "master", torch.zeros(1))
+    assert mod._maybe_enable_fused_zero1(cfg.model.optim) is True and attached == [opt]
+    monkeypatch.setenv("NXDT_FUSED_ZERO1", "0")
+    assert mod._maybe_enable_fused_zero1(cfg.model.optim) is False
