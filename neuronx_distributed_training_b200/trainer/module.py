@@ -111,6 +111,13 @@ class BaseModelModule:
     # ---- lifecycle ---------------------------------------------------------------------------------
     def setup(self, stage: str = "fit"):
         fus = self.config.get("fusions", Config({})) if "fusions" in self.config else Config({})
+        kernels = str(self.cfg.get("kernels", "fused") or "fused").lower()
+        if kernels not in ("fused", "baseline"):
+            raise ValueError(f"kernels: expected 'fused' or 'baseline', got {kernels!r}")
+        if kernels == "baseline":
+            # top-level `kernels: baseline`: every hot op on the library path (NCCL + cuBLAS + SDPA + unfused torch ops) --
+            # the A/B arm against which the sm_100a kernels are measured (same as NXDT_OPS_BACKEND=torch)
+            ops.set_backend("torch")
         if "fp8_gemm" in fus or str(self.cfg.get("precision", Config({})).get("gemm_dtype", "")).lower() in ("fp8", "e4m3"):
             # linear-layer GEMMs in e4m3 with row / column block scales (ops/fp8.py); LM head, attention, norms stay bf16
             ops.fp8.set_enabled(bool(fus.get("fp8_gemm", True)))

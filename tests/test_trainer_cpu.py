@@ -275,3 +275,20 @@ def test_fused_kernel_attachment_policy(tmp_path, monkeypatch):
     assert mod._maybe_enable_fused_zero1(cfg.model.optim) is True and attached == [opt]
     monkeypatch.setenv("NXDT_FUSED_ZERO1", "0")
     assert mod._maybe_enable_fused_zero1(cfg.model.optim) is False
+
+
+def test_kernels_switch_selects_the_library_path(tmp_path):
+    from neuronx_distributed_training_b200 import ops
+    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
+    cfg = _cfg(str(tmp_path / "run"))
+    cfg["kernels"] = "baseline"
+    process_config(cfg, 1)
+    assert ops.get_backend() != "torch"
+    try:
+        HFLlamaModule(cfg, None).setup()
+        assert ops.get_backend() == "torch"
+    finally:
+        ops.set_backend("auto")
+    cfg["kernels"] = "fast"
+    with pytest.raises(ValueError):
+        HFLlamaModule(cfg, None).setup()
