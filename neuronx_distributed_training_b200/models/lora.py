@@ -174,6 +174,14 @@ def inject_lora(model: nn.Module, cfg: LoraConfig) -> List[str]:
                 p.requires_grad_(True)
     if not wrapped:
         raise ValueError(f"LoRA target_modules {sorted(targets)} matched nothing")
+    if cfg.lora_verbose and ps.get_rank() == 0:
+        import logging
+        log = logging.getLogger("nxdt")
+        n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        n_all = sum(p.numel() for p in model.parameters())
+        log.info("LoRA: rank %d, alpha %g, dropout %g, bias %s; wrapped %d modules (%s%s); trainable parameters on this "
+                 "rank %d of %d (%.3f %%)", cfg.lora_rank, cfg.lora_alpha, cfg.lora_dropout, cfg.lora_bias, len(wrapped),
+                 ", ".join(wrapped[:4]), ", ..." if len(wrapped) > 4 else "", n_train, n_all, 100.0 * n_train / max(n_all, 1))
     return wrapped
 
 
