@@ -6,13 +6,16 @@ mkdir -p gpurun_out
 run() {  # name, timeout, command...
   name=$1; t=$2; shift 2
   timeout "$t" "$@" > gpurun_out/r2_$name.log 2>&1
-  echo "== $name exit $? : $(grep -E '_OK|rel err|TFLOP|Error|error|assert' gpurun_out/r2_$name.log | tail -4 | cut -c1-220 | tr '\n' '|')"
+  echo "== $name exit $? : $(grep -E '_OK|rel err|TFLOP|TB/s|passed|failed|Error|error|assert' gpurun_out/r2_$name.log | tail -4 | cut -c1-220 | tr '\n' '|')"
 }
 run pytest_gpu 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu
 run flash_bwd 120 python tests/gpu_checks/check_flash_bwd.py
 run flash_fwd 120 python tests/gpu_checks/check_flash.py
 NXDT_FLASH_SPLIT=2 run flash_fwd_split2 120 python tests/gpu_checks/check_flash.py      # eight-softmax-warp variant
 run fp8 180 python tests/gpu_checks/check_fp8.py
+run adam_v1 120 python tests/gpu_checks/check_adam.py
+NXDT_ADAM_V2=1 run adam_v2 120 python tests/gpu_checks/check_adam.py
+NXDT_ADAM_V2=1 run adam_v2_numerics 200 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "adamw_flat"
 run smoke 120 python -c "import __graft_entry__ as g; g.smoke()"
 NXDT_FLASH_BWD_PREVIEW=1 run bench_flash_native 200 python bench.py --steps 2 --warmup 3 --layers 8 --no-e2e
 run bench_default_8L 200 python bench.py --steps 2 --warmup 3 --layers 8 --no-e2e
