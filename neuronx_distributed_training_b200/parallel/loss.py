@@ -176,9 +176,10 @@ class _FusedLinearCrossEntropy(torch.autograd.Function):
                 if dw_acc is not None:
                     ops.gemm_wgrad(dlog, h, out=dw_acc, accumulate=True, fp8=False)
                 del dlog
-        if need_grad and tp > 1:
-            # hidden is replicated over TP here (already gathered); sum the partial d(hidden)
-            dist.all_reduce(dh, group=group)
+        # d(hidden) stays PARTIAL (this rank's vocabulary slice), exactly like the input gradient of a plain
+        # ``F.linear(hidden, w_local)``: the mapping the caller used to bring ``hidden`` into the tensor-parallel region
+        # sums it in its backward (``gather_from_sequence_parallel_region(..., to_model_parallel=True)`` reduce-scatters,
+        # ``copy_to_tensor_model_parallel_region`` all-reduces).  Reducing here as well would count it TP times.
         ctx.save_for_backward(dh, dw_acc)
         ctx.dw_is_main = dw_is_main
         ctx.weight = weight
@@ -224,7 +225,9 @@ def _get_scratch(like: torch.Tensor, tag: str, dtype):
 def fused_linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, group=None,
                                ignore_index: int = -100, chunk_tokens: int = 2048):
     """hidden [T,H] (already gathered over the sequence), weight [V/TP,H], labels [T].
-    Returns (sum of per-token losses, number of non-ignored tokens)."""
+    Returns (sum of per-token losses, number of non-ignored tokens).  With TP > 1 ``hidden`` must come out of
+    ``copy_to_tensor_model_parallel_region`` or ``gather_from_sequence_parallel_region(..., True)``: the gradient handed
+    back is the partial sum over this rank's vocabulary slice and that mapping's backward completes it."""
     group = ps.get_tensor_model_parallel_group() if group is None else group
     loss_sum, n_valid, _ = _FusedLinearCrossEntropy.apply(hidden, weight, labels, group, ignore_index,
                                                          chunk_tokens, False)

@@ -99,7 +99,8 @@ wv = torch.randn(V, H, generator=g) * 0.2
 lab = torch.randint(0, V, (T,), generator=g); lab[:2] = -100
 h1 = hid.clone().requires_grad_(True)
 wl = shard_master_weight(wv, 0, tp, tpr).clone().requires_grad_(True)
-ls, n = fused_linear_cross_entropy(h1, wl, lab, chunk_tokens=7)
+# the fused op returns the PARTIAL d(hidden) of its vocabulary slice; the region-entry mapping sums it over TP
+ls, n = fused_linear_cross_entropy(mp.copy_to_tensor_model_parallel_region(h1), wl, lab, chunk_tokens=7)
 (ls / n).backward()
 h2 = hid.clone().requires_grad_(True); w2_ = wv.clone().requires_grad_(True)
 r = F.cross_entropy(h2 @ w2_.t(), lab, ignore_index=-100)

@@ -1,0 +1,42 @@
+"""Whole Llama under tensor parallelism (with and without sequence parallelism, fused and unfused LM-head loss) against
+the single-process model: same loss and the same gradient for EVERY parameter (replicated ones summed over the ranks
+that saw different tokens, sharded ones compared with the matching slice of the reference gradient)."""
+from common import *
+from neuronx_distributed_training_b200.models.llama import LlamaConfig, LlamaForCausalLM
+from neuronx_distributed_training_b200.parallel.layers import shard_master_weight
+
+TP = int(os.environ.get("TP", "2"))
+rank, world = init(tp=TP)
+tp, tpr = ps.get_tensor_model_parallel_size(), ps.get_tensor_model_parallel_rank()
+g = torch.Generator().manual_seed(5)
+ids = torch.randint(0, 64, (2, 8 * TP), generator=g)
+base = dict(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+            num_key_value_heads=max(2, TP), torch_dtype="float32", use_flash_attention=False, use_cpu_initialization=True, fuse_qkv=False)
+runs = {}
+for sp in (False, True):
+    for fused_ce in (True, False):
+        torch.manual_seed(11)
+        m = LlamaForCausalLM(LlamaConfig(**base, sequence_parallel_enabled=sp, fused_linear_ce=fused_ce))
+        loss, _ = m(input_ids=ids, labels=ids)
+        loss.backward()
+        grads = {}
+        for n, p in m.named_parameters():
+            gr = p.grad.clone()
+            if getattr(p, "sequence_parallel_enabled", False):
+                dist.all_reduce(gr)                      # each TP rank saw S/TP of the tokens (the optimizer does this sum)
+            grads[n] = (gr, bool(getattr(p, "tensor_model_parallel", False)), getattr(p, "partition_dim", -1),
+                        getattr(p, "partition_stride", 1))
+        runs[(sp, fused_ce)] = (loss.detach().clone(), grads)
+ps.destroy_model_parallel(); ps.initialize_model_parallel(1, 1, 1)
+torch.manual_seed(11)
+ref = LlamaForCausalLM(LlamaConfig(**base))
+l1, _ = ref(input_ids=ids, labels=ids)
+l1.backward()
+rg = {n: p.grad for n, p in ref.named_parameters()}
+for key, (loss, grads) in runs.items():
+    check(f"loss {key}", loss, l1.detach(), atol=1e-5)
+    assert set(grads) == set(rg), (sorted(set(grads) ^ set(rg))[:4])
+    for n, (gr, is_tp, dim, stride) in grads.items():
+        want = shard_master_weight(rg[n], dim, tp, tpr, stride) if is_tp else rg[n]
+        check(f"grad {n} sp={key[0]} fused_ce={key[1]}", gr, want, atol=2e-5)
+finish()

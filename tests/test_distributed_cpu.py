@@ -29,6 +29,13 @@ def test_tp_sp_layers_match_dense(tp):
     run_dist("tp_layers.py", tp, {"TP": str(tp)})
 
 
+@pytest.mark.parametrize("tp", [2, 4])
+def test_tensor_parallel_model_matches_single_process_gradients(tp):
+    """Every parameter gradient of a TP(+SP) Llama equals the single-process one (caught: d(hidden) of the fused LM-head
+    loss used to be summed over the TP group twice)."""
+    run_dist("tp_model.py", tp, {"TP": str(tp)})
+
+
 def test_zero1_matches_adamw():
     run_dist("zero1.py", 2)
 
@@ -60,6 +67,10 @@ def test_ulysses_attention_context_parallel(cp):
 
 def test_checkpoint_load_reads_once_per_model_shard_and_broadcasts(tmp_path):
     run_dist("ckpt_broadcast_load.py", 2, {"WORKDIR": str(tmp_path)})
+
+
+def test_context_parallel_composes_with_tensor_parallel():
+    run_dist("cp_tp_model.py", 4)
 
 
 def test_moe_expert_parallel_matches_single_process():
