@@ -36,6 +36,10 @@ def test_tensor_parallel_model_matches_single_process_gradients(tp):
     run_dist("tp_model.py", tp, {"TP": str(tp)})
 
 
+def test_megatron_gpt_tensor_parallel_matches_single_process_gradients():
+    run_dist("megatron_tp_model.py", 2, {"TP": "2"})
+
+
 def test_zero1_matches_adamw():
     run_dist("zero1.py", 2)
 
