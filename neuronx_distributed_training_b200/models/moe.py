@@ -234,8 +234,13 @@ class MoE(nn.Module):
 
     def forward(self, hidden: torch.Tensor):
         tp_group = ps.get_tensor_model_parallel_group()
+        tp = ps.group_size(tp_group)
+        # Entering the tensor-parallel region: the experts are sharded on the FFN dimension, so every rank produces a
+        # PARTIAL d(hidden); the entry mapping sums it in backward (reduce-scatter with SP, all-reduce without).
         if self.sp:
             hidden = mp.gather_from_sequence_parallel_region(hidden, True, tp_group)
+        elif tp > 1:
+            hidden = mp.copy_to_tensor_model_parallel_region(hidden, tp_group)
         shape = hidden.shape
         x = hidden.reshape(-1, shape[-1])
         T = x.shape[0]
@@ -249,10 +254,16 @@ class MoE(nn.Module):
             x = _A2A.apply(x.index_select(0, perm), counts, counts, self._shuffle_group)
             unshuffle = (perm, counts)
         E, k = self.router.num_experts, self.router.top_k
-        logits, aff, idx = self.router(x)
+        # The router is replicated over the TP group (same tokens, same weights on every rank): its input gradient is
+        # complete on each rank and must not be summed TP times by the entry mapping -> pre-scale it by 1/TP.
+        logits, aff, idx = self.router(mp.scale_gradient(x, 1.0 / tp) if tp > 1 else x)
         w = aff.gather(-1, idx)                                   # [T,k]
         if self.normalize and k > 1:
             w = w / w.sum(-1, keepdim=True).clamp_min(1e-9)
+        if tp > 1:
+            # the affinities weight PARTIAL expert outputs (one FFN slice per rank): their gradient <d(out), y_partial> is
+            # completed over the TP group, which also makes the router-weight gradient identical on every rank
+            w = mp.copy_to_tensor_model_parallel_region(w, tp_group)
         flat_e = idx.reshape(-1)                                  # [T*k]
         flat_t = torch.arange(T, device=x.device).repeat_interleave(k)
         flat_w = w.reshape(-1)

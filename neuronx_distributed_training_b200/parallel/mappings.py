@@ -166,6 +166,24 @@ class _ReduceScatterSeq(torch.autograd.Function):
         return all_gather_dim0(g, ctx.group), None, None
 
 
+class _ScaleGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.scale, None
+
+
+def scale_gradient(x, scale: float):
+    """Identity in forward, ``grad * scale`` in backward.  Used where a computation inside a tensor-parallel region is
+    REPLICATED on every rank (e.g. the MoE router): its input gradient is identical on all ranks, and the region-entry
+    mapping (all-reduce / reduce-scatter in backward) would otherwise count it TP times."""
+    return x if scale == 1.0 else _ScaleGrad.apply(x, scale)
+
+
 def copy_to_tensor_model_parallel_region(x, group=None):
     return _CopyToTP.apply(x, _tp_group() if group is None else group)
 
