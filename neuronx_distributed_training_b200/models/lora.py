@@ -77,7 +77,8 @@ class LoraAdapter(nn.Module):
         nn.init.kaiming_uniform_(self.lora_A, a=math.sqrt(5))
         tp = ps.group_size(self.group)
         if self.kind == "column":
-            set_tensor_model_parallel_attributes(self.lora_B, True, 0, 1)
+            # B's rows follow the parent's output layout (e.g. gate||up interleaved per rank: stride 2)
+            set_tensor_model_parallel_attributes(self.lora_B, True, 0, int(getattr(w, "partition_stride", 1) or 1))
             self.lora_A.sequence_parallel_enabled = tp > 1        # replicated, partial grads => TP all-reduce
         else:
             set_tensor_model_parallel_attributes(self.lora_A, True, 1, 1)

@@ -44,6 +44,10 @@ def test_mixtral_tensor_parallel_matches_single_process_gradients():
     run_dist("mixtral_tp_model.py", 2, {"TP": "2"})
 
 
+def test_lora_adapters_under_tensor_parallelism_match_single_process():
+    run_dist("lora_tp_model.py", 2, {"TP": "2"})
+
+
 def test_zero1_matches_adamw():
     run_dist("zero1.py", 2)
 
