@@ -91,6 +91,14 @@ loss.sum().backward(); ref.sum().backward()
 check("pce grad", ll.grad, logits_full.grad.chunk(tp, -1)[tpr])
 lp = from_parallel_logits_to_logprobs(ll.detach(), labels)
 check("logprobs", lp, -ref.detach())
+# ... and its backward (the DPO / ORPO losses differentiate through the per-token log-probabilities)
+ll2 = logits_full.detach().chunk(tp, -1)[tpr].clone().requires_grad_(True)
+wts = torch.randn(B, S, generator=g)
+(from_parallel_logits_to_logprobs(ll2, labels) * wts).sum().backward()
+lf = logits_full.detach().clone().requires_grad_(True)
+lpr = -F.cross_entropy(lf.reshape(-1, V), labels.reshape(-1), reduction="none", ignore_index=-100).view(B, S)
+(lpr * wts).sum().backward()
+check("logprobs grad", ll2.grad, lf.grad.chunk(tp, -1)[tpr])
 
 # ---- fused linear + CE ------------------------------------------------------------------------------------------
 T = 24

@@ -48,6 +48,10 @@ def test_lora_adapters_under_tensor_parallelism_match_single_process():
     run_dist("lora_tp_model.py", 2, {"TP": "2"})
 
 
+def test_task_module_step_under_tensor_parallelism_matches_single_process():
+    run_dist("tp_trainer_step.py", 2, {"TP": "2"})
+
+
 def test_zero1_matches_adamw():
     run_dist("zero1.py", 2)
 
