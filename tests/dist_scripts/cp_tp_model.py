@@ -11,8 +11,9 @@ base = dict(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_laye
             num_key_value_heads=2, torch_dtype="float32", use_flash_attention=False, use_cpu_initialization=True)
 results = {}
 rank, world = init(tp=TP, cp=CP)
-for mode in ("ring", "ulysses"):
-    cfg = LlamaConfig(**base, use_ring_attention=(mode == "ring"), use_ulysses_attention=(mode == "ulysses"))
+for mode, sp in (("ring", False), ("ulysses", False), ("ring", True), ("ulysses", True)):
+    cfg = LlamaConfig(**base, use_ring_attention=(mode == "ring"), use_ulysses_attention=(mode == "ulysses"),
+                      sequence_parallel_enabled=sp)
     torch.manual_seed(11)
     m = LlamaForCausalLM(cfg)
     batch = get_batch_on_this_context_parallel_rank({"input_ids": ids, "labels": ids.clone()})
@@ -22,8 +23,9 @@ for mode in ("ring", "ulysses"):
     dist.all_reduce(tot, group=ps.get_context_model_parallel_group())
     (loss * n_loc / tot[1]).backward()
     gn = m.model.norm.weight.grad.clone()
-    dist.all_reduce(gn)                       # sum over CP (different tokens) and TP (replicas): divide the replicas out
-    results[mode] = (tot[0] / tot[1], gn / TP)
+    dist.all_reduce(gn)                       # sum over CP (different tokens) and TP
+    # without SP the TP ranks hold replicas of the norm gradient (divide them out); with SP each holds its tokens' share
+    results[(mode, sp)] = (tot[0] / tot[1], gn if sp else gn / TP)
 ps.destroy_model_parallel(); ps.initialize_model_parallel(1, 1, 1)
 torch.manual_seed(11)
 m1 = LlamaForCausalLM(LlamaConfig(**base))
