@@ -27,7 +27,35 @@ for sp in (False, True):
             grads[n] = (gr, bool(getattr(p, "tensor_model_parallel", False)), getattr(p, "partition_dim", -1),
                         getattr(p, "partition_stride", 1))
         runs[(sp, fused_ce)] = (loss.detach().clone(), grads)
+# DPO path: sequence log-probabilities of chosen || rejected through the vocab-parallel logits, and a DPO-shaped loss on them
+from neuronx_distributed_training_b200.trainer.dpo import sequence_logps, dpo_loss
+lab = ids.clone(); lab[:, :3] = -100
+cat = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": lab}
+def dpo_like(model):
+    c, r = sequence_logps(model, cat)
+    loss, _, _ = dpo_loss(c, r, torch.zeros_like(c) - 1.0, torch.zeros_like(r) - 2.0, beta=0.3)
+    return c.detach().clone(), r.detach().clone(), loss
+dpo_runs = {}
+for sp in (False, True):
+    torch.manual_seed(11)
+    m = LlamaForCausalLM(LlamaConfig(**base, sequence_parallel_enabled=sp))
+    c, r, loss = dpo_like(m)
+    loss.backward()
+    gn = m.model.norm.weight.grad.clone()
+    if sp:
+        dist.all_reduce(gn)
+    dpo_runs[sp] = (c, r, loss.detach().clone(), gn)
 ps.destroy_model_parallel(); ps.initialize_model_parallel(1, 1, 1)
+torch.manual_seed(11)
+ref = LlamaForCausalLM(LlamaConfig(**base))
+c1, r1, ld = dpo_like(ref)
+ld.backward()
+for sp, (c, r, loss, gn) in dpo_runs.items():
+    check(f"dpo chosen logps sp={sp}", c, c1, atol=2e-5)
+    check(f"dpo rejected logps sp={sp}", r, r1, atol=2e-5)
+    check(f"dpo loss sp={sp}", loss, ld.detach(), atol=1e-5)
+    check(f"dpo final-norm grad sp={sp}", gn, ref.model.norm.weight.grad, atol=2e-5)
+ref.zero_grad()
 torch.manual_seed(11)
 ref = LlamaForCausalLM(LlamaConfig(**base))
 l1, _ = ref(input_ids=ids, labels=ids)
