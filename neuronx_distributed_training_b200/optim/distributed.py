@@ -310,6 +310,13 @@ class DistributedOptimizer:
             if s.tp_dup and tp_rank != 0:
                 continue
             total = total + ops.sq_norm(gshard[lo:hi])
+        # KV-head replicas (TP larger than the number of KV heads): elements another rank already counts
+        for o, p in zip(self.offsets, self.params):
+            dup = getattr(p, "norm_duplicate_range", None)
+            if dup is not None:
+                lo, hi = max(o + dup[0], self.shard_lo), min(o + dup[1], self.shard_hi)
+                if lo < hi:
+                    total = total - ops.sq_norm(gshard[lo - self.shard_lo:hi - self.shard_lo].contiguous())
         if dist.is_initialized():
             if self.zero1:
                 dist.all_reduce(total, group=self.dp_group)

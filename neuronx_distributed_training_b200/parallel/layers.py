@@ -527,6 +527,14 @@ class GQAQKVColumnParallelLinear(nn.Module):
             # their gradients get one more reduction after backward: not eligible for an early data-parallel reduce
             for p in ((self.weight_qkv,) if self.fuse_qkv else (self.weight_k, self.weight_v)):
                 p.kv_replica_sync = True
+            # After the sync every replica holds the same K / V gradient: count those elements once in global norms.
+            # ``norm_duplicate_range`` = flat [lo, hi) of this parameter that duplicates what another rank already counts
+            if dist.get_rank(self._kv_replica_group) != 0:
+                if self.fuse_qkv:
+                    self.weight_qkv.norm_duplicate_range = (self.q_local * self.input_size, self.weight_qkv.numel())
+                else:
+                    for p in (self.weight_k, self.weight_v):
+                        p.norm_duplicate_range = (0, p.numel())
 
     def _sync_replica_grads(self, *params):
         """Sum KV gradients over the ranks that hold replicas of the same logical head."""

@@ -233,6 +233,8 @@ class BaseModelModule:
             return False
         if opt.master is None or opt.algorithm != "adamw" or opt.exp_avg.dtype != torch.float32:
             return False
+        if any(getattr(p, "norm_duplicate_range", None) is not None for p in opt.params):
+            return False            # KV-head replicas: the fused kernels' norm mask has no per-row exclusion
         try:
             from ..optim.fused_zero1 import enable_fused_zero1
             self.fused_zero1 = bool(enable_fused_zero1(opt))

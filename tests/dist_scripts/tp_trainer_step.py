@@ -12,7 +12,8 @@ def cfg(tp):
     return process_config(from_dict({
         "name": "hf_llama", "model_source": "hf", "seed": 5,
         "trainer": {"devices": tp, "num_nodes": 1, "max_steps": 10, "gradient_clip_val": 0.5},
-        "distributed_strategy": {"tensor_model_parallel_size": tp, "zero1": True, "sequence_parallel": tp > 1},
+        "distributed_strategy": {"tensor_model_parallel_size": tp, "zero1": True, "sequence_parallel": tp > 1,
+                                 "kv_replicator": max(1, tp // 2)},      # TP 4 with 2 KV heads: every KV head lives on two ranks
         "data": {"micro_batch_size": 1, "global_batch_size": 2},
         "model": {"model_config": "llama_125m", "encoder_seq_length": 16, "num_layers": 2, "hidden_size": 32, "intermediate_size": 64,
                   "num_attention_heads": 4, "num_kv_heads": 2, "vocab_size": 64, "fusions": {"flash_attention": False},

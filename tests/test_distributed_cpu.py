@@ -48,8 +48,10 @@ def test_lora_adapters_under_tensor_parallelism_match_single_process():
     run_dist("lora_tp_model.py", 2, {"TP": "2"})
 
 
-def test_task_module_step_under_tensor_parallelism_matches_single_process():
-    run_dist("tp_trainer_step.py", 2, {"TP": "2"})
+@pytest.mark.parametrize("tp", [2, 4])
+def test_task_module_step_under_tensor_parallelism_matches_single_process(tp):
+    """tp=4 with 2 KV heads also exercises KV-head replication (kv_replicator=2) and the replica-gradient sync."""
+    run_dist("tp_trainer_step.py", tp, {"TP": str(tp)})
 
 
 def test_zero1_matches_adamw():
