@@ -455,6 +455,9 @@ class BaseModelModule:
             if param_is_tp_duplicate(p) and tp_rank != 0:
                 continue
             total += p.detach().float().pow(2).sum()
+            dup = getattr(p, "norm_duplicate_range", None)          # KV-head replica rows another rank already counts
+            if dup is not None:
+                total -= p.detach().reshape(-1)[dup[0]:dup[1]].float().pow(2).sum()
         for grp in (ps.get_tensor_model_parallel_group(), ps.get_pipeline_model_parallel_group()):
             if ps.group_size(grp) > 1:
                 dist.all_reduce(total, group=grp)

@@ -29,7 +29,7 @@ mod = HFLlamaModule(cfg(TP), None); mod.setup(); mod.configure_optimizers(10)
 ours = []
 for ids in batches:
     loss = mod.training_step({"input_ids": ids, "labels": ids.clone()})
-    ours.append((loss.detach().clone(), mod.optimizer.grad_norm.detach().clone()))
+    ours.append((loss.detach().clone(), mod.optimizer.grad_norm.detach().clone(), mod.parameter_norm().detach().clone()))
 # single-process reference on every rank (no process groups involved)
 ps.destroy_model_parallel()
 _saved = dist.is_initialized
@@ -37,10 +37,11 @@ dist.is_initialized = lambda: False
 try:
     ps.initialize_model_parallel(1, 1, 1)
     ref = HFLlamaModule(cfg(1), None); ref.setup(); ref.configure_optimizers(10)
-    for (l, gn), ids in zip(ours, batches):
+    for (l, gn, pn), ids in zip(ours, batches):
         lr_ = ref.training_step({"input_ids": ids, "labels": ids.clone()})
         check("loss", l, lr_, atol=2e-5)
         check("global grad norm", gn, ref.optimizer.grad_norm, atol=1e-4)
+        check("parameter norm", pn, ref.parameter_norm(), atol=1e-4)
 finally:
     dist.is_initialized = _saved
 finish()
