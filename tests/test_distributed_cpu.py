@@ -95,6 +95,11 @@ def test_moe_expert_parallel_matches_single_process():
     run_dist("moe_ep.py", 2, {"EP": "2"})
 
 
+def test_moe_expert_parallel_with_tensor_parallel_matches_single_process():
+    """EP=2 x TP=2 (+SP) on 4 ranks: all-to-all dispatch of tokens to FFN-sharded experts, one optimizer step."""
+    run_dist("moe_ep.py", 4, {"EP": "2", "TP": "2"})
+
+
 def test_kill_and_resume_fault_injection(tmp_path):
     """SURVEY section 4 fault-injection tier: hard-kill a rank mid-run, relaunch, identical end state."""
     env = {"WORKDIR": str(tmp_path)}
