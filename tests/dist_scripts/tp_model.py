@@ -61,6 +61,21 @@ ref = LlamaForCausalLM(LlamaConfig(**base))
 l1, _ = ref(input_ids=ids, labels=ids)
 l1.backward()
 rg = {n: p.grad for n, p in ref.named_parameters()}
+# tied input / output embeddings: one vocabulary-sharded tensor receives the gradient of both uses
+ps.destroy_model_parallel(); ps.initialize_model_parallel(TP, 1, 1)
+torch.manual_seed(11)
+mt = LlamaForCausalLM(LlamaConfig(**base, sequence_parallel_enabled=True, tie_word_embeddings=True))
+lt, _ = mt(input_ids=ids, labels=ids)
+lt.backward()
+assert mt.lm_head.weight is mt.model.embed_tokens.weight
+gt = mt.model.embed_tokens.weight.grad.clone()
+ps.destroy_model_parallel(); ps.initialize_model_parallel(1, 1, 1)
+torch.manual_seed(11)
+rt = LlamaForCausalLM(LlamaConfig(**base, tie_word_embeddings=True))
+lrt, _ = rt(input_ids=ids, labels=ids)
+lrt.backward()
+check("tied loss", lt.detach(), lrt.detach(), atol=1e-5)
+check("tied embedding grad", gt, shard_master_weight(rt.model.embed_tokens.weight.grad, 0, tp, tpr), atol=2e-5)
 for key, (loss, grads) in runs.items():
     check(f"loss {key}", loss, l1.detach(), atol=1e-5)
     assert set(grads) == set(rg), (sorted(set(grads) ^ set(rg))[:4])
