@@ -48,10 +48,11 @@ def test_lora_adapters_under_tensor_parallelism_match_single_process():
     run_dist("lora_tp_model.py", 2, {"TP": "2"})
 
 
-@pytest.mark.parametrize("tp", [2, 4])
-def test_task_module_step_under_tensor_parallelism_matches_single_process(tp):
-    """tp=4 with 2 KV heads also exercises KV-head replication (kv_replicator=2) and the replica-gradient sync."""
-    run_dist("tp_trainer_step.py", tp, {"TP": str(tp)})
+@pytest.mark.parametrize("tp,nproc", [(2, 2), (4, 4), (2, 4)])
+def test_task_module_step_under_tensor_parallelism_matches_single_process(tp, nproc):
+    """tp=4 with 2 KV heads also exercises KV-head replication (kv_replicator=2) and the replica-gradient sync;
+    (tp=2, 4 ranks) adds data parallelism with the ZeRO-1 sharded optimizer."""
+    run_dist("tp_trainer_step.py", nproc, {"TP": str(tp)})
 
 
 def test_zero1_matches_adamw():
