@@ -30,7 +30,6 @@ dpr = ps.get_data_parallel_rank()
 loss = mod.training_step({"input_ids": ids_all[dpr:dpr + 1], "labels": ids_all[dpr:dpr + 1].clone()})
 gn = mod.optimizer.grad_norm.clone()
 # reference: same seed, EP=1, single process sees the whole batch as `world` microbatches
-state = {n: p.detach().clone() for n, p in mod.local_named_parameters()}
 ps.destroy_model_parallel(); 
 import torch.distributed as dist
 # build the reference on every rank without process groups (pure local computation)
@@ -51,8 +50,6 @@ El = 4 // EP
 epr = (rank // TP) % EP                       # TP varies fastest in the rank grid
 from neuronx_distributed_training_b200.parallel.layers import shard_master_weight
 tp_, tpr_ = TP, rank % TP
-for n, p in state.items():
-    pass
 for n, p in mod.local_named_parameters():
     r = ref_params[n]
     if getattr(p, "expert_parallel", False):
