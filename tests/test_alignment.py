@@ -1,7 +1,6 @@
 import json
 import math
 
-import pytest
 import torch
 import torch.nn.functional as F
 

@@ -1,5 +1,4 @@
 import math
-import torch
 from neuronx_distributed_training_b200.optim.lr_schedulers import (LinearAnnealingWithWarmUp, CosineAnnealing, WarmupAnnealing,
                                                                    NoamAnnealing, get_scheduler, prepare_lr_scheduler)
 
