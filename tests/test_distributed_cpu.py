@@ -92,6 +92,10 @@ def test_context_parallel_composes_with_tensor_parallel():
     run_dist("cp_tp_model.py", 4)
 
 
+def test_mixtral_through_the_pipeline():
+    run_dist("mixtral_pp.py", 2)
+
+
 def test_moe_expert_parallel_matches_single_process():
     run_dist("moe_ep.py", 2, {"EP": "2"})
 
