@@ -92,6 +92,10 @@ def test_context_parallel_composes_with_tensor_parallel():
     run_dist("cp_tp_model.py", 4)
 
 
+def test_megatron_gpt_through_the_pipeline():
+    run_dist("megatron_pp.py", 2)
+
+
 def test_mixtral_through_the_pipeline():
     run_dist("mixtral_pp.py", 2)
 
