@@ -157,3 +157,13 @@ def test_memory_estimate_matches_the_measured_llama3_8b_footprints():
     a, b = estimate_memory_gib(**dims, tp=2, dp=1), estimate_memory_gib(**dims, tp=2, dp=4)
     assert abs(b["optimizer"] * 4 - a["optimizer"]) < 1e-6 and b["weights"] == a["weights"]
     assert estimate_memory_gib(**dims, tp=2, pp=2)["activations"] > 0.9 * a["activations"]
+
+
+def test_package_has_no_undefined_names_or_unused_imports():
+    """tools/lint_names.py over the package, examples, tools, bench.py and __graft_entry__.py (the image has no third-party
+    linter): a NameError hiding in a GPU-only branch would otherwise first show up on the GPU box."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "lint_names.py")], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
