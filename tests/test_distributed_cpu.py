@@ -55,6 +55,11 @@ def test_task_module_step_under_tensor_parallelism_matches_single_process(tp, np
     run_dist("tp_trainer_step.py", nproc, {"TP": str(tp)})
 
 
+def test_transformers_weights_through_the_converter_into_tensor_parallel_model():
+    pytest.importorskip("transformers")
+    run_dist("hf_weights_tp.py", 2, {"TP": "2"})
+
+
 def test_zero1_matches_adamw():
     run_dist("zero1.py", 2)
 
