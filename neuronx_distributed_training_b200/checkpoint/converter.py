@@ -317,6 +317,17 @@ class MixtralCheckpointConverter(CheckpointConverterBase):
         for k, v in state.items():
             if "block_sparse_moe" not in k:
                 out[k] = v
+        # transformers >= 5 keeps (and may save) the experts fused: ``mlp.gate.weight`` [E,H],
+        # ``mlp.experts.gate_up_proj`` [E, 2I, H] (gate rows first) and ``mlp.experts.down_proj`` [E, H, I]
+        for k in [k for k in out if re.search(r"\.mlp\.(gate\.weight|experts\.(gate_up_proj|down_proj))$", k)]:
+            v = out.pop(k)
+            l = _LAYER_RE.search(k).group(1)
+            if k.endswith("mlp.gate.weight"):
+                out[f"model.layers.{l}.mlp.moe.router.linear_router.weight"] = v
+            elif k.endswith("experts.gate_up_proj"):
+                out[f"model.layers.{l}.mlp.moe.expert_mlps.mlp_op.gate_up_proj"] = v.transpose(1, 2).contiguous()    # [E,H,2I]
+            else:
+                out[f"model.layers.{l}.mlp.moe.expert_mlps.mlp_op.down_proj"] = v.transpose(1, 2).contiguous()       # [E,I,H]
         for l in layers:
             pre = f"model.layers.{l}.block_sparse_moe"
             out[f"model.layers.{l}.mlp.moe.router.linear_router.weight"] = state[f"{pre}.gate.weight"]

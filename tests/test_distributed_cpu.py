@@ -60,6 +60,11 @@ def test_transformers_weights_through_the_converter_into_tensor_parallel_model()
     run_dist("hf_weights_tp.py", 2, {"TP": "2"})
 
 
+def test_transformers_mixtral_weights_through_the_converter_into_tensor_parallel_model():
+    pytest.importorskip("transformers")
+    run_dist("hf_mixtral_weights_tp.py", 2, {"TP": "2"})
+
+
 def test_zero1_matches_adamw():
     run_dist("zero1.py", 2)
 
