@@ -11,9 +11,26 @@ from ..parallel import state as ps
 
 
 @torch.no_grad()
+def filter_logits(logits: torch.Tensor, top_k: int = 0, top_p: float = 1.0) -> torch.Tensor:
+    """[B, V] logits with everything outside the top-k / nucleus (top-p) set pushed to -inf."""
+    if top_k and top_k > 0:
+        kth = torch.topk(logits, min(int(top_k), logits.shape[-1]), dim=-1).values[..., -1:]
+        logits = logits.masked_fill(logits < kth, float("-inf"))
+    if top_p < 1.0:
+        srt, idx = torch.sort(logits, dim=-1, descending=True)
+        cum = torch.softmax(srt, -1).cumsum(-1)
+        drop = cum - torch.softmax(srt, -1) >= top_p            # tokens that start beyond the nucleus (the first always stays)
+        srt = srt.masked_fill(drop, float("-inf"))
+        logits = torch.full_like(logits, float("-inf")).scatter(-1, idx, srt)
+    return logits
+
+
 def generate(model, input_ids: torch.Tensor, max_new_tokens: int = 64, eos_token_id: Optional[int] = None,
-             temperature: float = 0.0, pad_to_multiple: int = 1) -> torch.Tensor:
-    """input_ids [B, S0] -> [B, S0 + n].  Works with TP (logits are vocab-parallel and gathered)."""
+             temperature: float = 0.0, pad_to_multiple: int = 1, top_k: int = 0, top_p: float = 1.0) -> torch.Tensor:
+    """input_ids [B, S0] -> [B, S0 + n].  Works with TP (logits are vocab-parallel and gathered).  ``temperature <= 0``:
+    greedy; otherwise sampling, optionally restricted to the ``top_k`` most likely tokens and / or the smallest set whose
+    probability mass reaches ``top_p``.  The forward pass is re-run over the whole prefix for every new token (no KV
+    cache): adequate for the short generations of the SFT evaluation, not a serving path."""
     model.eval()
     tp = ps.get_tensor_model_parallel_size()
     ids = input_ids
@@ -28,7 +45,10 @@ def generate(model, input_ids: torch.Tensor, max_new_tokens: int = 64, eos_token
         last = logits[:, ids.shape[1] - 1].float()
         if tp > 1:
             last = mp.all_gather_last_dim(last)
-        nxt = torch.argmax(last, -1) if temperature <= 0 else torch.multinomial(torch.softmax(last / temperature, -1), 1).squeeze(-1)
+        if temperature <= 0:
+            nxt = torch.argmax(last, -1)
+        else:
+            nxt = torch.multinomial(torch.softmax(filter_logits(last / temperature, top_k, top_p), -1), 1).squeeze(-1)
         if eos_token_id is not None:
             nxt = torch.where(finished, torch.full_like(nxt, eos_token_id), nxt)
             finished |= nxt == eos_token_id

@@ -30,3 +30,17 @@ def test_llama3_8b_flops_model():
     f = llama_flops_per_seq(4096, 32, 8192, 128256, 14336, 32, 8, 128)
     assert 4.5e14 < f < 5.5e14                      # ~5.0e14 FLOPs / 8k-token sequence
     assert abs(calculate_mfu(1.0, f, 1, 1000.0) - f / 1e15) < 1e-12
+
+
+def test_top_k_and_top_p_filtering():
+    import torch
+    from neuronx_distributed_training_b200.utils.generation import filter_logits
+    logits = torch.tensor([[2.0, 1.0, 0.5, -1.0, 3.0]])
+    f = filter_logits(logits, top_k=2)
+    assert torch.isfinite(f).sum() == 2 and torch.isfinite(f[0, [0, 4]]).all()
+    p = torch.softmax(logits, -1)
+    f = filter_logits(logits, top_p=float(p[0, 4]) + 1e-4)                   # nucleus = the best token + the next one
+    assert torch.isfinite(f).sum() == 2 and torch.isfinite(f[0, [0, 4]]).all()
+    f = filter_logits(logits, top_p=0.01)                                    # the most likely token always survives
+    assert torch.isfinite(f).sum() == 1 and torch.isfinite(f[0, 4])
+    assert torch.equal(filter_logits(logits), logits)
