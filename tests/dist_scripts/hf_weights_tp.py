@@ -64,4 +64,24 @@ for rs in ({"rope_type": "llama3", "factor": 4.0, "low_freq_factor": 1.0, "high_
     with torch.no_grad():
         got, _ = m(input_ids=ids, labels=ids)
     check(f"rope_scaling {rs['rope_type']} loss vs transformers", got, want, atol=2e-5)
+# sliding-window attention against transformers' Mistral (same parameter names as Llama)
+torch.manual_seed(3)
+mc = transformers.MistralConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                num_key_value_heads=2, max_position_embeddings=64, rope_theta=10000.0, rms_norm_eps=1e-5,
+                                sliding_window=5, tie_word_embeddings=False, attn_implementation="eager", head_dim=8)
+mm_ = transformers.MistralForCausalLM(mc).float()
+with torch.no_grad():
+    want = mm_(input_ids=ids, labels=ids).loss
+conv = CheckpointConverterBase(tp_size=tp, pp_size=1, model_style="hf", kv_size_multiplier=1, fuse_qkv=True, qkv_linear=True,
+                               config={"num_attention_heads": 4, "num_key_value_heads": 2, "hidden_size": 32, "head_dim": 8,
+                                       "num_hidden_layers": 2})
+shard = conv.shard_for_rank(conv.hf_to_framework_full({k: v.detach().clone() for k, v in mm_.state_dict().items()}), tpr, 0)
+m = LlamaForCausalLM(LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                 num_key_value_heads=2, max_position_embeddings=64, rope_theta=10000.0, rms_norm_eps=1e-5,
+                                 sliding_window=5, torch_dtype="float32", use_flash_attention=False, fuse_qkv=True,
+                                 sequence_parallel_enabled=True, use_cpu_initialization=True))
+m.load_state_dict(shard, strict=False)
+with torch.no_grad():
+    got, _ = m(input_ids=ids, labels=ids)
+check("sliding-window loss vs transformers Mistral", got, want, atol=2e-5)
 finish()
