@@ -69,7 +69,7 @@ class CheckpointConverterBase:
         (r"embed_tokens\.weight$", 0, 1), (r"lm_head\.weight$", 0, 1),
         (r"qkv_proj\.weight_(qkv|q|k|v)$", 0, 1), (r"qkv_proj\.bias_(qkv|q|k|v)$", 0, 1),
         (r"(q_proj|k_proj|v_proj)\.weight$", 0, 1), (r"o_proj\.weight$", 1, 1),
-        (r"gate_up_proj\.weight$", 0, 2), (r"down_proj\.weight$", 1, 1),
+        (r"gate_up_proj\.(weight|bias)$", 0, 2), (r"down_proj\.weight$", 1, 1),
         (r"expert_mlps\.mlp_op\.gate_up_proj$", 2, 2), (r"expert_mlps\.mlp_op\.down_proj$", 1, 1),
         # Megatron names
         (r"word_embeddings\.weight$", 0, 1), (r"output_layer\.weight$", 0, 1),
@@ -194,12 +194,12 @@ class CheckpointConverterBase:
                     else:
                         out[f"{base}.qkv_proj.{kind}_q"], out[f"{base}.qkv_proj.{kind}_k"], out[f"{base}.qkv_proj.{kind}_v"] = qs, ks, vs
                     continue
-                m = re.match(r"(.*mlp)\.(gate_proj|up_proj)\.weight$", name)
+                m = re.match(r"(.*mlp)\.(gate_proj|up_proj)\.(weight|bias)$", name)        # bias: models with mlp_bias
                 if m:
-                    base = m.group(1)
-                    g, u = full[f"{base}.gate_proj.weight"], full[f"{base}.up_proj.weight"]
-                    done.update((f"{base}.gate_proj.weight", f"{base}.up_proj.weight"))
-                    out[f"{base}.gate_up_proj.weight"] = shard_master_weight(torch.cat([g, u], 0), 0, tp, tp_rank, stride=2)
+                    base, kind = m.group(1), m.group(3)
+                    g, u = full[f"{base}.gate_proj.{kind}"], full[f"{base}.up_proj.{kind}"]
+                    done.update((f"{base}.gate_proj.{kind}", f"{base}.up_proj.{kind}"))
+                    out[f"{base}.gate_up_proj.{kind}"] = shard_master_weight(torch.cat([g, u], 0), 0, tp, tp_rank, stride=2)
                     continue
             dim, stride = self._rule(name)
             if stride == -1:
@@ -234,11 +234,11 @@ class CheckpointConverterBase:
                                 w = w if kind == "weight" else w.squeeze(-1)
                             full[f"{base}.{which}_proj.{kind}"] = w
                         continue
-                    m = re.match(r"(.*mlp)\.gate_up_proj\.weight$", name)
+                    m = re.match(r"(.*mlp)\.gate_up_proj\.(weight|bias)$", name)
                     if m:
                         gu = unshard_weights(parts, 0, stride=2)
                         g, u = gu.chunk(2, 0)
-                        full[f"{m.group(1)}.gate_proj.weight"], full[f"{m.group(1)}.up_proj.weight"] = g, u
+                        full[f"{m.group(1)}.gate_proj.{m.group(2)}"], full[f"{m.group(1)}.up_proj.{m.group(2)}"] = g, u
                         continue
                 dim, stride = self._rule(name)
                 if stride == -1:

@@ -64,6 +64,34 @@ for rs in ({"rope_type": "llama3", "factor": 4.0, "low_freq_factor": 1.0, "high_
     with torch.no_grad():
         got, _ = m(input_ids=ids, labels=ids)
     check(f"rope_scaling {rs['rope_type']} loss vs transformers", got, want, atol=2e-5)
+# attention / MLP biases (fused and split QKV)
+for fuse in (True, False):
+    torch.manual_seed(3)
+    hc = transformers.LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                  num_key_value_heads=2, max_position_embeddings=64, rope_theta=10000.0, rms_norm_eps=1e-5,
+                                  tie_word_embeddings=False, attention_bias=True, mlp_bias=True, attn_implementation="eager")
+    hm = transformers.LlamaForCausalLM(hc).float()
+    with torch.no_grad():
+        for n_, p_ in hm.named_parameters():
+            if n_.endswith("bias"):
+                p_.normal_(0, 0.1)                      # transformers initialises biases to zero
+        want = hm(input_ids=ids, labels=ids).loss
+    conv = CheckpointConverterBase(tp_size=tp, pp_size=1, model_style="hf", kv_size_multiplier=1, fuse_qkv=fuse, qkv_linear=True,
+                                   config={"num_attention_heads": 4, "num_key_value_heads": 2, "hidden_size": 32, "head_dim": 8,
+                                           "num_hidden_layers": 2})
+    shard = conv.shard_for_rank(conv.hf_to_framework_full({k: v.detach().clone() for k, v in hm.state_dict().items()}), tpr, 0)
+    m = LlamaForCausalLM(LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                     num_key_value_heads=2, max_position_embeddings=64, rope_theta=10000.0, rms_norm_eps=1e-5,
+                                     attention_bias=True, mlp_bias=True, torch_dtype="float32", use_flash_attention=False,
+                                     fuse_qkv=fuse, sequence_parallel_enabled=True, use_cpu_initialization=True))
+    own = m.state_dict()
+    missing = [k for k in own if k not in shard and not k.endswith("rotary_emb.inv_freq")]
+    unexpected = [k for k in shard if k not in own]
+    assert not missing and not unexpected, ("bias model", missing[:4], unexpected[:4])
+    m.load_state_dict(shard, strict=False)
+    with torch.no_grad():
+        got, _ = m(input_ids=ids, labels=ids)
+    check(f"biased model loss vs transformers fuse_qkv={fuse}", got, want, atol=2e-5)
 # sliding-window attention against transformers' Mistral (same parameter names as Llama)
 torch.manual_seed(3)
 mc = transformers.MistralConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,

@@ -32,6 +32,16 @@ def test_hf_roundtrip_bit_exact(tmp_path):
     cfg = dict(hidden_size=32, intermediate_size=48, vocab_size=64, num_hidden_layers=4, num_attention_heads=8, num_key_value_heads=2)
     (tmp_path / "config.json").write_text(json.dumps(cfg))
     hf = _hf_llama_state(cfg)
+    # attention_bias / mlp_bias models: q/k/v biases and the gate / up biases that are fused with stride 2
+    gb = torch.Generator().manual_seed(9)
+    for l in range(cfg["num_hidden_layers"]):
+        p_ = f"model.layers.{l}"
+        hd = cfg["hidden_size"] // cfg["num_attention_heads"]
+        hf[f"{p_}.self_attn.q_proj.bias"] = torch.randn(cfg["num_attention_heads"] * hd, generator=gb)
+        hf[f"{p_}.self_attn.k_proj.bias"] = torch.randn(cfg["num_key_value_heads"] * hd, generator=gb)
+        hf[f"{p_}.self_attn.v_proj.bias"] = torch.randn(cfg["num_key_value_heads"] * hd, generator=gb)
+        hf[f"{p_}.mlp.gate_proj.bias"] = torch.randn(cfg["intermediate_size"], generator=gb)
+        hf[f"{p_}.mlp.up_proj.bias"] = torch.randn(cfg["intermediate_size"], generator=gb)
     src = tmp_path / "hf"; src.mkdir()
     torch.save(hf, src / "pytorch_model.bin")
     for tp, pp, mult, fuse, xser in [(2, 2, 1, True, True), (4, 1, 2, True, False), (2, 1, 1, False, True)]:
