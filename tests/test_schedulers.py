@@ -42,3 +42,25 @@ def test_state_dict_roundtrip_and_registry():
     assert o2.param_groups[0]["lr"] == o.param_groups[0]["lr"]
     s3 = prepare_lr_scheduler(_Opt(1.0), {"name": "NoamAnnealing", "warmup_steps": 10, "d_model": 1.0}, max_steps=100)
     assert isinstance(s3, NoamAnnealing)
+
+
+def test_linear_annealing_with_warmup_matches_transformers_schedule():
+    """The reference defines LinearAnnealingWithWarmUp as HF's linear-warmup / linear-decay LambdaLR (reference
+    optim/lr_schedulers.py:11-23): compare step by step with transformers.get_linear_schedule_with_warmup."""
+    import pytest
+    import torch
+    tr = pytest.importorskip("transformers")
+    from neuronx_distributed_training_b200.optim.lr_schedulers import LinearAnnealingWithWarmUp
+
+    class _Opt:
+        def __init__(self):
+            self.param_groups = [{"lr": 3e-4}]
+
+    ours_opt = _Opt()
+    ours = LinearAnnealingWithWarmUp(ours_opt, warmup_steps=5, max_steps=40)
+    p = torch.nn.Parameter(torch.zeros(1))
+    ref_opt = torch.optim.SGD([p], lr=3e-4)
+    ref = tr.get_linear_schedule_with_warmup(ref_opt, num_warmup_steps=5, num_training_steps=40)
+    for step in range(40):
+        assert abs(ours_opt.param_groups[0]["lr"] - ref_opt.param_groups[0]["lr"]) < 1e-12, step
+        ref_opt.step(); ref.step(); ours.step()
