@@ -506,7 +506,8 @@ def _broadcast_over_dp(obj):
             if idx not in received:
                 t = tensors[idx].to(dev).contiguous() if is_src else torch.empty(shape, dtype=dtype, device=dev)
                 dist.broadcast(t, src=src, group=group)
-                received[idx] = tensors[idx] if is_src else t
+                # hand back host tensors, like a read from disk would: the GPU copy is only the NCCL staging buffer
+                received[idx] = tensors[idx] if is_src else (t.cpu() if use_cuda else t)
             return received[idx]
         if isinstance(x, dict):
             return {k: fill(v) for k, v in x.items()}
