@@ -8,6 +8,7 @@ from neuronx_distributed_training_b200.checkpoint.converter import CheckpointCon
 from neuronx_distributed_training_b200.models.llama import LlamaConfig, LlamaForCausalLM
 
 TP = int(os.environ.get("TP", "2"))
+KVM = int(os.environ.get("KVM", "1"))        # kv_size_multiplier: TP=4 with 2 KV heads needs every KV head on two ranks
 rank, world = init(tp=TP)
 tp, tpr = ps.get_tensor_model_parallel_size(), ps.get_tensor_model_parallel_rank()
 torch.manual_seed(3)                       # same HF model on every rank
@@ -25,11 +26,12 @@ for fuse in (True, False):
         conv = CheckpointConverterBase(tp_size=tp, pp_size=1, model_style="hf",
                                        config={"num_attention_heads": 4, "num_key_value_heads": 2, "hidden_size": 32, "head_dim": 8,
                                                "num_hidden_layers": 2},
-                                       kv_size_multiplier=1, fuse_qkv=fuse, qkv_linear=True)
+                                       kv_size_multiplier=KVM, fuse_qkv=fuse, qkv_linear=True)
         shard = conv.shard_for_rank(conv.hf_to_framework_full(dict(full)), tpr, 0)
         m = LlamaForCausalLM(LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
                                          num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64, rope_theta=10000.0,
                                          rms_norm_eps=1e-5, torch_dtype="float32", use_flash_attention=False, fuse_qkv=fuse,
+                                         kv_shared_group_size=KVM,
                                          sequence_parallel_enabled=sp, use_cpu_initialization=True))
         own = m.state_dict()
         missing = [k for k in own if k not in shard and not k.endswith("rotary_emb.inv_freq")]
@@ -42,6 +44,9 @@ for fuse in (True, False):
         from neuronx_distributed_training_b200.parallel.layers import shard_master_weight
         check(f"embedding grad fuse_qkv={fuse} sp={sp}", m.model.embed_tokens.weight.grad,
               shard_master_weight(hf.model.embed_tokens.weight.grad, 0, tp, tpr), atol=2e-5)
+if KVM > 1:
+    finish()
+    sys.exit(0)
 # RoPE scaling variants against transformers (forward loss, TP=2 + SP, fused QKV): Llama-3.1 style, linear, dynamic NTK
 for rs in ({"rope_type": "llama3", "factor": 4.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0, "original_max_position_embeddings": 8},
            {"rope_type": "linear", "factor": 2.0}):

@@ -55,9 +55,11 @@ def test_task_module_step_under_tensor_parallelism_matches_single_process(tp, np
     run_dist("tp_trainer_step.py", nproc, {"TP": str(tp)})
 
 
-def test_transformers_weights_through_the_converter_into_tensor_parallel_model():
+@pytest.mark.parametrize("tp,kvm", [(2, 1), (4, 2)])
+def test_transformers_weights_through_the_converter_into_tensor_parallel_model(tp, kvm):
+    """(4, 2): TP larger than the number of KV heads -- the converter replicates every KV head (kv_size_multiplier)."""
     pytest.importorskip("transformers")
-    run_dist("hf_weights_tp.py", 2, {"TP": "2"})
+    run_dist("hf_weights_tp.py", tp, {"TP": str(tp), "KVM": str(kvm)})
 
 
 def test_transformers_mixtral_weights_through_the_converter_into_tensor_parallel_model():
