@@ -124,3 +124,53 @@ def test_config_validation():
         MegatronGPTModel(_cfg({"activations_checkpoint_granularity": "full", "activations_checkpoint_num_layers": 2}), None)
     with pytest.raises(ValueError):
         _module(_cfg({"activations_checkpoint_granularity": "selective", "activations_checkpoint_recompute": ["Nope"]}))
+
+
+def test_gpt2_style_model_matches_transformers_gpt2():
+    """Independent oracle for the Megatron-GPT path (learned positions, LayerNorm, biases, tanh-GeLU, tied embeddings,
+    per-head interleaved QKV): the weights of a `transformers` GPT2LMHeadModel give the same loss."""
+    tr = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    H, nh, L, S, V, F_ = 64, 4, 2, 32, 128, 128
+    hd = H // nh
+    hcfg = tr.GPT2Config(vocab_size=V, n_positions=S, n_embd=H, n_layer=L, n_head=nh, n_inner=F_, activation_function="gelu_new",
+                         resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0, layer_norm_epsilon=1e-5, attn_implementation="eager")
+    hf = tr.GPT2LMHeadModel(hcfg).float().eval()
+    with torch.no_grad():
+        for p in hf.parameters():
+            p.normal_(0, 0.05)                         # non-trivial biases / norms (the LM head is tied to wte)
+    mod = _module(_cfg({"layernorm_epsilon": 1e-5}))
+    sd = {k: v.detach() for k, v in hf.state_dict().items()}
+    new = {"language_model.embedding.word_embeddings.weight": sd["transformer.wte.weight"],
+           "language_model.embedding.position_embeddings.weight": sd["transformer.wpe.weight"],
+           "language_model.encoder.final_layernorm.weight": sd["transformer.ln_f.weight"],
+           "language_model.encoder.final_layernorm.bias": sd["transformer.ln_f.bias"]}
+    for l in range(L):
+        a, b = f"transformer.h.{l}", f"language_model.encoder.layers.{l}"
+        for src, dst in (("ln_1", "input_layernorm"), ("ln_2", "post_attention_layernorm")):
+            new[f"{b}.{dst}.weight"], new[f"{b}.{dst}.bias"] = sd[f"{a}.{src}.weight"], sd[f"{a}.{src}.bias"]
+        w = sd[f"{a}.attn.c_attn.weight"].t()          # Conv1D stores [in, out]: rows of w are [q_all; k_all; v_all]
+        bias = sd[f"{a}.attn.c_attn.bias"]
+        wq, wk, wv = w.view(3, nh, hd, H)
+        bq, bk, bv = bias.view(3, nh, hd)
+        new[f"{b}.self_attention.query_key_value.weight"] = torch.stack([wq, wk, wv], 1).reshape(3 * H, H)     # per head: q, k, v
+        new[f"{b}.self_attention.query_key_value.bias"] = torch.stack([bq, bk, bv], 1).reshape(3 * H)
+        new[f"{b}.self_attention.dense.weight"] = sd[f"{a}.attn.c_proj.weight"].t()
+        new[f"{b}.self_attention.dense.bias"] = sd[f"{a}.attn.c_proj.bias"]
+        new[f"{b}.mlp.dense_h_to_4h.weight"] = sd[f"{a}.mlp.c_fc.weight"].t()
+        new[f"{b}.mlp.dense_h_to_4h.bias"] = sd[f"{a}.mlp.c_fc.bias"]
+        new[f"{b}.mlp.dense_4h_to_h.weight"] = sd[f"{a}.mlp.c_proj.weight"].t()
+        new[f"{b}.mlp.dense_4h_to_h.bias"] = sd[f"{a}.mlp.c_proj.bias"]
+    params = {n.split("chunks.0.", 1)[-1]: p for n, p in mod.model.named_parameters()}
+    assert set(params) == set(new), sorted(set(params) ^ set(new))[:6]
+    with torch.no_grad():
+        for n, p in params.items():
+            p.copy_(new[n].reshape(p.shape))
+    ids = torch.randint(0, V, (2, S))
+    with torch.no_grad():
+        want = hf(input_ids=ids, labels=ids).loss
+        labels = torch.cat([ids[:, 1:], ids[:, :1]], 1)
+        mask = torch.ones(2, S); mask[:, -1] = 0
+        got, _ = mod.model_fwd_calc_loss({"tokens": ids, "labels": labels, "loss_mask": mask,
+                                          "position_ids": torch.arange(S).unsqueeze(0).expand(2, S).contiguous()})
+    assert abs(float(got) - float(want)) < 2e-5, (float(got), float(want))
