@@ -174,3 +174,42 @@ def test_gpt2_style_model_matches_transformers_gpt2():
         got, _ = mod.model_fwd_calc_loss({"tokens": ids, "labels": labels, "loss_mask": mask,
                                           "position_ids": torch.arange(S).unsqueeze(0).expand(2, S).contiguous()})
     assert abs(float(got) - float(want)) < 2e-5, (float(got), float(want))
+
+
+def test_llama_style_megatron_model_matches_transformers_llama():
+    """RoPE + RMSNorm + SwiGLU + untied head on the Megatron path against `transformers` LlamaForCausalLM (MHA)."""
+    tr = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    H, nh, L, S, V, F_ = 64, 4, 2, 32, 128, 128
+    hd = H // nh
+    hcfg = tr.LlamaConfig(vocab_size=V, hidden_size=H, intermediate_size=F_, num_hidden_layers=L, num_attention_heads=nh,
+                          num_key_value_heads=nh, max_position_embeddings=S, rope_theta=10000.0, rms_norm_eps=1e-5,
+                          tie_word_embeddings=False, attn_implementation="eager")
+    hf = tr.LlamaForCausalLM(hcfg).float().eval()
+    sd = {k: v.detach() for k, v in hf.state_dict().items()}
+    mod = _module(_cfg({**VARIANTS["llama_style"], "layernorm_epsilon": 1e-5}))
+    new = {"language_model.embedding.word_embeddings.weight": sd["model.embed_tokens.weight"],
+           "language_model.output_layer.weight": sd["lm_head.weight"],
+           "language_model.encoder.final_layernorm.weight": sd["model.norm.weight"]}
+    for l in range(L):
+        a, b = f"model.layers.{l}", f"language_model.encoder.layers.{l}"
+        new[f"{b}.input_layernorm.weight"] = sd[f"{a}.input_layernorm.weight"]
+        new[f"{b}.post_attention_layernorm.weight"] = sd[f"{a}.post_attention_layernorm.weight"]
+        wq, wk, wv = (sd[f"{a}.self_attn.{n}_proj.weight"].view(nh, hd, H) for n in "qkv")
+        new[f"{b}.self_attention.query_key_value.weight"] = torch.stack([wq, wk, wv], 1).reshape(3 * H, H)
+        new[f"{b}.self_attention.dense.weight"] = sd[f"{a}.self_attn.o_proj.weight"]
+        new[f"{b}.mlp.dense_h_to_4h.weight"] = torch.cat([sd[f"{a}.mlp.gate_proj.weight"], sd[f"{a}.mlp.up_proj.weight"]], 0)
+        new[f"{b}.mlp.dense_4h_to_h.weight"] = sd[f"{a}.mlp.down_proj.weight"]
+    params = {n.split("chunks.0.", 1)[-1]: p for n, p in mod.model.named_parameters()}
+    assert set(params) == set(new), sorted(set(params) ^ set(new))[:6]
+    with torch.no_grad():
+        for n, p in params.items():
+            p.copy_(new[n].reshape(p.shape))
+    ids = torch.randint(0, V, (2, S))
+    with torch.no_grad():
+        want = hf(input_ids=ids, labels=ids).loss
+        labels = torch.cat([ids[:, 1:], ids[:, :1]], 1)
+        mask = torch.ones(2, S); mask[:, -1] = 0
+        got, _ = mod.model_fwd_calc_loss({"tokens": ids, "labels": labels, "loss_mask": mask,
+                                          "position_ids": torch.arange(S).unsqueeze(0).expand(2, S).contiguous()})
+    assert abs(float(got) - float(want)) < 2e-5, (float(got), float(want))
