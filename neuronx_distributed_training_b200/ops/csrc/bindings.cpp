@@ -19,6 +19,8 @@ std::vector<at::Tensor> qkv_rope_split_fwd(const at::Tensor& packed, const at::T
                                            int64_t B, int64_t S, int64_t Hq, int64_t Hk);
 at::Tensor qkv_rope_split_bwd(const at::Tensor& dq, const at::Tensor& dk, const at::Tensor& dv, const at::Tensor& cos,
                               const at::Tensor& sin);
+std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
+                                        int64_t window, double scale);
 std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
                                        int64_t window, double scale);
 void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
@@ -82,6 +84,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("qkv_rope_split_fwd", &qkv_rope_split_fwd);
   m.def("qkv_rope_split_bwd", &qkv_rope_split_bwd);
   m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 causal flash attention forward (head_dim 128)");
+  m.def("flash_attn_fwd1", &flash_attn_fwd1, "single-tile forward kernel (any multiple of 128)");
   m.def("flash_attn_bwd_preview", &flash_attn_bwd_preview,
         "tcgen05 causal flash attention backward (preview: compiled, not yet validated on hardware)");
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");

@@ -325,8 +325,22 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
 // q [B,S,Hq,128], k/v [B,S,Hk,128] bf16 with a contiguous last dim and row (token) pitch given by stride(1);
 // returns (out [B,S,Hq,128] bf16, lse [B,Hq,S] fp32)
+std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
+                                        int64_t window, double scale);
+
+std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
+                                        int64_t window, double scale);
+
+// sequence lengths that are a multiple of 256 take the two-tile ping-pong kernel (flash_attn_fwd2_sm100.cu), the
+// remaining multiples of 128 the single-tile kernel below
 std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
                                        int64_t window, double scale) {
+  if (q.dim() == 4 && q.size(1) % 256 == 0) return flash_attn_fwd2(q, k, v, causal, window, scale);
+  return flash_attn_fwd1(q, k, v, causal, window, scale);
+}
+
+std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
+                                        int64_t window, double scale) {
   using namespace fa100;
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16);
   TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.size(3) == D && k.size(3) == D && v.size(3) == D,

@@ -6,13 +6,13 @@ from neuronx_distributed_training_b200 import ops
 C = ops.C()
 torch.manual_seed(0)
 def rel(a, b): return ((a.float() - b.float()).norm() / b.float().norm()).item()
-for (B, S, Hq, Hk, w) in [(1, 256, 4, 1, 0), (2, 1024, 8, 2, 0), (1, 1024, 4, 1, 300)]:
+for (B, S, Hq, Hk, w) in [(1, 256, 4, 1, 0), (2, 1024, 8, 2, 0), (1, 1024, 4, 1, 300), (1, 384, 2, 2, 0), (1, 2048, 4, 2, 700), (2, 4096, 2, 1, 0), (1, 2048, 2, 1, 100)]:
     q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16(); k = torch.randn(B, S, Hk, 128, device="cuda").bfloat16(); v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
     o, lse = C.flash_attn_fwd(q, k, v, True, w, 1 / math.sqrt(128)); torch.cuda.synchronize()
     r, lr = ops.attention_ref(q, k, v, causal=True, window=w or None, return_lse=True)
     print(f"fwd B{B} S{S} Hq{Hq} Hk{Hk} w{w}: rel_err={rel(o, r):.3e} lse_err={(lse - lr).abs().max().item():.3e}", flush=True)
 # full (non-causal) attention: the off-diagonal blocks of ring attention (added after round 1's GPU budget; validate first)
-for (B, S, Hq, Hk) in [(1, 256, 4, 1), (2, 512, 8, 2)]:
+for (B, S, Hq, Hk) in [(1, 256, 4, 1), (2, 512, 8, 2), (1, 2048, 4, 4)]:
     q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16(); k = torch.randn(B, S, Hk, 128, device="cuda").bfloat16(); v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
     o, lse = C.flash_attn_fwd(q, k, v, False, 0, 1 / math.sqrt(128)); torch.cuda.synchronize()
     r, lr = ops.attention_ref(q, k, v, causal=False, return_lse=True)
