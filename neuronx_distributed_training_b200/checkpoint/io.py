@@ -18,6 +18,7 @@ avoids the fork-doubles-host-memory problem the reference documents (known_issue
 """
 from __future__ import annotations
 
+import logging
 import os
 import shutil
 import struct
@@ -31,6 +32,8 @@ import torch.distributed as dist
 
 from ..parallel import state as ps
 from . import storage
+
+log = logging.getLogger(__name__)
 
 _MAGIC = b"NXDTB200"
 _DTYPES = [torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int8, torch.uint8, torch.int16,
@@ -264,6 +267,8 @@ def save_checkpoint(checkpoint_dir: str, tag: str, model: Optional[Dict[str, Any
             mp_ = os.path.join(root, marker)
             if os.path.exists(mp_):
                 os.remove(mp_)
+        # completion markers of an earlier (possibly torn) save of the same tag must not count for this one
+        shutil.rmtree(os.path.join(root, ".ranks"), ignore_errors=True)
     ps.barrier()
     if model is not None and dp_rank == 0:
         _save_object(model, os.path.join(root, "model", shard_file_name(0, tp_rank, pp_rank)), use_xser, async_save)
@@ -306,6 +311,10 @@ def save_checkpoint(checkpoint_dir: str, tag: str, model: Optional[Dict[str, Any
                 deadline = time.time() + 3600
                 while len([n for n in os.listdir(mdir) if n.endswith(".ok")]) < world and time.time() < deadline:
                     time.sleep(0.05)
+                if len([n for n in os.listdir(mdir) if n.endswith(".ok")]) < world:
+                    log.error("checkpoint %s: not every rank finished writing within the deadline; leaving it WITHOUT a "
+                              "'done' marker so that auto-resume skips it", root)
+                    return
                 finish()
         g_iostate.submit(mark)
     else:
@@ -357,10 +366,14 @@ def _save_checkpoint_remote(url_dir, tag, model, optimizer, user_content, use_xs
                     os.remove(os.path.join(dirpath, f))
         if rank == 0:
             deadline = time.time() + 3600
-            while time.time() < deadline:
-                if len([u for u in store.list(storage.join_url(root_url, ".ranks")) if u.endswith(".ok")]) >= world:
-                    break
-                time.sleep(0.05)
+            complete = False
+            while time.time() < deadline and not complete:
+                complete = len([u for u in store.list(storage.join_url(root_url, ".ranks")) if u.endswith(".ok")]) >= world
+                if not complete:
+                    time.sleep(0.05)
+            if not complete:
+                log.error("checkpoint %s: not every rank finished uploading within the deadline; not publishing 'done'", root_url)
+                return
             with open(os.path.join(local_root, "checkpoint"), "w") as f:
                 f.write(tag + "\n")
             with open(os.path.join(local_root, "done"), "w") as f:

@@ -104,9 +104,18 @@ class ResumableBatchSampler(Sampler):
         self.drop_last, self.shuffle, self.seed = drop_last, shuffle, seed
         self.pad_to_global_batch = False      # with drop_last=False: fill the last batch with index -1 (padding samples)
 
+    @property
+    def epoch_span(self) -> int:
+        """Samples the ``consumed_samples`` counter advances by per epoch: the counter moves one global batch per
+        step, so an epoch spans whole global batches (the remainder is dropped, or padded when ``drop_last=False``)."""
+        full = (self.total // self.gbs) * self.gbs
+        if self.drop_last or full == self.total:
+            return max(full, 1)
+        return full + self.gbs
+
     def __len__(self):
-        n = (self.total - self.consumed % max(self.total, 1))
-        return n // self.gbs if self.drop_last else (n + self.gbs - 1) // self.gbs
+        offset = self.consumed % self.epoch_span
+        return (self.epoch_span - offset) // self.gbs
 
     def _order(self, epoch: int) -> List[int]:
         if not self.shuffle:
@@ -116,8 +125,8 @@ class ResumableBatchSampler(Sampler):
         return torch.randperm(self.total, generator=g).tolist()
 
     def __iter__(self) -> Iterator[List[int]]:
-        epoch = self.consumed // max(self.total, 1)
-        offset = self.consumed % max(self.total, 1)
+        epoch = self.consumed // self.epoch_span
+        offset = self.consumed % self.epoch_span
         order = self._order(epoch)
         i = offset
         while i + self.gbs <= self.total:

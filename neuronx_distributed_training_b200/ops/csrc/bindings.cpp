@@ -61,6 +61,8 @@ void embedding_bwd_(at::Tensor dw, const at::Tensor& ids, const at::Tensor& g, i
 std::vector<at::Tensor> flash_attn_bwd_preview(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k,
                                                const at::Tensor& v, const at::Tensor& out, const at::Tensor& lse,
                                                bool causal, int64_t window, double scale);
+std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+                                       const at::Tensor& out, const at::Tensor& lse, bool causal, int64_t window, double scale);
 std::vector<at::Tensor> fp8_quantize_rows(const at::Tensor& x);
 std::vector<at::Tensor> fp8_quantize_cols_transposed(const at::Tensor& x);
 void gemm_fp8(const at::Tensor& a_q, const at::Tensor& a_scale, const at::Tensor& b_q, const at::Tensor& b_scale,
@@ -85,6 +87,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("qkv_rope_split_bwd", &qkv_rope_split_bwd);
   m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 causal flash attention forward (head_dim 128)");
   m.def("flash_attn_fwd1", &flash_attn_fwd1, "single-tile forward kernel (any multiple of 128)");
+  m.def("flash_attn_bwd", &flash_attn_bwd,
+        "tcgen05 flash attention backward: transposed scores, P^T in TMEM, software-pipelined (training path)");
   m.def("flash_attn_bwd_preview", &flash_attn_bwd_preview,
         "tcgen05 causal flash attention backward (preview: compiled, not yet validated on hardware)");
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");

@@ -1,0 +1,539 @@
+// Flash attention BACKWARD, second generation, for sm_100a (head_dim 128, GQA-native; causal with optional sliding
+// window, or full attention).  This is the kernel on the training path (reference call site: the NKI flash kernel's
+// backward behind src/neuronx_distributed_training/models/hf_models/modeling_llama.py:482-489).
+//
+// One CTA owns one 128-key block j of one (batch, kv head) and walks over 64-query chunks of every query head of the GQA
+// group, so dK_j / dV_j accumulate in tensor memory over the whole walk and are written once.  Everything is computed
+// TRANSPOSED (TMEM lane = key), which lets P^T feed the dV product straight from tensor memory:
+//     S^T  = K_j Q_i^T          A = K  (smem, K-major)     B = Q  (smem, K-major)     -> TMEM S buffer (double buffered)
+//     dP^T = V_j dO_i^T         A = V  (smem, K-major)     B = dO (smem, K-major)     -> TMEM dP
+//   compute warps (thread = key row):  P^T = exp2(S^T c - LSE_i) -> bf16, written over S^T in TMEM;
+//                                      dS^T = P^T o (dP^T - Delta_i) scale -> bf16 tile in shared memory (double buffered)
+//     dV  += P^T  dO_i          A = P^T (TMEM)             B = dO (smem, MN-major)
+//     dK  += dS^T Q_i           A = dS^T (smem, K-major)   B = Q  (smem, MN-major)
+//     dQ^T = K_j^T dS^T         A = K  (smem, MN-major)    B = dS^T (smem, MN-major)  -> TMEM dQ (lane = head-dim index)
+//   writer warps: dQ^T TMEM -> registers -> fp32 staging tile [64 q x 128 d] -> TMA reduce-add into the fp32 dQ
+//   accumulator (other key blocks add to the same rows).
+// The five GEMMs of step t are software-pipelined against the compute warps: S^T(t+1) is issued before dV(t), and
+// dP^T(t+1) as soon as dS^T(t) exists, so the tensor core always has the next scores ready while the exponentials run.
+//
+//   warps 0..3   compute (P, dS) + final dK / dV epilogue        warps 4..7   dQ writers
+//   warp  8      TMA producer (K, V once; Q_i, dO_i, LSE_i, Delta_i through a 3-stage ring)
+//   warp  9      tcgen05 issuer                                   warps 10,11  pad the third warpgroup (setmaxnreg)
+// Tensor memory (512 columns): [0,64) S^T/P^T even, [64,128) S^T/P^T odd, [128,192) dP^T, [192,256) dQ^T,
+// [256,384) dV, [384,512) dK.
+// A small pre-pass produces, per (batch, head, query):  -LSE log2(e)  and  -Delta scale  with Delta = rowsum(dO o O).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "sm100_ptx.cuh"
+#include "tma_utils.h"
+
+namespace fab2 {
+
+using namespace sm100;
+
+constexpr int BQ = 64;           // query rows per step
+constexpr int BN = 128;          // keys per CTA
+constexpr int D = 128;           // head dim
+constexpr int KV_TILE = 128 * 128 * 2;        // K / V tile: two [128 x 64] swizzle chunks of 16 KB
+constexpr int KV_CHUNK = 128 * 64 * 2;
+constexpr int Q_TILE = 64 * 128 * 2;          // Q / dO tile: two [64 x 64] swizzle chunks of 8 KB
+constexpr int Q_CHUNK = 64 * 64 * 2;
+constexpr int DS_TILE = 128 * 64 * 2;         // dS^T tile: one [128 keys x 64 q] swizzle chunk
+constexpr int DQ_STAGE = 64 * 128 * 4;        // fp32 [64 q x 128 d] as four [64 x 32] chunks of 8 KB
+constexpr int DQ_CHUNK = 64 * 32 * 4;
+constexpr int NS = 3;                         // Q / dO ring stages
+constexpr int STAT_BYTES = 2 * BQ * 4;        // per stage: 64 x (-LSE log2 e), 64 x (-Delta scale)
+constexpr int NUM_THREADS = 384;
+constexpr int SMEM_BYTES = 2 * KV_TILE + NS * 2 * Q_TILE + 2 * DS_TILE + DQ_STAGE + NS * STAT_BYTES + 256 + 1024;
+
+struct Params {
+  int B, S, Hq, Hk;
+  int num_kblocks;         // S / 128
+  int window;              // 0 = none
+  int causal;
+  float scale;             // softmax scale
+  float scale_log2;        // scale * log2(e)
+  const float* nlse2;      // [B, Hq, S]  -LSE * log2(e)   (-inf for rows without any visible key)
+  const float* nds;        // [B, Hq, S]  -Delta * scale
+};
+
+// ---- shared-memory matrix descriptors (128B swizzle); `rows_chunk_bytes` = bytes of one 64-column chunk of the tile ----
+__device__ __forceinline__ uint64_t desc_k(uint32_t tile, int kk, int chunk_bytes) {
+  // K-major operand: kk = 16-element step along the contiguous dimension (4 steps per 64-column chunk)
+  return make_smem_desc_sw128(tile + (kk >> 2) * chunk_bytes + (kk & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int kk, int chunk_bytes) {
+  // MN-major operand: rows of the tile are the reduction index (16 rows = 2048 bytes per step), the 64-column chunks
+  // are groups along M / N
+  return make_smem_desc_sw128(tile + kk * 2048, chunk_bytes, 1024);
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// pre-pass: one warp per (b, s, h) row of 128 elements
+//   nds[b, h, s]   = -scale * sum_d dO[b, s, h, d] * O[b, s, h, d]
+//   nlse2[b, h, s] = -lse[b, h, s] * log2(e)        (-inf when lse = -inf)
+__global__ void __launch_bounds__(256) flash_bwd2_prep_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                              const __nv_bfloat16* __restrict__ out,
+                                                              const float* __restrict__ lse, float* __restrict__ nds,
+                                                              float* __restrict__ nlse2, int B, int S, int H, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t rows = (int64_t)B * S * H;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const uint2 a = *reinterpret_cast<const uint2*>(dout + r * D + lane * 4);
+    const uint2 b = *reinterpret_cast<const uint2*>(out + r * D + lane * 4);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pb[i]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const int64_t h = r % H, bs = r / H;
+      const int64_t s = bs % S, b_ = bs / S;
+      const int64_t idx = (b_ * H + h) * S + s;
+      nds[idx] = -acc * scale;
+      const float l = lse[idx];
+      nlse2[idx] = (l == -INFINITY) ? -INFINITY : -l * 1.4426950408889634f;
+    }
+  }
+}
+
+// fp32 dQ accumulator -> bf16
+__global__ void __launch_bounds__(256) flash_bwd2_cast_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    out[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                  const __grid_constant__ CUtensorMap tma_dq, const __grid_constant__ CUtensorMap tma_dk,
+                  const __grid_constant__ CUtensorMap tma_dv, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KV_TILE;
+  uint8_t* sQ = sV + KV_TILE;                   // [NS]
+  uint8_t* sdO = sQ + NS * Q_TILE;              // [NS]
+  uint8_t* sdS = sdO + NS * Q_TILE;             // [2]
+  uint8_t* sdQ = sdS + 2 * DS_TILE;             // fp32 staging
+  float* sStat = reinterpret_cast<float*>(sdQ + DQ_STAGE);       // [NS][2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + NS * STAT_BYTES);
+  uint64_t* kv_full = bars;            // 1
+  uint64_t* ring_full = bars + 1;      // [NS]
+  uint64_t* ring_empty = bars + 4;     // [NS]
+  uint64_t* s_full = bars + 7;         // [2]
+  uint64_t* dp_full = bars + 9;        // 1
+  uint64_t* p_full = bars + 10;        // 1   (4 warps arrive)
+  uint64_t* ds_full = bars + 11;       // [2] (4 warps arrive)
+  uint64_t* ds_free = bars + 13;       // [2]
+  uint64_t* dq_full = bars + 15;       // 1
+  uint64_t* dq_free = bars + 16;       // 1   (4 warps arrive)
+  uint64_t* dkv_full = bars + 17;      // 1
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int j = blockIdx.x;                      // key block (block 0 has the longest walk and is scheduled first)
+  const int kv_head = blockIdx.y, batch = blockIdx.z;
+  const int rep = p.Hq / p.Hk;
+  const int k0 = j * BN;
+  const int n_chunks = p.S / BQ;
+  const int i_lo = p.causal ? 2 * j : 0;         // first 64-query chunk that sees this key block
+  int i_hi = n_chunks - 1;
+  if (p.window > 0) i_hi = min(i_hi, (k0 + BN - 1 + p.window - 1) / BQ);
+  const int n_i = i_hi - i_lo + 1;
+  const int steps = rep * n_i;
+  const int row_base = batch * p.S;
+
+  if (warp_idx == 8 && elect_one()) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
+    tma_prefetch_desc(&tma_dq); tma_prefetch_desc(&tma_dk); tma_prefetch_desc(&tma_dv);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 4); mbar_init(&ds_free[i], 1); }
+    mbar_init(dp_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 4);
+    mbar_init(dkv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 9) {
+    tmem_alloc<1>(tmem_ptr, 512);
+    tmem_relinquish<1>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 192, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
+
+  if (warp_idx == 8) {
+    // =========================== TMA producer ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * KV_TILE);
+      tma_load_2d(sK, &tma_k, kv_full, kv_head * D, row_base + k0);
+      tma_load_2d(sK + KV_CHUNK, &tma_k, kv_full, kv_head * D + 64, row_base + k0);
+      tma_load_2d(sV, &tma_v, kv_full, kv_head * D, row_base + k0);
+      tma_load_2d(sV + KV_CHUNK, &tma_v, kv_full, kv_head * D + 64, row_base + k0);
+      for (int t = 0; t < steps; ++t) {
+        const int st = t % NS;
+        const int head = kv_head * rep + t / n_i;
+        const int q0 = (i_lo + t % n_i) * BQ;
+        mbar_wait(&ring_empty[st], ((t / NS) & 1) ^ 1);
+        mbar_expect_tx(&ring_full[st], 2 * Q_TILE + STAT_BYTES);
+        tma_load_2d(sQ + st * Q_TILE, &tma_q, &ring_full[st], head * D, row_base + q0);
+        tma_load_2d(sQ + st * Q_TILE + Q_CHUNK, &tma_q, &ring_full[st], head * D + 64, row_base + q0);
+        tma_load_2d(sdO + st * Q_TILE, &tma_do, &ring_full[st], head * D, row_base + q0);
+        tma_load_2d(sdO + st * Q_TILE + Q_CHUNK, &tma_do, &ring_full[st], head * D + 64, row_base + q0);
+        const size_t stat = ((size_t)batch * p.Hq + head) * p.S + q0;
+        bulk_g2s(sStat + st * 2 * BQ, p.nlse2 + stat, BQ * 4, &ring_full[st]);
+        bulk_g2s(sStat + st * 2 * BQ + BQ, p.nds + stat, BQ * 4, &ring_full[st]);
+      }
+    }
+  } else if (warp_idx == 9) {
+    // =========================== MMA issuer ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, false, false);     // S^T, dP^T   [128 x 64], K = 128
+    constexpr uint32_t idesc_dv = make_idesc_bf16(128, D, false, true);      // dV (A in TMEM), dK   [128 x 128], K = 64
+    constexpr uint32_t idesc_dq = make_idesc_bf16(128, BQ, true, true);      // dQ^T        [128 x 64], K = 128
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_base = smem_u32(sQ), do_base = smem_u32(sdO);
+    const uint32_t ds_base = smem_u32(sdS);
+    auto issue_s = [&](int t) {          // S^T(t) -> buffer t & 1
+      const int st = t % NS;
+      mbar_wait(&ring_full[st], (t / NS) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t q_addr = q_base + st * Q_TILE;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16<1>(tmem_base + (t & 1) * BQ, desc_k(k_addr, kk, KV_CHUNK), desc_k(q_addr, kk, Q_CHUNK), idesc_s, kk != 0);
+        umma_commit(&s_full[t & 1]);
+      }
+      __syncwarp();
+    };
+    auto issue_dp = [&](int t) {         // dP^T(t); the ring stage has been waited for by issue_s(t)
+      const int st = t % NS;
+      if (elect_one()) {
+        const uint32_t do_addr = do_base + st * Q_TILE;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16<1>(tmem_dp, desc_k(v_addr, kk, KV_CHUNK), desc_k(do_addr, kk, Q_CHUNK), idesc_s, kk != 0);
+        umma_commit(dp_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    issue_s(0);
+    issue_dp(0);
+    for (int t = 0; t < steps; ++t) {
+      const int st = t % NS, b = t & 1;
+      if (t + 1 < steps) issue_s(t + 1);
+      // dV += P^T dO
+      mbar_wait(p_full, t & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t do_addr = do_base + st * Q_TILE;
+#pragma unroll
+        for (int kk = 0; kk < BQ / 16; ++kk)
+          umma_f16_ts(tmem_dv, tmem_base + b * BQ + kk * 8, desc_mn(do_addr, kk, Q_CHUNK), idesc_dv, (t | kk) != 0);
+      }
+      __syncwarp();
+      mbar_wait(&ds_full[b], (t >> 1) & 1);     // dS^T(t) is in shared memory, dP^T(t) has been read
+      tcgen05_fence_after();
+      if (t + 1 < steps) issue_dp(t + 1);
+      mbar_wait(dq_free, (t & 1) ^ 1);          // dQ^T(t-1) has left tensor memory
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t q_addr = q_base + st * Q_TILE, ds_addr = ds_base + b * DS_TILE;
+#pragma unroll
+        for (int kk = 0; kk < BQ / 16; ++kk)     // dK += dS^T Q   (reduction over the 64 queries)
+          umma_f16<1>(tmem_dk, desc_k(ds_addr, kk, DS_TILE), desc_mn(q_addr, kk, Q_CHUNK), idesc_dv, (t | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk)     // dQ^T = K^T dS^T   (reduction over the 128 keys)
+          umma_f16<1>(tmem_dq, desc_mn(k_addr, kk, KV_CHUNK), desc_mn(ds_addr, kk, DS_TILE), idesc_dq, kk != 0);
+        umma_commit(dq_full);
+        umma_commit(&ring_empty[st]);
+        umma_commit(&ds_free[b]);
+        if (t + 1 == steps) umma_commit(dkv_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx >= 10) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  } else if (warp_idx >= 4) {
+    // =========================== dQ writers (thread = head-dim index) ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    const uint32_t qd = warp_idx & 3;
+    const uint32_t dcol = qd * 32 + lane;
+    const uint32_t lane_off = (qd * 32u) << 16;
+    const bool issuer = threadIdx.x == 128;
+    uint8_t* my = sdQ + qd * DQ_CHUNK + lane * 4;          // chunk = 32 head-dim columns, row = query (128 bytes)
+    for (int t = 0; t < steps; ++t) {
+      const int head = kv_head * rep + t / n_i;
+      const int q0 = (i_lo + t % n_i) * BQ;
+      mbar_wait(dq_full, t & 1);
+      tcgen05_fence_after();
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(tmem_dq + lane_off, v[0]);
+      tmem_ld_32x32b_x32(tmem_dq + lane_off + 32, v[1]);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      // the previous reduce has finished reading the staging tile (its issuer waited before arriving here)
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) *reinterpret_cast<uint32_t*>(my + (h * 32 + e) * 128) = v[h][e];
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+      if (issuer) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_reduce_add_2d(&tma_dq, sdQ + c * DQ_CHUNK, head * D + c * 32, row_base + q0);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  } else {
+    // =========================== compute: P^T, dS^T (thread = key row) ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const uint32_t qd = warp_idx & 3;
+    const uint32_t row = qd * 32 + lane;
+    const uint32_t lane_off = (qd * 32u) << 16;
+    const int kpos = k0 + (int)row;
+    const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), scl2 = pack2(p.scale, p.scale);
+    for (int t = 0; t < steps; ++t) {
+      const int st = t % NS, b = t & 1;
+      const int q0 = (i_lo + t % n_i) * BQ;
+      const float4* nl4 = reinterpret_cast<const float4*>(sStat + st * 2 * BQ);
+      const float4* nd4 = nl4 + BQ / 4;
+      mbar_wait(&ring_full[st], (t / NS) & 1);              // LSE / Delta of this chunk are in shared memory
+      mbar_wait(&s_full[b], (t >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + b * BQ, sr[0]);
+      tmem_ld_32x32b_x32(tmem_base + lane_off + b * BQ + 32, sr[1]);
+      tmem_ld_wait();
+      // masks: causal -> key after the query; window -> key at or before (query - window)
+      const bool need_mask = (p.causal && q0 < k0 + BN) || (p.window > 0 && k0 <= q0 + BQ - 1 - p.window);
+      float pf[BQ];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 nl = nl4[h * 8 + g];
+          float x0, x1, x2, x3;
+          unpack2(ffma2(pack2(__uint_as_float(sr[h][4 * g]), __uint_as_float(sr[h][4 * g + 1])), sc2, pack2(nl.x, nl.y)), x0, x1);
+          unpack2(ffma2(pack2(__uint_as_float(sr[h][4 * g + 2]), __uint_as_float(sr[h][4 * g + 3])), sc2, pack2(nl.z, nl.w)), x2, x3);
+          pf[h * 32 + 4 * g + 0] = ex2(x0);
+          pf[h * 32 + 4 * g + 1] = ex2(x1);
+          pf[h * 32 + 4 * g + 2] = ex2(x2);
+          pf[h * 32 + 4 * g + 3] = ex2(x3);
+        }
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < BQ; ++c) {
+          const int q_pos = q0 + c;
+          if ((p.causal && kpos > q_pos) || (p.window > 0 && kpos <= q_pos - p.window)) pf[c] = 0.f;
+        }
+      }
+      {
+        uint32_t pk[2][16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[h][e] = pack_bf16x2(pf[h * 32 + 2 * e], pf[h * 32 + 2 * e + 1]);
+        tmem_st_32x32b_x16(tmem_base + lane_off + b * BQ, pk[0]);
+        tmem_st_32x32b_x16(tmem_base + lane_off + b * BQ + 16, pk[1]);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- dS^T = P^T o (dP^T - Delta) * scale ----
+      mbar_wait(dp_full, t & 1);
+      tcgen05_fence_after();
+      uint32_t dr[2][32];
+      tmem_ld_32x32b_x32(tmem_dp + lane_off, dr[0]);
+      tmem_ld_32x32b_x32(tmem_dp + lane_off + 32, dr[1]);
+      tmem_ld_wait();
+      mbar_wait(&ds_free[b], ((t >> 1) & 1) ^ 1);          // the MMAs that read this dS^T buffer two steps ago have retired
+      uint8_t* dsrow = sdS + b * DS_TILE + row * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                       // 8 queries = one 16-byte group
+          const float4 nda = nd4[h * 8 + 2 * g], ndb = nd4[h * 8 + 2 * g + 1];
+          const int c = h * 32 + 8 * g;
+          float e[8];
+          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 0]), __uint_as_float(dr[h][8 * g + 1])), scl2, pack2(nda.x, nda.y)),
+                        pack2(pf[c + 0], pf[c + 1])), e[0], e[1]);
+          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 2]), __uint_as_float(dr[h][8 * g + 3])), scl2, pack2(nda.z, nda.w)),
+                        pack2(pf[c + 2], pf[c + 3])), e[2], e[3]);
+          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 4]), __uint_as_float(dr[h][8 * g + 5])), scl2, pack2(ndb.x, ndb.y)),
+                        pack2(pf[c + 4], pf[c + 5])), e[4], e[5]);
+          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 6]), __uint_as_float(dr[h][8 * g + 7])), scl2, pack2(ndb.z, ndb.w)),
+                        pack2(pf[c + 6], pf[c + 7])), e[6], e[7]);
+          uint4 o;
+          o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+          o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+          const int g16 = h * 4 + g;                        // 16-byte group 0..7 within the 128-byte row
+          *reinterpret_cast<uint4*>(dsrow + ((g16 ^ (row & 7)) * 16)) = o;
+        }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[b]);
+    }
+    // ---------------- dV_j, dK_j: TMEM -> bf16 -> smem (the V / K tiles are free) -> TMA store ----------------
+    mbar_wait(dkv_full, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t src = which == 0 ? tmem_dv : tmem_dk;
+      uint8_t* orow = (which == 0 ? sV : sK) + row * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(src + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          const int c16 = c * 4 + g;
+          const int chunk = c16 >> 3, j16 = c16 & 7;
+          *reinterpret_cast<uint4*>(orow + chunk * KV_CHUNK + ((j16 ^ (row & 7)) * 16)) = o;
+        }
+      }
+    }
+    tcgen05_fence_before();
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+      tma_store_2d(&tma_dv, sV, kv_head * D, row_base + k0);
+      tma_store_2d(&tma_dv, sV + KV_CHUNK, kv_head * D + 64, row_base + k0);
+      tma_store_2d(&tma_dk, sK, kv_head * D, row_base + k0);
+      tma_store_2d(&tma_dk, sK + KV_CHUNK, kv_head * D + 64, row_base + k0);
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 9) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace fab2
+
+// dout / q / out [B,S,Hq,128], k / v [B,S,Hk,128] bf16 contiguous, lse [B,Hq,S] fp32 (natural log, from the forward).
+// Returns (dq [B,S,Hq,128], dk, dv [B,S,Hk,128]) in bf16.
+std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k,
+                                       const at::Tensor& v, const at::Tensor& out, const at::Tensor& lse,
+                                       bool causal, int64_t window, double scale) {
+  using namespace fab2;
+  TORCH_CHECK(causal || window == 0, "flash_attn_bwd: a sliding window needs causal attention");
+  for (const at::Tensor* t : {&dout, &q, &k, &v, &out})
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kBFloat16 && t->is_contiguous() && t->dim() == 4 && t->size(3) == D,
+                "flash_attn_bwd: contiguous bf16 [B,S,H,128] tensors required");
+  const int B = q.size(0), S = q.size(1), Hq = q.size(2), Hk = k.size(2);
+  TORCH_CHECK(k.size(1) == S && v.size(1) == S && v.size(2) == Hk && Hq % Hk == 0 && S % BN == 0);
+  TORCH_CHECK(dout.sizes() == q.sizes() && out.sizes() == q.sizes());
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)B * Hq * S);
+  c10::cuda::CUDAGuard guard(q.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  auto stats = at::empty({2, B, Hq, S}, q.options().dtype(at::kFloat));
+  float* nds = stats.data_ptr<float>();
+  float* nlse2 = nds + (int64_t)B * Hq * S;
+  {
+    const int64_t rows = (int64_t)B * S * Hq;
+    const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
+    flash_bwd2_prep_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dout.data_ptr(), (const __nv_bfloat16*)out.data_ptr(),
+                                                     lse.data_ptr<float>(), nds, nlse2, B, S, Hq, (float)scale);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+  }
+  auto dq_acc = at::empty({B, S, Hq, D}, q.options().dtype(at::kFloat));
+  C10_CUDA_CHECK(cudaMemsetAsync(dq_acc.data_ptr(), 0, dq_acc.numel() * sizeof(float), stream));
+  auto dq = at::empty_like(q);
+  auto dk = at::empty_like(k), dv = at::empty_like(v);
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const uint64_t rows = (uint64_t)B * S;
+  CUtensorMap tq = tma::make_2d(q.data_ptr(), BF, 2, rows, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, BQ, 64);
+  CUtensorMap tdo = tma::make_2d(dout.data_ptr(), BF, 2, rows, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, BQ, 64);
+  CUtensorMap tk = tma::make_2d(k.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tdk = tma::make_2d(dk.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tdv = tma::make_2d(dv.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tdq = tma::make_2d(dq_acc.data_ptr(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, (uint64_t)Hq * D,
+                                 (uint64_t)Hq * D * 4, BQ, 32, /*swizzle128=*/false);
+  Params p;
+  p.B = B; p.S = S; p.Hq = Hq; p.Hk = Hk; p.num_kblocks = S / BN; p.window = (int)window;
+  p.causal = causal ? 1 : 0;
+  p.scale = (float)scale;
+  p.scale_log2 = (float)(scale * 1.4426950408889634);
+  p.nlse2 = nlse2;
+  p.nds = nds;
+  static bool once = false;
+  if (!once) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    once = true;
+  }
+  dim3 grid(p.num_kblocks, Hk, B);      // key block 0 has the longest query walk and is scheduled first
+  flash_bwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  {
+    const int64_t n4 = dq_acc.numel() / 4;
+    const int grid2 = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)sms * 16);
+    flash_bwd2_cast_kernel<<<grid2, 256, 0, stream>>>((const float4*)dq_acc.data_ptr(), (uint2*)dq.data_ptr(), n4);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+  }
+  return {dq, dk, dv};
+}

@@ -513,16 +513,8 @@ class GQAQKVColumnParallelLinear(nn.Module):
         if heads_per_rank >= self.kv_size_multiplier:
             return  # every rank holds all replicas of its heads locally: handled in-rank
         reps = int(round(self.kv_size_multiplier / max(heads_per_rank, 1)))
-        # all TP groups of the world must create their groups collectively, in the same order
-        world_tp_groups = ps.enumerate_groups(ps.get_world_size(), ps.get_tensor_model_parallel_size(),
-                                              ps.get_pipeline_model_parallel_size(),
-                                              ps.get_context_model_parallel_size())["tp"]
-        for tpg in world_tp_groups:
-            for i in range(0, tp, reps):
-                sub = tpg[i:i + reps]
-                g = dist.new_group(ranks=sub)
-                if ps.get_rank() in sub:
-                    self._kv_replica_group = g
+        # one shared set of groups per (layout, reps), created once in parallel/state.py -- not one per layer
+        self._kv_replica_group, _ = ps.get_kv_replica_group(reps)
         if self._kv_replica_group is not None:
             # their gradients get one more reduction after backward: not eligible for an early data-parallel reduce
             for p in ((self.weight_qkv,) if self.fuse_qkv else (self.weight_k, self.weight_v)):

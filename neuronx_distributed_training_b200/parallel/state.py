@@ -174,8 +174,36 @@ def get_token_shuffle_group(size: int):
     return mine
 
 
+_KV_REPLICA_GROUPS: Dict[int, Tuple[object, List[int]]] = {}
+
+
+def get_kv_replica_group(reps: int):
+    """Process group of ``reps`` consecutive tensor-parallel ranks that hold replicas of the same logical KV head
+    (``kv_size_multiplier`` / ``kv_replicator``).  ONE set of groups per (layout, reps) for the whole model: every
+    attention layer looks the shared group up here, so the number of communicators does not grow with the layer
+    count and pipeline stages with different layer counts issue identical ``new_group`` sequences (the groups are
+    created collectively on first use; every rank builds at least one attention layer)."""
+    reps = int(reps)
+    if reps <= 1 or not dist.is_initialized() or _G.world_size == 1:
+        return None, []
+    if reps in _KV_REPLICA_GROUPS:
+        return _KV_REPLICA_GROUPS[reps]
+    if _G.tp % reps != 0:
+        raise ValueError(f"KV replica group size {reps} must divide the tensor-parallel size {_G.tp}")
+    mine = (None, [])
+    for ranks in enumerate_groups(_G.world_size, _G.tp, _G.pp, _G.cp, _G.ep)["tp"]:
+        for i in range(0, len(ranks), reps):
+            sub = ranks[i:i + reps]
+            g = dist.new_group(ranks=sub)
+            if _G.rank in sub:
+                mine = (g, sub)
+    _KV_REPLICA_GROUPS[reps] = mine
+    return mine
+
+
 def destroy_model_parallel() -> None:
     _SHUFFLE_GROUPS.clear()
+    _KV_REPLICA_GROUPS.clear()
     global _G
     _GROUPS.clear()
     _GROUP_RANKS.clear()

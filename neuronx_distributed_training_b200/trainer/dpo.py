@@ -57,12 +57,20 @@ def dpo_loss(pi_c, pi_r, ref_c, ref_r, beta: float, loss_type: str = "sigmoid", 
     return loss.mean(), chosen_rewards, rejected_rewards
 
 
+def _reject_context_parallel(module, what: str) -> None:
+    """Sequence log-probs sum over the whole sequence; with the sequence split over CP ranks the per-rank partial sums
+    would have to be reduced before the sigmoid.  The reference runs its alignment recipes with CP = 1 only."""
+    if getattr(module, "dims", None) is not None and module.dims.cp > 1:
+        raise ValueError(f"{what} does not support context_parallel_size > 1; set distributed_strategy.context_parallel_size=1")
+
+
 class DPOBaseModel:
     @staticmethod
     @torch.no_grad()
     def on_train_start(module, trainer):
         """Pre-compute reference log-probs with the frozen initial policy and add them as dataset columns."""
         dcfg = module.cfg.model_alignment_strategy.dpo
+        _reject_context_parallel(module, "DPO")
         if not bool(dcfg.get("precompute_ref_log_probs", True)):
             return
         dm = trainer.datamodule
@@ -96,6 +104,7 @@ class DPOBaseModel:
     @staticmethod
     def model_fwd_calc_loss(module, batch: Dict[str, torch.Tensor]):
         dcfg = module.cfg.model_alignment_strategy.dpo
+        _reject_context_parallel(module, "DPO")
         beta = float(dcfg.get("kl_beta", dcfg.get("beta", 0.1)))
         pi_c, pi_r = sequence_logps(module.model, concatenated_inputs(batch))
         ref_c = batch["reference_chosen_logps"].to(pi_c.dtype)

@@ -109,6 +109,12 @@ class MegatronGPTModel(MegatronBaseModel):
     def build_model(self):
         g = self._gpt_config()
         self.gpt_config = g
+        if self.dims.cp > 1:
+            # the reference offers context parallelism for HF-Llama only (ring attention lives in modeling_llama.py:483-484);
+            # the Megatron attention has no ring path and its datasets hand out pre-shifted labels, so a sequence split
+            # here would silently train chunk-local attention on doubly shifted labels
+            raise ValueError("context_parallel_size > 1 is not supported for Megatron-GPT models (HF-Llama only); "
+                             "set distributed_strategy.context_parallel_size=1")
         if self.dims.pp > 1 and g.share_embeddings_and_output_weights:
             raise ValueError("tied embeddings are not supported with pipeline parallelism; set "
                              "model.share_embeddings_and_output_weights=False (reference known_issues.rst:14-24)")

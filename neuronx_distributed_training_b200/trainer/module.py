@@ -447,21 +447,38 @@ class BaseModelModule:
 
     # ---- metrics -------------------------------------------------------------------------------------
     @torch.no_grad()
-    def parameter_norm(self) -> torch.Tensor:
-        """L2 norm over de-duplicated params across TP / CP / PP (reference base.py:397-452)."""
+    def parameter_norm(self, norm_type: float = 2.0) -> torch.Tensor:
+        """p-norm (``math.inf`` for the max norm) of the model parameters, every logical element counted once:
+        tensor-parallel duplicates and KV-head replicas are filtered, then the partial results are reduced over the
+        TP, CP and PP groups in that order, as the reference does (base.py:397-452).  Parameters are REPLICATED over
+        the context-parallel group, so the CP reduction is a MAX for the inf-norm and SUM / cp for p-norms (the
+        reference's plain SUM over CP counts every element cp times)."""
+        import math
         tp_rank = ps.get_tensor_model_parallel_rank()
+        norm_type = float(norm_type)
         total = torch.zeros((), dtype=torch.float32, device=self.device)
         for _, p in self.local_named_parameters():
             if param_is_tp_duplicate(p) and tp_rank != 0:
                 continue
-            total += p.detach().float().pow(2).sum()
+            x = p.detach().float()
+            if norm_type == math.inf:
+                total = torch.maximum(total, x.abs().max())
+                continue
+            total += x.pow(2).sum() if norm_type == 2.0 else x.abs().pow(norm_type).sum()
             dup = getattr(p, "norm_duplicate_range", None)          # KV-head replica rows another rank already counts
             if dup is not None:
-                total -= p.detach().reshape(-1)[dup[0]:dup[1]].float().pow(2).sum()
-        for grp in (ps.get_tensor_model_parallel_group(), ps.get_pipeline_model_parallel_group()):
+                d = x.reshape(-1)[dup[0]:dup[1]]
+                total -= d.pow(2).sum() if norm_type == 2.0 else d.abs().pow(norm_type).sum()
+        op = dist.ReduceOp.MAX if norm_type == math.inf else dist.ReduceOp.SUM
+        for kind, grp in (("tp", ps.get_tensor_model_parallel_group()), ("cp", ps.get_context_model_parallel_group()),
+                          ("pp", ps.get_pipeline_model_parallel_group())):
             if ps.group_size(grp) > 1:
-                dist.all_reduce(total, group=grp)
-        return total.sqrt()
+                dist.all_reduce(total, op=op, group=grp)
+                if kind == "cp" and norm_type != math.inf:
+                    total /= ps.group_size(grp)
+        if norm_type == math.inf:
+            return total
+        return total.sqrt() if norm_type == 2.0 else total.pow(1.0 / norm_type)
 
     def collect_metrics(self, loss: torch.Tensor, global_step: int, consumed_samples: int) -> Dict[str, float]:
         m = {"reduced_train_loss": float(loss), "global_step": float(global_step),

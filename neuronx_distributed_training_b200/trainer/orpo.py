@@ -26,6 +26,8 @@ def orpo_loss(logp_c: torch.Tensor, logp_r: torch.Tensor, beta: float):
 class ORPOBaseModel:
     @staticmethod
     def model_fwd_calc_loss(module, batch: Dict[str, torch.Tensor]):
+        from .dpo import _reject_context_parallel
+        _reject_context_parallel(module, "ORPO")
         ocfg = module.cfg.model_alignment_strategy.orpo
         beta = float(ocfg.get("beta", 0.1))
         logp_c, logp_r = sequence_logps(module.model, concatenated_inputs(batch), average=True)

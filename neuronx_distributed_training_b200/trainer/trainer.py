@@ -79,6 +79,7 @@ class Trainer:
         self.datamodule = None
         self.should_stop = False
         self._emergency = False
+        self._sig_emergency = False
         self.logged_metrics: Dict[str, float] = {}
         self.callback_metrics: Dict[str, float] = {}
         self.step_timer = DeviceStepTimer()
@@ -90,12 +91,24 @@ class Trainer:
             if fn is not None:
                 fn(self, *args)
 
+    # ---- stop decisions are collective -------------------------------------------------------------------
+    def _agree(self, *flags: bool):
+        """MAX-reduce local stop flags over all ranks: a signal lands on ONE rank and every rank reads its own
+        clock, but leaving the step loop (and entering the checkpoint barrier) must happen on the same step
+        everywhere, otherwise the remaining ranks hang in the next step's collectives."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return tuple(bool(f) for f in flags)
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([int(bool(f)) for f in flags], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(bool(v) for v in t.tolist())
+
     # ---- signals ---------------------------------------------------------------------------------------
     def _install_signal_handlers(self):
         def handler(signum, frame):
             log.warning("signal %s received: emergency checkpoint at next step boundary, then exit", signum)
-            self._emergency = True
-            self.should_stop = True
+            self._sig_emergency = True      # acted on at the next step boundary, after all ranks have agreed
         for sig in (signal.SIGTERM, signal.SIGUSR1):
             try:
                 signal.signal(sig, handler)
@@ -353,13 +366,22 @@ class Trainer:
                         self._call("on_save_checkpoint", model)
                     if self.watchdog is not None:
                         self.watchdog.pet()          # validation / checkpointing are not part of the step budget
-                    if self.max_time is not None and time.time() - t_start > self.max_time:
+                    timed_out = self.max_time is not None and time.time() - t_start > self.max_time
+                    emergency, timed_out, stop = self._agree(self._sig_emergency, timed_out, self.should_stop)
+                    if timed_out:
                         log.info("max_time reached")
-                        self.should_stop = True
+                    if emergency:
+                        self._emergency = True
+                    self.should_stop = stop or emergency or timed_out
                     if self.should_stop:
                         break
                 self.current_epoch += 1
                 if n_batches == 0:
+                    if not self.should_stop and (self.max_steps <= 0 or self.global_step < self.max_steps):
+                        log.warning("the training dataloader yielded no batch in epoch %d (dataset of %s samples, global "
+                                    "batch %s): stopping at step %d before max_steps", self.current_epoch - 1,
+                                    getattr(getattr(loader, "dataset", None), "__len__", lambda: "?")(),
+                                    getattr(datamodule, "global_batch_size", "?"), self.global_step)
                     break
                 if self.max_epochs and self.max_epochs > 0 and self.current_epoch >= self.max_epochs:
                     break

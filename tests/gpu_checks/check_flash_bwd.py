@@ -16,7 +16,7 @@ def rel(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-9)).item()
 
 
-def one(B, S, Hq, Hk, window):
+def one(B, S, Hq, Hk, window, causal=True, fn="flash_attn_bwd"):
     C = ops.C()
     torch.manual_seed(0)
     q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16().requires_grad_(True)
@@ -24,18 +24,19 @@ def one(B, S, Hq, Hk, window):
     v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16().requires_grad_(True)
     do = torch.randn(B, S, Hq, 128, device="cuda").bfloat16()
     scale = 1.0 / math.sqrt(128)
-    ref = ops.attention_ref(q, k, v, causal=True, window=window or None, scale=scale)
+    ref = ops.attention_ref(q, k, v, causal=causal, window=window or None, scale=scale)
     ref.backward(do)
-    out, lse = C.flash_attn_fwd(q.detach(), k.detach(), v.detach(), True, window, scale)
-    dq, dk, dv = C.flash_attn_bwd_preview(do, q.detach(), k.detach(), v.detach(), out, lse, True, window, scale)
+    out, lse = C.flash_attn_fwd(q.detach(), k.detach(), v.detach(), causal, window, scale)
+    dq, dk, dv = getattr(C, fn)(do, q.detach(), k.detach(), v.detach(), out, lse, causal, window, scale)
     torch.cuda.synchronize()
     errs = (rel(dq, q.grad), rel(dk, k.grad), rel(dv, v.grad))
-    print(f"B{B} S{S} Hq{Hq} Hk{Hk} window {window}: rel err dq {errs[0]:.2e} dk {errs[1]:.2e} dv {errs[2]:.2e}", flush=True)
+    print(f"{fn} B{B} S{S} Hq{Hq} Hk{Hk} window {window} causal {causal}: rel err dq {errs[0]:.2e} dk {errs[1]:.2e} dv {errs[2]:.2e}", flush=True)
     assert all(e < 2e-2 for e in errs), errs
 
 
-def timing():
+def timing(fn="flash_attn_bwd"):
     C = ops.C()
+    bwd = getattr(C, fn)
     B, S, Hq, Hk = 1, 8192, 32, 8
     q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16()
     k = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
@@ -44,17 +45,17 @@ def timing():
     scale = 1.0 / math.sqrt(128)
     out, lse = C.flash_attn_fwd(q, k, v, True, 0, scale)
     for _ in range(3):
-        C.flash_attn_bwd_preview(do, q, k, v, out, lse, True, 0, scale)
+        bwd(do, q, k, v, out, lse, True, 0, scale)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(10):
-        C.flash_attn_bwd_preview(do, q, k, v, out, lse, True, 0, scale)
+        bwd(do, q, k, v, out, lse, True, 0, scale)
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     flops = 2.5 * 4 * B * Hq * S * S * 128 / 2          # 5 GEMMs of the backward, causal half
-    print(f"backward B1 S8192 H32/8: {ms:.3f} ms, {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
+    print(f"{fn} backward B1 S8192 H32/8: {ms:.3f} ms, {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
     qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
     o = torch.nn.functional.scaled_dot_product_attention(qq.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2),
                                                          is_causal=True, enable_gqa=True)
@@ -72,7 +73,12 @@ def timing():
 
 
 if __name__ == "__main__":
-    for cfg in [(1, 128, 1, 1, 0), (1, 256, 2, 1, 0), (2, 512, 4, 2, 0), (1, 1024, 8, 2, 0), (1, 1024, 4, 4, 300)]:
+    for cfg in [(1, 128, 1, 1, 0), (1, 256, 2, 1, 0), (2, 512, 4, 2, 0), (1, 1024, 8, 2, 0), (1, 1024, 4, 4, 300),
+                (1, 2048, 4, 1, 0), (1, 2048, 2, 2, 500)]:
         one(*cfg)
+    one(1, 512, 4, 2, 0, causal=False)
+    one(2, 1024, 2, 1, 0, causal=False)
     timing()
+    if os.environ.get("CHECK_PREVIEW"):
+        timing("flash_attn_bwd_preview")
     print("FLASH_BWD_OK")

@@ -1,6 +1,7 @@
 import json
 import os
 
+import pytest
 import torch
 
 from neuronx_distributed_training_b200.checkpoint.converter import CheckpointConverterBase, MixtralCheckpointConverter
@@ -106,3 +107,56 @@ def test_mixtral_expert_stacking_roundtrip(tmp_path):
     assert set(back) == set(hf)
     for k in hf:
         assert torch.equal(back[k], hf[k]), k
+
+
+def test_nnm_local_to_global_roundtrip(tmp_path):
+    """NNM per-rank checkpoints (stage-local layer indices, ``model.`` prefix) -> sharded layout with global indices; the
+    CLI flag ``--local_to_global_layers`` drives the same code (reference nnm_model_ckpt_to_nxdt_model_ckpt_converter.py)."""
+    import subprocess
+    import sys
+    from neuronx_distributed_training_b200.checkpoint import io as ckpt_io, nnm
+    tp, pp, n_layers = 2, 2, 4
+    src = tmp_path / "nnm"
+    truth = {}
+    for t in range(tp):
+        for p_ in range(pp):
+            d = src / nnm.nnm_worker_dir(t, p_)
+            d.mkdir(parents=True)
+            sd = {}
+            for l in range(n_layers // pp):
+                w = torch.randn(3, 5)
+                sd[f"model.language_model.encoder.layers.{l}.self_attention.dense.weight"] = w
+                truth[(t, p_, f"language_model.encoder.layers.{l + p_ * (n_layers // pp)}.self_attention.dense.weight")] = w
+            if p_ == 0:
+                e = torch.randn(7, 5)
+                sd["model.language_model.embedding.word_embeddings.weight"] = e
+                truth[(t, p_, "language_model.embedding.word_embeddings.weight")] = e
+            torch.save({"state_dict": sd, "optimizer_states": [1, 2]}, d / "model_optim_rng.ckpt")
+    assert nnm.local_to_global_key("model.language_model.encoder.layers.3.mlp.dense_h_to_4h.weight", 8) == \
+        "language_model.encoder.layers.11.mlp.dense_h_to_4h.weight"
+    assert nnm.local_to_global_key("model.language_model.encoder.final_layernorm.weight", 8) == \
+        "language_model.encoder.final_layernorm.weight"
+    out = tmp_path / "out" / "step_10"
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples",
+                          "checkpoint_converter_scripts", "megatron_ckpt_converter.py")
+    r = subprocess.run([sys.executable, script, "--local_to_global_layers", "--tp", str(tp), "--pp", str(pp), "--n_layers",
+                        str(n_layers), "--nnm_ckpt_path", str(src), "--nxdt_ckpt_path", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (out / "done").exists() and (out / "checkpoint").exists()
+    seen = 0
+    for t in range(tp):
+        for p_ in range(pp):
+            sd = ckpt_io._load_object(str(out / "model" / ckpt_io.shard_file_name(0, t, p_)))
+            for k, v in sd.items():
+                assert torch.equal(v, truth[(t, p_, k)]), k
+                seen += 1
+    assert seen == len(truth)
+    # a second conversion into the same (now non-empty) directory goes to a versioned sibling, in-process + process pool
+    out2 = nnm.convert(str(src), str(out), tp, pp, n_layers, num_processes=2)
+    assert out2.endswith("_v1") and os.path.exists(os.path.join(out2, "done"))
+    # a missing worker folder is an error, not a silent partial conversion
+    import shutil
+    shutil.rmtree(src / nnm.nnm_worker_dir(1, 1))
+    with pytest.raises(ValueError):
+        nnm.convert(str(src), str(tmp_path / "bad"), tp, pp, n_layers)

@@ -149,3 +149,38 @@ def test_preprocess_tool_roundtrip(tmp_path, monkeypatch):
     info = tool.main(["--input", str(src), "--format", "hf", "--output-dir", str(tmp_path / "arrow"), "--seq-length", "32"])
     arrow = datasets.load_from_disk(str(tmp_path / "arrow"))
     assert len(arrow) == info["sequences"] > 0 and len(arrow[0]["input_ids"]) == 32 and arrow[0]["labels"] == arrow[0]["input_ids"]
+
+
+def test_resumable_sampler_second_epoch_with_remainder():
+    """len(dataset) % global_batch != 0: an epoch consumes floor(total/gbs) global batches, the next epoch starts at
+    offset 0 again (it used to yield 0 batches and silently end training), and a mid-epoch resume continues in place."""
+    from neuronx_distributed_training_b200.data.base import ResumableBatchSampler
+    total, gbs = 1000, 64
+    per_epoch = total // gbs
+    consumed = 0
+    seen = []
+    for epoch in range(3):
+        s = ResumableBatchSampler(total, consumed, gbs, dp_rank=0, dp_size=1)
+        assert len(s) == per_epoch
+        batches = list(s)
+        assert len(batches) == per_epoch
+        assert batches[0] == list(range(gbs))
+        consumed += len(batches) * gbs
+        seen.append(batches)
+    assert seen[0] == seen[1] == seen[2]
+    # resume 5 batches into the second epoch
+    consumed = per_epoch * gbs + 5 * gbs
+    s = ResumableBatchSampler(total, consumed, gbs, dp_rank=1, dp_size=2)
+    rest = list(s)
+    assert len(rest) == len(s) == per_epoch - 5
+    assert rest[0] == list(range(5 * gbs + 32, 5 * gbs + 64))
+    # shuffled: epochs differ, resume reproduces the tail of the same epoch
+    a = list(ResumableBatchSampler(total, per_epoch * gbs, gbs, 0, 1, shuffle=True, seed=3))
+    b = list(ResumableBatchSampler(total, 0, gbs, 0, 1, shuffle=True, seed=3))
+    c = list(ResumableBatchSampler(total, per_epoch * gbs + 3 * gbs, gbs, 0, 1, shuffle=True, seed=3))
+    assert a != b and c == a[3:]
+    # drop_last=False: the padded tail batch counts as one more global batch of the epoch
+    s = ResumableBatchSampler(total, 0, gbs, 0, 1, drop_last=False)
+    assert len(s) == len(list(s)) == per_epoch + 1
+    s = ResumableBatchSampler(total, (per_epoch + 1) * gbs, gbs, 0, 1, drop_last=False)
+    assert len(list(s)) == per_epoch + 1
