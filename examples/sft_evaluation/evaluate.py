@@ -1,11 +1,14 @@
 """Generation-based evaluation of fine-tuned weights (ROUGE / exact match).
 
     python evaluate.py --config ../conf/hf_llama3_8B_SFT_config.yaml --checkpoint <dir/*.ckpt | hf dir> \
-        --data eval.jsonl --metric rouge --prompt_template "{input}" --label_template "{output}" --max_new_tokens 64
+        --data eval.jsonl --metric rouge --prompt_template "{{ input }}" --label_template "{{ output }}" \
+        --max_new_tokens 64 --batch_size 8
 
-Counterpart of the reference's examples/sft_evaluation/evaluate.py: instead of separate inference runtimes the
-fine-tuned (TP-sharded or HF-format) weights are loaded into the training model class and decoded greedily.
-Launch with torchrun when the checkpoint is TP-sharded."""
+Counterpart of the reference's examples/sft_evaluation/evaluate.py (:45-147): instead of separate inference runtimes the
+fine-tuned (TP-sharded or HF-format) weights are loaded into the training model class (HF-Llama or HF-Mixtral, chosen
+like the trainer does by ``"mixtral" in cfg.name``) and decoded in batches with a KV cache
+(``utils/generation.py:generate_cached``).  Prompt / label templates are jinja2 (``{{ field }}``), as in the reference;
+plain ``str.format`` templates (``{field}``) keep working.  Launch with torchrun when the checkpoint is TP-sharded."""
 import argparse
 import json
 import os
@@ -19,12 +22,23 @@ from neuronx_distributed_training_b200.checkpoint import io as ckpt_io  # noqa: 
 from neuronx_distributed_training_b200.checkpoint.converter import CheckpointConverterBase, load_full_state  # noqa: E402
 from neuronx_distributed_training_b200.config import ParallelDims, load_config, process_config  # noqa: E402
 from neuronx_distributed_training_b200.parallel import state as ps  # noqa: E402
-from neuronx_distributed_training_b200.utils.generation import generate  # noqa: E402
+from neuronx_distributed_training_b200.utils.generation import generate_cached  # noqa: E402
+
+
+def render(template: str, record: dict) -> str:
+    """jinja2 when the template uses ``{{ }}`` / ``{% %}``, otherwise ``str.format``."""
+    if "{{" in template or "{%" in template:
+        import jinja2
+        return jinja2.Environment(undefined=jinja2.StrictUndefined).from_string(template).render(**record)
+    return template.format(**record)
 
 
 def load_model(cfg, checkpoint: str):
-    from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
-    module = HFLlamaModule(cfg, None)
+    if "mixtral" in str(cfg.get("name", "")).lower():
+        from neuronx_distributed_training_b200.trainer.hf_mixtral_module import HFMixtralModule as Module
+    else:
+        from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule as Module
+    module = Module(cfg, None)
     module.setup("fit")
     if os.path.isdir(checkpoint) and os.path.isdir(os.path.join(checkpoint, "model")):
         sd = ckpt_io._load_object(os.path.join(checkpoint, "model", ckpt_io.shard_file_name(
@@ -57,12 +71,20 @@ def evaluate(args):
         tok = AutoTokenizer.from_pretrained(cfg.data.tokenizer.type)
     recs = [json.loads(l) for l in open(args.data) if l.strip()][: args.limit or None]
     preds, refs = [], []
-    for r in recs:
-        prompt = args.prompt_template.format(**r)
-        ids = torch.tensor([tok.encode(prompt)], device=module.device)
-        out = generate(module.model, ids, args.max_new_tokens, tok.eos_token_id)
-        preds.append(tok.decode(out[0, ids.shape[1]:].tolist(), skip_special_tokens=True))
-        refs.append(args.label_template.format(**r))
+    bs = max(1, int(args.batch_size))
+    order = sorted(range(len(recs)), key=lambda i: len(render(args.prompt_template, recs[i])))     # similar lengths per batch
+    prompts = {i: tok.encode(render(args.prompt_template, recs[i])) for i in order}
+    out_text = {}
+    for s0 in range(0, len(order), bs):
+        idx = order[s0:s0 + bs]
+        new = generate_cached(module.model, [prompts[i] for i in idx], args.max_new_tokens, tok.eos_token_id,
+                              temperature=args.temperature, top_k=args.top_k, top_p=args.top_p,
+                              pad_token_id=tok.pad_token_id if tok.pad_token_id is not None else 0)
+        for i, ids in zip(idx, new):
+            out_text[i] = tok.decode(ids, skip_special_tokens=True)
+    for i, r in enumerate(recs):
+        preds.append(out_text[i])
+        refs.append(render(args.label_template, r))
     scores = MetricFactory.create(args.metric)(preds, refs)
     if ps.get_rank() == 0:
         print(json.dumps({"n": len(preds), **scores}))
@@ -83,6 +105,10 @@ if __name__ == "__main__":
     ap.add_argument("--prompt_template", default="{input}")
     ap.add_argument("--label_template", default="{output}")
     ap.add_argument("--max_new_tokens", type=int, default=64)
+    ap.add_argument("--batch_size", type=int, default=8)
+    ap.add_argument("--temperature", type=float, default=0.0)
+    ap.add_argument("--top_k", type=int, default=0)
+    ap.add_argument("--top_p", type=float, default=1.0)
     ap.add_argument("--limit", type=int, default=0)
     ap.add_argument("--output", default=None)
     ap.add_argument("overrides", nargs="*")

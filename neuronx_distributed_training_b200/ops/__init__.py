@@ -624,6 +624,9 @@ def attention_ref(q, k, v, causal: bool = True, window: Optional[int] = None, sc
 
 
 class _FlashAttnFn(torch.autograd.Function):
+    """tcgen05 flash attention: ``flash_attn_fwd`` (two-tile ping-pong, P in TMEM) + ``flash_attn_bwd`` (transposed scores,
+    P^T in TMEM, software-pipelined).  Three launches in the backward: statistics pre-pass, main kernel, fp32->bf16 dQ."""
+
     @staticmethod
     def forward(ctx, q, k, v, causal, window, scale):
         _count()
@@ -641,26 +644,6 @@ class _FlashAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
-class _FlashAttnPreviewFn(torch.autograd.Function):
-    """Native forward + the PREVIEW native backward (``NXDT_FLASH_BWD_PREVIEW=1``; see flash_attn_bwd_sm100.cu)."""
-
-    @staticmethod
-    def forward(ctx, q, k, v, causal, window, scale):
-        _count()
-        o, lse = C().flash_attn_fwd(q, k, v, causal, window, scale)
-        ctx.save_for_backward(q, k, v, o, lse)
-        ctx.cfg = (causal, window, scale)
-        return o
-
-    @staticmethod
-    def backward(ctx, do):
-        q, k, v, o, lse = ctx.saved_tensors
-        causal, window, scale = ctx.cfg
-        _count(2)
-        dq, dk, dv = C().flash_attn_bwd_preview(do.contiguous(), q, k, v, o, lse, causal, window, scale)
-        return dq, dk, dv, None, None, None
-
-
 def _sdpa(q, k, v, causal, scale):
     # torch SDPA wants [B,H,S,D]
     o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
@@ -668,21 +651,22 @@ def _sdpa(q, k, v, causal, scale):
     return o.transpose(1, 2)
 
 
+def flash_attention_native_ok(q, k, window=None, causal=True) -> bool:
+    """Shapes the hand-written kernels cover: bf16, head_dim 128, equal q / k lengths that are a multiple of 128,
+    causal (optionally with a sliding window) or full attention."""
+    return (_use_native(q) and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and q.shape[1] % 128 == 0
+            and q.shape[1] == k.shape[1] and q.shape[2] % k.shape[2] == 0 and (causal or not window))
+
+
 def flash_attention(q, k, v, causal: bool = True, window: Optional[int] = None, scale: Optional[float] = None):
+    """Attention on ``[B, S, heads, D]``.  On the GPU the native kernels run forward AND backward (sliding window
+    included); the library SDPA is only the ``kernels: baseline`` arm and the fallback for shapes outside the native
+    coverage (head_dim != 128, ragged lengths)."""
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
-    native_ok = (_use_native(q) and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and causal and q.shape[1] % 128 == 0
-                 and q.shape[1] == k.shape[1] and hasattr(C(), "flash_attn_fwd"))
-    if native_ok and os.environ.get("NXDT_FLASH_BWD_PREVIEW", "0") == "1" and hasattr(C(), "flash_attn_bwd_preview"):
-        return _FlashAttnPreviewFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal,
-                                         int(window or 0), float(scale))
-    if native_ok and hasattr(C(), "flash_attn_bwd"):
-        return _FlashAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal,
-                                  int(window or 0), float(scale))
-    if native_ok and not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)):
-        _count()
-        return C().flash_attn_fwd(q.contiguous(), k.contiguous(), v.contiguous(), True, int(window or 0), float(scale))[0]
+    if flash_attention_native_ok(q, k, window, causal):
+        return _FlashAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), bool(causal), int(window or 0), float(scale))
     if q.is_cuda and (window is None or window <= 0):
-        return _sdpa(q, k, v, causal, scale)   # baseline arm: library flash attention through SDPA
+        return _sdpa(q, k, v, causal, scale)
     return attention_ref(q, k, v, causal, window, scale)
 
 

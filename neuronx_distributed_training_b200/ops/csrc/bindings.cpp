@@ -22,7 +22,7 @@ at::Tensor qkv_rope_split_bwd(const at::Tensor& dq, const at::Tensor& dk, const 
 std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
                                         int64_t window, double scale);
 std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
-                                       int64_t window, double scale);
+                                       int64_t window, double scale, int64_t q_offset);
 void ag_gemm(at::Tensor xg, const at::Tensor& x_local, const at::Tensor& b, at::Tensor out, const at::Tensor& other,
              std::vector<int64_t> xg_peer, std::vector<int64_t> flags_peer, int64_t hs_local_ptr,
              std::vector<int64_t> hs_peer, int64_t epoch, int64_t rank, int64_t tp, int64_t mode, bool b_kmajor,
@@ -62,7 +62,9 @@ std::vector<at::Tensor> flash_attn_bwd_preview(const at::Tensor& dout, const at:
                                                const at::Tensor& v, const at::Tensor& out, const at::Tensor& lse,
                                                bool causal, int64_t window, double scale);
 std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
-                                       const at::Tensor& out, const at::Tensor& lse, bool causal, int64_t window, double scale);
+                                       const at::Tensor& out, const at::Tensor& lse, bool causal, int64_t window, double scale,
+                                       int64_t q_offset);
+void flash_fwd2_set_debug(const at::Tensor& t);
 std::vector<at::Tensor> fp8_quantize_rows(const at::Tensor& x);
 std::vector<at::Tensor> fp8_quantize_cols_transposed(const at::Tensor& x);
 void gemm_fp8(const at::Tensor& a_q, const at::Tensor& a_scale, const at::Tensor& b_q, const at::Tensor& b_scale,
@@ -85,10 +87,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ce_grad_", &ce_grad_);
   m.def("qkv_rope_split_fwd", &qkv_rope_split_fwd);
   m.def("qkv_rope_split_bwd", &qkv_rope_split_bwd);
-  m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 causal flash attention forward (head_dim 128)");
+  namespace py = pybind11;
+  m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 flash attention forward (head_dim 128); q_offset / longer k, v: context parallelism",
+        py::arg("q"), py::arg("k"), py::arg("v"), py::arg("causal"), py::arg("window"), py::arg("scale"), py::arg("q_offset") = 0);
+  m.def("flash_fwd2_set_debug", &flash_fwd2_set_debug, "in-kernel clock64 timeline of CTA (0,0) of the forward kernel");
   m.def("flash_attn_fwd1", &flash_attn_fwd1, "single-tile forward kernel (any multiple of 128)");
   m.def("flash_attn_bwd", &flash_attn_bwd,
-        "tcgen05 flash attention backward: transposed scores, P^T in TMEM, software-pipelined (training path)");
+        "tcgen05 flash attention backward: transposed scores, P^T in TMEM, software-pipelined (training path)",
+        py::arg("dout"), py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("causal"),
+        py::arg("window"), py::arg("scale"), py::arg("q_offset") = 0);
   m.def("flash_attn_bwd_preview", &flash_attn_bwd_preview,
         "tcgen05 causal flash attention backward (preview: compiled, not yet validated on hardware)");
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");

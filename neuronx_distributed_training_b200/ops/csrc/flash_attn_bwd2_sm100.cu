@@ -50,8 +50,10 @@ constexpr int NUM_THREADS = 384;
 constexpr int SMEM_BYTES = 2 * KV_TILE + NS * 2 * Q_TILE + 2 * DS_TILE + DQ_STAGE + NS * STAT_BYTES + 256 + 1024;
 
 struct Params {
-  int B, S, Hq, Hk;
-  int num_kblocks;         // S / 128
+  int B, S, Hq, Hk;        // S = number of (local) queries per batch entry
+  int Sk;                  // number of keys per batch entry (the gathered sequence under context parallelism)
+  int q_off;               // absolute position of query 0 relative to key 0 (multiple of 128)
+  int num_kblocks;         // Sk / 128
   int window;              // 0 = none
   int causal;
   float scale;             // softmax scale
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256) flash_bwd2_cast_kernel(const float4* __re
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
-                  const __grid_constant__ CUtensorMap tma_dq, const __grid_constant__ CUtensorMap tma_dk,
+                  const __grid_constant__ CUtensorMap tma_dqh, const __grid_constant__ CUtensorMap tma_dk,
                   const __grid_constant__ CUtensorMap tma_dv, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,21 +172,25 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   uint64_t* dkv_full = bars + 17;      // 1
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
 
-  const int j = blockIdx.x;                      // key block (block 0 has the longest walk and is scheduled first)
-  const int kv_head = blockIdx.y, batch = blockIdx.z;
+  // key block 0 has the longest walk: key blocks vary SLOWEST in launch order (longest-processing-time-first over the
+  // whole grid), heads and batches fastest
+  const int j = blockIdx.y;
+  const int kv_head = blockIdx.x % p.Hk, batch = blockIdx.x / p.Hk;
   const int rep = p.Hq / p.Hk;
   const int k0 = j * BN;
   const int n_chunks = p.S / BQ;
-  const int i_lo = p.causal ? 2 * j : 0;         // first 64-query chunk that sees this key block
+  // local 64-query chunks whose (absolute) positions q_off + 64 i .. can see keys of this block
+  const int i_lo = p.causal ? max(0, (k0 - p.q_off) / BQ) : 0;
   int i_hi = n_chunks - 1;
-  if (p.window > 0) i_hi = min(i_hi, (k0 + BN - 1 + p.window - 1) / BQ);
-  const int n_i = i_hi - i_lo + 1;
-  const int steps = rep * n_i;
+  if (p.window > 0) i_hi = min(i_hi, (k0 + BN - 1 + p.window - 1 - p.q_off) / BQ - ((k0 + BN - 1 + p.window - 1 - p.q_off) < 0 ? 1 : 0));
+  const int n_i = max(0, i_hi - i_lo + 1);
+  const int steps = rep * n_i;                   // 0: no local query sees this key block (dK = dV = 0)
   const int row_base = batch * p.S;
+  const int krow_base = batch * p.Sk;
 
   if (warp_idx == 8 && elect_one()) {
     tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
-    tma_prefetch_desc(&tma_dq); tma_prefetch_desc(&tma_dk); tma_prefetch_desc(&tma_dv);
+    tma_prefetch_desc(&tma_dqh); tma_prefetch_desc(&tma_dk); tma_prefetch_desc(&tma_dv);
     mbar_init(kv_full, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 4); mbar_init(&ds_free[i], 1); }
@@ -210,10 +216,10 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * KV_TILE);
-      tma_load_2d(sK, &tma_k, kv_full, kv_head * D, row_base + k0);
-      tma_load_2d(sK + KV_CHUNK, &tma_k, kv_full, kv_head * D + 64, row_base + k0);
-      tma_load_2d(sV, &tma_v, kv_full, kv_head * D, row_base + k0);
-      tma_load_2d(sV + KV_CHUNK, &tma_v, kv_full, kv_head * D + 64, row_base + k0);
+      tma_load_2d(sK, &tma_k, kv_full, kv_head * D, krow_base + k0);
+      tma_load_2d(sK + KV_CHUNK, &tma_k, kv_full, kv_head * D + 64, krow_base + k0);
+      tma_load_2d(sV, &tma_v, kv_full, kv_head * D, krow_base + k0);
+      tma_load_2d(sV + KV_CHUNK, &tma_v, kv_full, kv_head * D + 64, krow_base + k0);
       for (int t = 0; t < steps; ++t) {
         const int st = t % NS;
         const int head = kv_head * rep + t / n_i;
@@ -262,8 +268,10 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       __syncwarp();
     };
     mbar_wait(kv_full, 0);
-    issue_s(0);
-    issue_dp(0);
+    if (steps > 0) {
+      issue_s(0);
+      issue_dp(0);
+    }
     for (int t = 0; t < steps; ++t) {
       const int st = t % NS, b = t & 1;
       if (t + 1 < steps) issue_s(t + 1);
@@ -305,8 +313,11 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     const uint32_t qd = warp_idx & 3;
     const uint32_t dcol = qd * 32 + lane;
     const uint32_t lane_off = (qd * 32u) << 16;
-    const bool issuer = threadIdx.x == 128;
-    uint8_t* my = sdQ + qd * DQ_CHUNK + lane * 4;          // chunk = 32 head-dim columns, row = query (128 bytes)
+    // every warp owns one staging chunk (its 32 head-dim columns x 64 queries, 8 KB) and reduces it on its own: no
+    // cross-warp barrier.  The chunk is written and reduced in two halves of 32 queries so that the stores of one half
+    // overlap the TMA read of the other.
+    const uint32_t my = smem_u32(sdQ) + qd * DQ_CHUNK + lane * 4;     // row = query (128 bytes), column = lane
+    const uint8_t* chunk = sdQ + qd * DQ_CHUNK;
     for (int t = 0; t < steps; ++t) {
       const int head = kv_head * rep + t / n_i;
       const int q0 = (i_lo + t % n_i) * BQ;
@@ -319,22 +330,22 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
-      // the previous reduce has finished reading the staging tile (its issuer waited before arriving here)
-      asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
+        // the reduce that read this half one step ago must have finished with it (at most one newer group in flight)
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) *reinterpret_cast<uint32_t*>(my + (h * 32 + e) * 128) = v[h][e];
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 4, 128;" ::: "memory");
-      if (issuer) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tma_reduce_add_2d(&tma_dq, sdQ + c * DQ_CHUNK, head * D + c * 32, row_base + q0);
-        tma_store_commit();
-        tma_store_wait_read<0>();
+        for (int e = 0; e < 32; ++e) st_shared_b32(my + (h * 32 + e) * 128, v[h][e]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tma_dqh, chunk + h * (DQ_CHUNK / 2), head * D + qd * 32, row_base + q0 + h * 32);
+          tma_store_commit();
+        }
       }
     }
-    if (issuer) tma_store_wait<0>();
+    if (lane == 0) tma_store_wait<0>();
   } else {
     // =========================== compute: P^T, dS^T (thread = key row) ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
@@ -346,8 +357,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     for (int t = 0; t < steps; ++t) {
       const int st = t % NS, b = t & 1;
       const int q0 = (i_lo + t % n_i) * BQ;
-      const float4* nl4 = reinterpret_cast<const float4*>(sStat + st * 2 * BQ);
-      const float4* nd4 = nl4 + BQ / 4;
+      const uint32_t nl_addr = smem_u32(sStat) + st * STAT_BYTES, nd_addr = nl_addr + BQ * 4;
       mbar_wait(&ring_full[st], (t / NS) & 1);              // LSE / Delta of this chunk are in shared memory
       mbar_wait(&s_full[b], (t >> 1) & 1);
       tcgen05_fence_after();
@@ -356,13 +366,14 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tmem_ld_32x32b_x32(tmem_base + lane_off + b * BQ + 32, sr[1]);
       tmem_ld_wait();
       // masks: causal -> key after the query; window -> key at or before (query - window)
-      const bool need_mask = (p.causal && q0 < k0 + BN) || (p.window > 0 && k0 <= q0 + BQ - 1 - p.window);
+      const int qa0 = p.q_off + q0;                          // absolute position of the chunk's first query
+      const bool need_mask = (p.causal && qa0 < k0 + BN) || (p.window > 0 && k0 <= qa0 + BQ - 1 - p.window);
       float pf[BQ];
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 nl = nl4[h * 8 + g];
+          const float4 nl = ld_shared_f4(nl_addr + (h * 8 + g) * 16);
           float x0, x1, x2, x3;
           unpack2(ffma2(pack2(__uint_as_float(sr[h][4 * g]), __uint_as_float(sr[h][4 * g + 1])), sc2, pack2(nl.x, nl.y)), x0, x1);
           unpack2(ffma2(pack2(__uint_as_float(sr[h][4 * g + 2]), __uint_as_float(sr[h][4 * g + 3])), sc2, pack2(nl.z, nl.w)), x2, x3);
@@ -374,7 +385,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       if (need_mask) {
 #pragma unroll
         for (int c = 0; c < BQ; ++c) {
-          const int q_pos = q0 + c;
+          const int q_pos = qa0 + c;
           if ((p.causal && kpos > q_pos) || (p.window > 0 && kpos <= q_pos - p.window)) pf[c] = 0.f;
         }
       }
@@ -399,12 +410,12 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tmem_ld_32x32b_x32(tmem_dp + lane_off + 32, dr[1]);
       tmem_ld_wait();
       mbar_wait(&ds_free[b], ((t >> 1) & 1) ^ 1);          // the MMAs that read this dS^T buffer two steps ago have retired
-      uint8_t* dsrow = sdS + b * DS_TILE + row * 128;
+      const uint32_t dsrow = smem_u32(sdS) + b * DS_TILE + row * 128;
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {                       // 8 queries = one 16-byte group
-          const float4 nda = nd4[h * 8 + 2 * g], ndb = nd4[h * 8 + 2 * g + 1];
+          const float4 nda = ld_shared_f4(nd_addr + (h * 8 + 2 * g) * 16), ndb = ld_shared_f4(nd_addr + (h * 8 + 2 * g + 1) * 16);
           const int c = h * 32 + 8 * g;
           float e[8];
           unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 0]), __uint_as_float(dr[h][8 * g + 1])), scl2, pack2(nda.x, nda.y)),
@@ -419,7 +430,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
           o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
           const int g16 = h * 4 + g;                        // 16-byte group 0..7 within the 128-byte row
-          *reinterpret_cast<uint4*>(dsrow + ((g16 ^ (row & 7)) * 16)) = o;
+          st_shared_v4(dsrow + ((g16 ^ (row & 7)) * 16), o);
         }
       tcgen05_fence_before();
       fence_proxy_async_smem();
@@ -427,17 +438,22 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       if (lane == 0) mbar_arrive(&ds_full[b]);
     }
     // ---------------- dV_j, dK_j: TMEM -> bf16 -> smem (the V / K tiles are free) -> TMA store ----------------
-    mbar_wait(dkv_full, 0);
+    if (steps > 0) mbar_wait(dkv_full, 0);
+    else mbar_wait(kv_full, 0);                  // no step ran: the accumulators were never written, the result is zero
     tcgen05_fence_after();
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t src = which == 0 ? tmem_dv : tmem_dk;
-      uint8_t* orow = (which == 0 ? sV : sK) + row * 128;
+      const uint32_t orow = smem_u32(which == 0 ? sV : sK) + row * 128;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(src + lane_off + c * 32, v);
         tmem_ld_wait();
+        if (steps == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 o;
@@ -447,7 +463,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
           const int c16 = c * 4 + g;
           const int chunk = c16 >> 3, j16 = c16 & 7;
-          *reinterpret_cast<uint4*>(orow + chunk * KV_CHUNK + ((j16 ^ (row & 7)) * 16)) = o;
+          st_shared_v4(orow + chunk * KV_CHUNK + ((j16 ^ (row & 7)) * 16), o);
         }
       }
     }
@@ -455,10 +471,10 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x == 0) {
-      tma_store_2d(&tma_dv, sV, kv_head * D, row_base + k0);
-      tma_store_2d(&tma_dv, sV + KV_CHUNK, kv_head * D + 64, row_base + k0);
-      tma_store_2d(&tma_dk, sK, kv_head * D, row_base + k0);
-      tma_store_2d(&tma_dk, sK + KV_CHUNK, kv_head * D + 64, row_base + k0);
+      tma_store_2d(&tma_dv, sV, kv_head * D, krow_base + k0);
+      tma_store_2d(&tma_dv, sV + KV_CHUNK, kv_head * D + 64, krow_base + k0);
+      tma_store_2d(&tma_dk, sK, kv_head * D, krow_base + k0);
+      tma_store_2d(&tma_dk, sK + KV_CHUNK, kv_head * D + 64, krow_base + k0);
       tma_store_commit();
       tma_store_wait<0>();
     }
@@ -473,18 +489,21 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 
 }  // namespace fab2
 
-// dout / q / out [B,S,Hq,128], k / v [B,S,Hk,128] bf16 contiguous, lse [B,Hq,S] fp32 (natural log, from the forward).
+// dout / q / out [B,S,Hq,128], k / v [B,Sk,Hk,128] bf16 contiguous (Sk >= q_offset + S: gathered keys under context
+// parallelism, query i at absolute position q_offset + i), lse [B,Hq,S] fp32 (natural log, from the forward).
 // Returns (dq [B,S,Hq,128], dk, dv [B,S,Hk,128]) in bf16.
 std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k,
                                        const at::Tensor& v, const at::Tensor& out, const at::Tensor& lse,
-                                       bool causal, int64_t window, double scale) {
+                                       bool causal, int64_t window, double scale, int64_t q_offset) {
   using namespace fab2;
   TORCH_CHECK(causal || window == 0, "flash_attn_bwd: a sliding window needs causal attention");
   for (const at::Tensor* t : {&dout, &q, &k, &v, &out})
     TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kBFloat16 && t->is_contiguous() && t->dim() == 4 && t->size(3) == D,
                 "flash_attn_bwd: contiguous bf16 [B,S,H,128] tensors required");
   const int B = q.size(0), S = q.size(1), Hq = q.size(2), Hk = k.size(2);
-  TORCH_CHECK(k.size(1) == S && v.size(1) == S && v.size(2) == Hk && Hq % Hk == 0 && S % BN == 0);
+  const int Sk = k.size(1);
+  TORCH_CHECK(v.size(1) == Sk && v.size(2) == Hk && Hq % Hk == 0 && S % BN == 0 && Sk % BN == 0 && k.size(0) == B && v.size(0) == B);
+  TORCH_CHECK(q_offset % BN == 0 && q_offset >= 0 && q_offset + S <= Sk, "flash_attn_bwd: keys must cover [0, q_offset + S)");
   TORCH_CHECK(dout.sizes() == q.sizes() && out.sizes() == q.sizes());
   TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)B * Hq * S);
   c10::cuda::CUDAGuard guard(q.device());
@@ -505,17 +524,17 @@ std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor&
   auto dq = at::empty_like(q);
   auto dk = at::empty_like(k), dv = at::empty_like(v);
   const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const uint64_t rows = (uint64_t)B * S;
+  const uint64_t rows = (uint64_t)B * S, krows = (uint64_t)B * Sk;
   CUtensorMap tq = tma::make_2d(q.data_ptr(), BF, 2, rows, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, BQ, 64);
   CUtensorMap tdo = tma::make_2d(dout.data_ptr(), BF, 2, rows, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, BQ, 64);
-  CUtensorMap tk = tma::make_2d(k.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
-  CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
-  CUtensorMap tdk = tma::make_2d(dk.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
-  CUtensorMap tdv = tma::make_2d(dv.data_ptr(), BF, 2, rows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tk = tma::make_2d(k.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tdk = tma::make_2d(dk.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tdv = tma::make_2d(dv.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
   CUtensorMap tdq = tma::make_2d(dq_acc.data_ptr(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, (uint64_t)Hq * D,
-                                 (uint64_t)Hq * D * 4, BQ, 32, /*swizzle128=*/false);
+                                 (uint64_t)Hq * D * 4, BQ / 2, 32, /*swizzle128=*/false);   // half chunk: 32 q x 32 d
   Params p;
-  p.B = B; p.S = S; p.Hq = Hq; p.Hk = Hk; p.num_kblocks = S / BN; p.window = (int)window;
+  p.B = B; p.S = S; p.Sk = Sk; p.q_off = (int)q_offset; p.Hq = Hq; p.Hk = Hk; p.num_kblocks = Sk / BN; p.window = (int)window;
   p.causal = causal ? 1 : 0;
   p.scale = (float)scale;
   p.scale_log2 = (float)(scale * 1.4426950408889634);
@@ -526,7 +545,7 @@ std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor&
     C10_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     once = true;
   }
-  dim3 grid(p.num_kblocks, Hk, B);      // key block 0 has the longest query walk and is scheduled first
+  dim3 grid(Hk * B, p.num_kblocks);     // heads x batches fastest, key block 0 (longest query walk) first
   flash_bwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   {

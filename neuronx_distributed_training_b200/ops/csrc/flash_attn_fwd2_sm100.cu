@@ -42,12 +42,15 @@ constexpr int SMEM_BYTES = (2 + KV_SLOTS) * TILE_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
 struct Params {
-  int B, S, Hq, Hk;
+  int B, S, Hq, Hk;      // S = number of (local) queries per batch entry
+  int Sk;                // number of keys per batch entry (>= S under context parallelism: the gathered sequence)
+  int q_off;             // absolute position of query row 0 relative to key 0 (multiple of 128; context-parallel rank offset)
   int num_q_pairs;       // S / 256
   int window;            // 0 = none; otherwise keys with k <= q - window are masked
   int causal;            // 1: keys after the query are masked; 0: full attention
   float scale_log2;      // softmax scale * log2(e)
   float* lse;            // [B, Hq, S]
+  long long* dbg;        // optional in-kernel timeline of CTA (0, 0): [3 roles][128 blocks][4 stamps] of clock64 (else nullptr)
 };
 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kk) {
@@ -109,19 +112,22 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   uint64_t* s_full = bars + 12;                     // [2]  S_t(j) is in TMEM (and PV_t(j-1) has retired)
   uint64_t* p_full = bars + 14;                     // [2]  P_t(j) is in TMEM, O_t has been rescaled if necessary
   uint64_t* o_full = bars + 16;                     // [2]  last PV of tile t has retired
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* turn = bars + 18;                       // [2]  exp-phase hand-over between the two softmax warpgroups
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
 
   // heavy (late) query blocks first; heads vary fastest so that concurrently running CTAs have equal lengths and the
   // heads of one GQA group share their K/V tiles in L2
   const int qp = p.num_q_pairs - 1 - (int)blockIdx.y;
-  const int head = blockIdx.x, batch = blockIdx.z;
+  const int head = blockIdx.x % p.Hq, batch = blockIdx.x / p.Hq;
   const int kv_head = head / (p.Hq / p.Hk);
   const int q0 = qp * 2 * BM;
-  const int j_lo = (p.window > 0) ? max(0, (q0 - p.window + 1) / BN) : 0;
-  const int j_hi = p.causal ? 2 * qp + 1 : 2 * p.num_q_pairs - 1;      // inclusive, for tile 1
+  const int qa0 = p.q_off + q0;                                        // absolute position of the CTA's first query
+  const int j_lo = (p.window > 0) ? max(0, (qa0 - p.window + 1) / BN) : 0;
+  const int j_hi = p.causal ? qa0 / BN + 1 : p.Sk / BN - 1;            // inclusive, for tile 1
   const int n = j_hi - j_lo + 1;                                       // key blocks of tile 1
   const int n0 = p.causal ? n - 1 : n;                                 // key blocks of tile 0 (its diagonal is one earlier)
-  const int row_base = batch * p.S;                                    // row of token 0 of this batch in the [B*S, H*D] views
+  const int row_base = batch * p.S;                                    // row of query 0 of this batch in the [B*S, Hq*D] views
+  const int krow_base = batch * p.Sk;                                  // row of key 0 of this batch in the [B*Sk, Hk*D] views
 
   if (warp_idx == 8 && elect_one()) {
     tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_o);
@@ -130,6 +136,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
+      mbar_init(&turn[i], 4);
     }
     for (int i = 0; i < KV_SLOTS; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -159,8 +166,8 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         mbar_wait(&kv_empty[slot], ph ^ 1);
         mbar_expect_tx(&kv_full[slot], TILE_BYTES);
         uint8_t* dst = sKV + slot * TILE_BYTES;
-        tma_load_2d(dst, map, &kv_full[slot], kv_head * D, row_base + j * BN);
-        tma_load_2d(dst + CHUNK_BYTES, map, &kv_full[slot], kv_head * D + 64, row_base + j * BN);
+        tma_load_2d(dst, map, &kv_full[slot], kv_head * D, krow_base + j * BN);
+        tma_load_2d(dst + CHUNK_BYTES, map, &kv_full[slot], kv_head * D + 64, krow_base + j * BN);
         ++u;
       };
       auto load_q = [&](int t) {
@@ -203,6 +210,8 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     auto issue_pv = [&](int t, int i, bool release_v, bool last) {
       const int u = 2 * i + 1;
       mbar_wait(&p_full[t], i & 1);
+      const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && i < 128;
+      if (stamp) p.dbg[(2 * 128 + i) * 4 + 2 * t] = clock64();        // MMA warp saw P_t(i)
       wait_kv(u);
       tcgen05_fence_after();
       if (elect_one()) {
@@ -215,6 +224,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         if (last) umma_commit(&o_full[t]);
       }
       __syncwarp();
+      if (stamp) p.dbg[(2 * 128 + i) * 4 + 2 * t + 1] = clock64();    // PV_t(i) issued
     };
     mbar_wait(&q_full[0], 0);
     issue_qk(0, 0, false);
@@ -239,9 +249,9 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     const uint32_t lane_off = (qd * 32u) << 16;
     const uint32_t tS = tmem_base + lane_off + t * BN;
     const uint32_t tO = tmem_base + lane_off + 256 + t * D;
-    const int q_pos = q0 + t * BM + (int)row;
+    const int q_pos = qa0 + t * BM + (int)row;        // absolute position (mask arithmetic)
     const int nt = t == 0 ? n0 : n;
-    const int j_diag = 2 * qp + t;
+    const int j_diag = qa0 / BN + t;
     const float sc = p.scale_log2;
     float m_used = -INFINITY;                        // raw (unscaled) score domain
     uint64_t l2 = pack2(0.f, 0.f);                   // two partial row sums
@@ -249,6 +259,8 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       const int j = j_lo + i;
       mbar_wait(&s_full[t], i & 1);
       tcgen05_fence_after();
+      const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && qd == 0 && i < 128;
+      if (stamp) p.dbg[(t * 128 + i) * 4 + 0] = clock64();            // S_t(i) observed
       uint32_t sr[4][32];                            // the fp32 score row (raw bits), 4 x 32 columns
       tmem_ld_32x32b_x32(tS + 0, sr[0]);
       tmem_ld_32x32b_x32(tS + 32, sr[1]);
@@ -306,6 +318,16 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           }
         }
       }
+      // The exponentials of the two query tiles take turns (tile 0 block i, tile 1 block i, tile 0 block i+1, ...), the
+      // order in which the MMA warp serves them.  Without the hand-over both warpgroups share the MUFU pipe, the
+      // higher-numbered warps win the issue arbitration and overtake tile 0, and the tensor core -- which needs P0 first
+      // -- idles until the preempted tile finishes.  Loading S and the row maximum above stay outside the turn.
+      if (t == 0) {
+        if (i > 0) mbar_wait(&turn[0], (i - 1) & 1);
+      } else if (i < n0) {
+        mbar_wait(&turn[1], i & 1);
+      }
+      if (stamp) p.dbg[(t * 128 + i) * 4 + 1] = clock64();            // turn acquired: exponentials start
       // a row can still be fully masked so far (sliding window): keep exp2(-inf - 0) = 0 instead of NaN
       const float m_sc = (m_used == -INFINITY) ? 0.f : m_used * sc;
       const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_sc, -m_sc);
@@ -323,10 +345,14 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         }
         tmem_st_32x32b_x16(tS + c * 16, pk);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&turn[t ^ 1]);
+      if (stamp) p.dbg[(t * 128 + i) * 4 + 2] = clock64();            // exponentials issued, turn handed over
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
+      if (stamp) p.dbg[(t * 128 + i) * 4 + 3] = clock64();            // P_t(i) published
     }
     // ---------------- epilogue: O / l -> bf16 -> smem (the Q tile is free now) -> TMA store; LSE ----------------
     float l_lo, l_hi;
@@ -335,7 +361,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     mbar_wait(&o_full[t], 0);
     tcgen05_fence_after();
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    uint8_t* orow = sQ + t * TILE_BYTES + row * 128;
+    const uint32_t orow = smem_u32(sQ) + t * TILE_BYTES + row * 128;
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
       uint32_t v[32];
@@ -350,10 +376,10 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         o.w = pack_bf16x2(__uint_as_float(v[t8 * 8 + 6]) * inv_l, __uint_as_float(v[t8 * 8 + 7]) * inv_l);
         const int c16 = c * 4 + t8;      // 16-byte column group 0..15
         const int chunk = c16 >> 3, j16 = c16 & 7;
-        *reinterpret_cast<uint4*>(orow + chunk * CHUNK_BYTES + ((j16 ^ (row & 7)) * 16)) = o;
+        st_shared_v4(orow + chunk * CHUNK_BYTES + ((j16 ^ (row & 7)) * 16), o);
       }
     }
-    p.lse[((size_t)batch * p.Hq + head) * p.S + q_pos] =
+    p.lse[((size_t)batch * p.Hq + head) * p.S + q0 + t * BM + row] =
         l > 0.f ? (m_used * sc + log2f(l)) * 0.6931471805599453f : -INFINITY;
     tcgen05_fence_before();
     fence_proxy_async_smem();
@@ -375,9 +401,16 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 
 }  // namespace fa2
 
-// q [B,S,Hq,128], k/v [B,S,Hk,128] bf16 contiguous, S a multiple of 256; returns (out [B,S,Hq,128] bf16, lse [B,Hq,S] fp32)
+static long long* g_fwd2_dbg = nullptr;
+// int64 tensor of >= 3 * 128 * 4 elements on the device: the next launches record the timeline of CTA (0, 0); empty -> off
+void flash_fwd2_set_debug(const at::Tensor& t) {
+  g_fwd2_dbg = t.numel() >= 3 * 128 * 4 ? reinterpret_cast<long long*>(t.data_ptr<int64_t>()) : nullptr;
+}
+
+// q [B,S,Hq,128], k/v [B,Sk,Hk,128] bf16 contiguous, S a multiple of 256, Sk >= q_offset + S (context parallelism: the
+// gathered keys; query i sits at absolute position q_offset + i); returns (out [B,S,Hq,128] bf16, lse [B,Hq,S] fp32)
 std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
-                                        int64_t window, double scale) {
+                                        int64_t window, double scale, int64_t q_offset) {
   using namespace fa2;
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16);
   TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.size(3) == D && k.size(3) == D && v.size(3) == D,
@@ -385,28 +418,32 @@ std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k
   TORCH_CHECK(causal || window == 0, "flash_attn_fwd2: a sliding window needs causal attention");
   TORCH_CHECK(q.is_contiguous() && k.is_contiguous() && v.is_contiguous(), "flash_attn_fwd2: contiguous [B,S,H,D] inputs required");
   const int B = q.size(0), S = q.size(1), Hq = q.size(2), Hk = k.size(2);
-  TORCH_CHECK(k.size(1) == S && v.size(1) == S && v.size(2) == Hk && Hq % Hk == 0);
-  TORCH_CHECK(S % (2 * BM) == 0, "flash_attn_fwd2: sequence length must be a multiple of 256");
+  const int Sk = k.size(1);
+  TORCH_CHECK(v.size(1) == Sk && v.size(2) == Hk && Hq % Hk == 0 && k.size(0) == B && v.size(0) == B);
+  TORCH_CHECK(S % (2 * BM) == 0, "flash_attn_fwd2: the query length must be a multiple of 256");
+  TORCH_CHECK(Sk % BN == 0 && q_offset % BN == 0 && q_offset >= 0 && q_offset + S <= Sk,
+              "flash_attn_fwd2: keys must cover [0, q_offset + S) in whole blocks of 128");
   c10::cuda::CUDAGuard guard(q.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   auto out = at::empty_like(q);
   auto lse = at::empty({B, Hq, S}, q.options().dtype(at::kFloat));
   const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tq = tma::make_2d(q.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, 128, 64);
-  CUtensorMap tk = tma::make_2d(k.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
-  CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tk = tma::make_2d(k.data_ptr(), BF, 2, (uint64_t)B * Sk, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, (uint64_t)B * Sk, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
   CUtensorMap to = tma::make_2d(out.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, 128, 64);
   Params p;
-  p.B = B; p.S = S; p.Hq = Hq; p.Hk = Hk; p.num_q_pairs = S / (2 * BM); p.window = (int)window;
+  p.B = B; p.S = S; p.Sk = Sk; p.q_off = (int)q_offset; p.Hq = Hq; p.Hk = Hk; p.num_q_pairs = S / (2 * BM); p.window = (int)window;
   p.causal = causal ? 1 : 0;
   p.scale_log2 = (float)(scale * 1.4426950408889634);
   p.lse = lse.data_ptr<float>();
+  p.dbg = g_fwd2_dbg;
   static bool once = false;
   if (!once) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     once = true;
   }
-  dim3 grid(Hq, p.num_q_pairs, B);
+  dim3 grid(Hq * B, p.num_q_pairs);
   flash_fwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, lse};

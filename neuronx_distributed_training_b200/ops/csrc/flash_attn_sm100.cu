@@ -326,7 +326,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 // q [B,S,Hq,128], k/v [B,S,Hk,128] bf16 with a contiguous last dim and row (token) pitch given by stride(1);
 // returns (out [B,S,Hq,128] bf16, lse [B,Hq,S] fp32)
 std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
-                                        int64_t window, double scale);
+                                        int64_t window, double scale, int64_t q_offset);
 
 std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
                                         int64_t window, double scale);
@@ -334,8 +334,10 @@ std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k
 // sequence lengths that are a multiple of 256 take the two-tile ping-pong kernel (flash_attn_fwd2_sm100.cu), the
 // remaining multiples of 128 the single-tile kernel below
 std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
-                                       int64_t window, double scale) {
-  if (q.dim() == 4 && q.size(1) % 256 == 0) return flash_attn_fwd2(q, k, v, causal, window, scale);
+                                       int64_t window, double scale, int64_t q_offset) {
+  if (q.dim() == 4 && q.size(1) % 256 == 0) return flash_attn_fwd2(q, k, v, causal, window, scale, q_offset);
+  TORCH_CHECK(q_offset == 0 && k.size(1) == q.size(1), "flash_attn_fwd: a query offset / longer key sequence needs a query "
+              "length that is a multiple of 256");
   return flash_attn_fwd1(q, k, v, causal, window, scale);
 }
 

@@ -10,6 +10,16 @@ Backward walks the ring again: dK/dV accumulators travel together with their K/V
 steps; dQ accumulates locally.  Block math uses the global LSE saved by the forward, so it is exact.
 NVSwitch note: bandwidth is uniform, so ring order is only a scheduling choice (a direct all-to-all fetch is
 equivalent); K/V transfers are issued before the block math so they overlap with it.
+
+B200-native path (``_GatheredKVAttention``, taken on GPUs for bf16 / head_dim 128 / local length % 256 == 0): every GPU
+has full NVLink bandwidth to every peer through NVSwitch, so the K/V shards are all-gathered ONCE (K/V of a GQA model are
+small: 2 x S x Hk_local x 128 bf16) and each rank runs ONE tcgen05 flash-attention launch over its local queries against
+the gathered keys with a query offset (``flash_attn_fwd(..., q_offset=rank * S_local)``: causal masking in absolute
+positions, key blocks beyond the diagonal are never loaded).  The backward is one launch of the native backward with the
+same offset; dK / dV come out for the whole gathered sequence and are reduce-scattered back to their owners.  Compared
+with rotating blocks this removes cp - 1 kernel launches, the per-step online-softmax merges (fp32 passes over O) and
+the exposed p2p latency; pulling K/V tiles from peers inside the kernel would re-read them over NVLink once per query
+tile (peer memory bypasses the local L2), which is why the gather is done once up front.
 """
 from __future__ import annotations
 
@@ -26,8 +36,7 @@ _Q_CHUNK = 1024
 
 
 def _native_block_ok(q, k) -> bool:
-    # opt-in until the non-causal mode of the tcgen05 forward has been validated on hardware
-    if os.environ.get("NXDT_RING_NATIVE_FWD", "0") != "1" or not q.is_cuda:
+    if not q.is_cuda:
         return False
     from .. import ops
     return ops.get_backend() != "torch" and ops.C() is not None and hasattr(ops.C(), "flash_attn_fwd") \
@@ -153,6 +162,62 @@ class _RingAttention(torch.autograd.Function):
         return dq.to(q.dtype), dkb.to(k.dtype), dvb.to(v.dtype), None, None, None, None
 
 
+def _native_cp_ok(q: torch.Tensor, k: torch.Tensor) -> bool:
+    if not q.is_cuda:
+        return False
+    from .. import ops
+    return ops.get_backend() != "torch" and ops.C() is not None and hasattr(ops.C(), "flash_attn_bwd") \
+        and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and q.shape[1] == k.shape[1] and q.shape[1] % 256 == 0 \
+        and q.shape[2] % k.shape[2] == 0
+
+
+def _gather_seq(x: torch.Tensor, group, cp: int) -> torch.Tensor:
+    """[B, S_local, H, D] on every rank -> [B, cp * S_local, H, D] in rank order."""
+    B, S, H, D = x.shape
+    buf = torch.empty(cp, B, S, H, D, dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(buf, x.contiguous(), group=group)
+    return buf[0] if cp == 1 else (buf.view(cp * S, H, D).unsqueeze(0) if B == 1 else
+                                   buf.permute(1, 0, 2, 3, 4).reshape(B, cp * S, H, D))
+
+
+def _scatter_sum_seq(x: torch.Tensor, group, cp: int) -> torch.Tensor:
+    """[B, cp * S_local, H, D] partial sums on every rank -> this rank's [B, S_local, H, D] slice of the total."""
+    B, St, H, D = x.shape
+    S = St // cp
+    src = x.view(cp, S, H, D) if B == 1 else x.view(B, cp, S, H, D).permute(1, 0, 2, 3, 4).contiguous()
+    out = torch.empty(B, S, H, D, dtype=x.dtype, device=x.device)
+    dist.reduce_scatter_tensor(out, src.contiguous(), group=group)
+    return out
+
+
+class _GatheredKVAttention(torch.autograd.Function):
+    """Context-parallel causal attention on the native kernels: all-gather K / V, one offset-causal launch."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, group, cp, my_idx):
+        from .. import ops
+        C = ops.C()
+        kf, vf = _gather_seq(k, group, cp), _gather_seq(v, group, cp)
+        q = q.contiguous()
+        ops._count()
+        o, lse = C.flash_attn_fwd(q, kf, vf, True, 0, float(scale), my_idx * q.shape[1])
+        ctx.save_for_backward(q, kf, vf, o, lse)
+        ctx.cfg = (float(scale), group, cp, my_idx)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        from .. import ops
+        q, kf, vf, o, lse = ctx.saved_tensors
+        scale, group, cp, my_idx = ctx.cfg
+        ops._count(3)
+        dq, dkf, dvf = ops.C().flash_attn_bwd(do.contiguous(), q, kf, vf, o, lse, True, 0, scale, my_idx * q.shape[1])
+        # every rank produced gradients for all keys its queries could see (zeros beyond its diagonal)
+        dk = _scatter_sum_seq(dkf.float(), group, cp).to(q.dtype)
+        dv = _scatter_sum_seq(dvf.float(), group, cp).to(q.dtype)
+        return dq, dk, dv, None, None, None, None
+
+
 def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None, group=None,
                    ranks: Optional[List[int]] = None) -> torch.Tensor:
     """q [B,S_local,H,D], k/v [B,S_local,Hkv,D] (this rank's contiguous sequence chunk) -> [B,S_local,H,D]."""
@@ -163,4 +228,6 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Opt
         from .. import ops
         return ops.flash_attention(q, k, v, causal=True, scale=scale)
     my_idx = ranks.index(dist.get_rank())
+    if _native_cp_ok(q, k):
+        return _GatheredKVAttention.apply(q, k, v, scale, group, len(ranks), my_idx)
     return _RingAttention.apply(q, k, v, scale, group, ranks, my_idx)

@@ -1,0 +1,75 @@
+"""Whole-model parity ON HARDWARE: Llama in bf16 under TP=N (+SP) with the fused AG->GEMM / GEMM->RS kernels, the native
+flash attention and the fused LM-head loss, against the same weights on one GPU (TP=1).  Every parameter gradient is
+compared per tensor: relative loss error <= 1e-3, cosine >= 0.999, norm within 2 %.  (The CPU twin is
+tests/dist_scripts/tp_model.py, fp32 / gloo / allclose.)    torchrun --nproc-per-node N check_tp_model_gpu.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch, torch.distributed as dist
+from neuronx_distributed_training_b200 import ops
+from neuronx_distributed_training_b200.parallel import state as ps
+from neuronx_distributed_training_b200.parallel.fused import enable_fused_tp
+from neuronx_distributed_training_b200.parallel.layers import shard_master_weight
+from neuronx_distributed_training_b200.models.llama import LlamaConfig, LlamaForCausalLM
+
+ps.init_distributed("nccl")
+rank, world = dist.get_rank(), dist.get_world_size()
+TP = world
+dev = torch.device("cuda", torch.cuda.current_device())
+S = int(os.environ.get("SEQ", "2048"))
+FUSED = os.environ.get("FUSED", "1") == "1"
+base = dict(vocab_size=8192, hidden_size=1024, intermediate_size=2816, num_hidden_layers=int(os.environ.get("LAYERS", "3")),
+            num_attention_heads=8, num_key_value_heads=max(2, TP), head_dim=128, torch_dtype="bfloat16",
+            use_cpu_initialization=True)
+g = torch.Generator().manual_seed(5)
+ids = torch.randint(0, 8192, (2, S), generator=g).to(dev)
+
+
+def run(tp_size, sp):
+    ps.destroy_model_parallel()
+    ps.initialize_model_parallel(tp_size, 1, 1)
+    torch.manual_seed(11)
+    m = LlamaForCausalLM(LlamaConfig(**base, sequence_parallel_enabled=sp), device=dev)
+    n_fused = enable_fused_tp(m, seq_len=S, micro_batch=2) if (FUSED and tp_size > 1) else 0
+    ops.reset_native_launch_count()
+    loss, _ = m(input_ids=ids, labels=ids)
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {}
+    for n, p in m.named_parameters():
+        gr = (p.main_grad if getattr(p, "main_grad", None) is not None else p.grad).float().clone()
+        if tp_size > 1 and getattr(p, "sequence_parallel_enabled", False):
+            dist.all_reduce(gr)                  # each TP rank saw S/TP of the tokens (the optimizer does this sum)
+        grads[n] = (gr, bool(getattr(p, "tensor_model_parallel", False)), getattr(p, "partition_dim", -1),
+                    getattr(p, "partition_stride", 1))
+    return loss.detach().float().clone(), grads, n_fused, ops.native_launch_count()
+
+
+loss_tp, g_tp, n_fused, launches = run(TP, True)
+tpr = ps.get_tensor_model_parallel_rank()
+loss_1, g_1, _, _ = run(1, False)
+bad = []
+rel_loss = abs(loss_tp.item() - loss_1.item()) / abs(loss_1.item())
+if rel_loss > 1e-3:
+    bad.append(f"loss {loss_tp.item()} vs {loss_1.item()}")
+worst_cos, worst_norm = 1.0, 0.0
+assert set(g_tp) == set(g_1)
+for n, (gr, is_tp, dim, stride) in g_tp.items():
+    want = g_1[n][0]
+    want = shard_master_weight(want, dim, TP, tpr, stride) if is_tp else want
+    cos = torch.nn.functional.cosine_similarity(gr.flatten(), want.flatten(), dim=0).item()
+    nr = (gr.norm() / want.norm().clamp_min(1e-12)).item()
+    worst_cos, worst_norm = min(worst_cos, cos), max(worst_norm, abs(nr - 1))
+    if cos < 0.999 or abs(nr - 1) > 0.02:
+        bad.append(f"{n}: cosine {cos:.5f} norm ratio {nr:.4f}")
+flag = torch.tensor([len(bad)], device=dev)
+dist.all_reduce(flag)
+print(f"[rank {rank}] TP={TP} fused layers {n_fused} native launches {launches}: loss {loss_tp.item():.5f} vs TP=1 {loss_1.item():.5f} "
+      f"(rel {rel_loss:.2e}); worst cosine {worst_cos:.5f}, worst |norm ratio - 1| {worst_norm:.4f}" + ("".join("\n   BAD " + b for b in bad[:8])),
+      flush=True)
+if FUSED:
+    assert n_fused > 0, "the fused tensor-parallel kernels were not attached"
+assert launches > 0, "no native kernels were launched"
+dist.barrier()
+if rank == 0:
+    print("TP_MODEL_GPU_OK" if flag.item() == 0 else "TP_MODEL_GPU_MISMATCH", flush=True)
+dist.destroy_process_group()

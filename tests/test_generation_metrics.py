@@ -44,3 +44,31 @@ def test_top_k_and_top_p_filtering():
     f = filter_logits(logits, top_p=0.01)                                    # the most likely token always survives
     assert torch.isfinite(f).sum() == 1 and torch.isfinite(f[0, 4])
     assert torch.equal(filter_logits(logits), logits)
+
+
+def test_kv_cached_batched_generation_matches_uncached():
+    """Variable-length prompts, left-padded and decoded with the KV cache, give exactly the tokens of the prefix-re-running
+    decoder run on every prompt alone (Llama with GQA + sliding window, and Mixtral)."""
+    from neuronx_distributed_training_b200.models.mixtral import MixtralConfig, MixtralForCausalLM
+    from neuronx_distributed_training_b200.utils.generation import generate_cached, generate_uncached, supports_kv_cache
+    torch.manual_seed(1)
+    models = [
+        LlamaForCausalLM(LlamaConfig(vocab_size=61, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                     num_key_value_heads=2, torch_dtype="float32", use_flash_attention=False, sliding_window=6)),
+        MixtralForCausalLM(MixtralConfig(vocab_size=61, hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=4,
+                                         num_key_value_heads=2, torch_dtype="float32", use_flash_attention=False,
+                                         num_local_experts=4, num_experts_per_tok=2)),
+    ]
+    prompts = [[3, 9, 27, 4, 8, 15, 16, 23, 42], [5], [7, 7, 7, 1]]
+    for m in models:
+        assert supports_kv_cache(m)
+        new = generate_cached(m, prompts, max_new_tokens=6)
+        for p, n in zip(prompts, new):
+            ref = generate_uncached(m, torch.tensor([p]), max_new_tokens=6)[0, len(p):].tolist()
+            assert n == ref, (type(m).__name__, p, n, ref)
+    # eos stops a row early and is not part of the returned text
+    m = models[0]
+    first = generate_cached(m, prompts, max_new_tokens=6)
+    eos = first[0][2]
+    cut = generate_cached(m, prompts, max_new_tokens=6, eos_token_id=eos)
+    assert cut[0] == first[0][:first[0].index(eos)]

@@ -162,6 +162,38 @@ def test_flash_attn_fwd(C, B, S, Hq, Hk, window):
     assert (lse - lse_ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("B,S,Hq,Hk,window,causal", [
+    (1, 256, 4, 1, 0, True),        # GQA 4:1, two-tile forward kernel
+    (2, 1024, 8, 2, 0, True),
+    (1, 384, 2, 2, 0, True),        # 3 x 128: single-tile forward kernel
+    (1, 2048, 4, 1, 700, True),     # sliding window across several key blocks
+    (1, 1024, 4, 4, 100, True),     # window shorter than a block
+    (2, 512, 4, 2, 0, False),       # full attention (off-diagonal blocks of context parallelism)
+])
+def test_flash_attention_forward_backward(C, B, S, Hq, Hk, window, causal):
+    """``ops.flash_attention`` (the call the model makes): native tcgen05 forward AND backward through autograd, against
+    the fp32 eager oracle; no library attention kernel is involved."""
+    from neuronx_distributed_training_b200 import ops
+    assert hasattr(C, "flash_attn_bwd"), "the native flash attention backward is not built"
+    torch.manual_seed(0)
+    q = torch.randn(B, S, Hq, 128, device="cuda").bfloat16().requires_grad_(True)
+    k = torch.randn(B, S, Hk, 128, device="cuda").bfloat16().requires_grad_(True)
+    v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16().requires_grad_(True)
+    do = torch.randn(B, S, Hq, 128, device="cuda").bfloat16()
+    assert ops.flash_attention_native_ok(q, k, window or None, causal)
+    n0 = ops.native_launch_count()
+    out = ops.flash_attention(q, k, v, causal=causal, window=window or None)
+    out.backward(do)
+    assert ops.native_launch_count() - n0 == 4          # forward + (statistics, main, dQ cast)
+    got = (out.detach(), q.grad, k.grad, v.grad)
+    q.grad = k.grad = v.grad = None
+    ref = ops.attention_ref(q, k, v, causal=causal, window=window or None)
+    ref.backward(do)
+    for name, a, b in zip(("out", "dq", "dk", "dv"), got, (ref.detach(), q.grad, k.grad, v.grad)):
+        assert torch.isfinite(a.float()).all(), name
+        assert _rel_err(a, b) < 1e-2, (name, _rel_err(a, b))
+
+
 def test_qkv_rope_split(C):
     from neuronx_distributed_training_b200 import ops
     torch.manual_seed(0)
@@ -463,15 +495,22 @@ def _tiny_llama_loss_and_grads(backend, device="cuda", dtype="bfloat16"):
 
 
 def test_whole_model_native_path_matches_library_path(C):
-    """Every native op in one forward + backward (RMSNorm, fused QKV split + RoPE, flash attention, SwiGLU, tcgen05 GEMMs
-    for fwd / dgrad / wgrad, fused LM head + cross-entropy) against the same model on the library path
-    (cuBLAS / SDPA / unfused torch ops): same loss, same gradient directions."""
+    """Every native op in one forward + backward (RMSNorm, fused QKV split + RoPE, flash attention fwd + bwd, SwiGLU,
+    tcgen05 GEMMs for fwd / dgrad / wgrad, fused LM head + cross-entropy) against (a) the same bf16 model on the library
+    path (cuBLAS / SDPA / unfused torch ops) and (b) the fp32 model as ground truth.  Bounds per gradient tensor: cosine
+    >= 0.999 and norm within 2 % of the fp32 truth (or, where bf16 itself cannot reach that, no worse than the library
+    path by more than 5e-4 / 0.5 %) -- tight enough to expose a 2x error in any single tensor class."""
     loss_n, g_n = _tiny_llama_loss_and_grads("auto")
     loss_t, g_t = _tiny_llama_loss_and_grads("torch")
-    assert loss_n == loss_n and abs(loss_n - loss_t) / abs(loss_t) < 2e-2, (loss_n, loss_t)
-    assert set(g_n) == set(g_t) and g_n
+    loss_f, g_f = _tiny_llama_loss_and_grads("torch", dtype="float32")
+    assert loss_n == loss_n
+    assert abs(loss_n - loss_f) / abs(loss_f) < max(1e-3, 2 * abs(loss_t - loss_f) / abs(loss_f)), (loss_n, loss_t, loss_f)
+    assert set(g_n) == set(g_t) == set(g_f) and g_n
+    cosf = torch.nn.functional.cosine_similarity
     for name in g_n:
-        a, b = g_n[name].flatten(), g_t[name].flatten()
-        cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
-        assert cos > 0.95, (name, cos)
-        assert abs(a.norm().item() - b.norm().item()) <= 0.2 * b.norm().item() + 1e-6, name
+        a, b, f = g_n[name].flatten(), g_t[name].flatten(), g_f[name].flatten()
+        cos_n, cos_t = cosf(a, f, dim=0).item(), cosf(b, f, dim=0).item()
+        assert cos_n >= min(0.999, cos_t - 5e-4), (name, cos_n, cos_t)
+        dev_n, dev_t = abs(a.norm().item() / f.norm().item() - 1), abs(b.norm().item() / f.norm().item() - 1)
+        assert dev_n <= max(0.02, dev_t + 0.005), (name, dev_n, dev_t)
+        assert cosf(a, b, dim=0).item() > 0.995, name
