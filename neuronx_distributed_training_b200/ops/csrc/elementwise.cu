@@ -112,36 +112,41 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_fwd_kernel(const T* __restric
   }
 }
 
-// backward: dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) ; dw[c] += sum_rows dy * xhat   (persistent grid)
+// backward: dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) ; dw[c] = sum_rows dy * xhat   (persistent grid)
+// One pass over global memory: x, dy of a row stay in registers between the row reduction and the dx store, w is loaded
+// once per CTA.  dw is DETERMINISTIC: every CTA writes its partial column sums to its own row of `dw_part`
+// [gridDim.x, H]; `colsum_kernel` then adds the partials in a fixed order (no floating-point atomics).
 template <typename T, int THREADS, int MAXV>
 __global__ void __launch_bounds__(THREADS) rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                               const T* __restrict__ w, const float* __restrict__ rstd,
-                                                              T* __restrict__ dx, float* __restrict__ dw, int rows,
+                                                              T* __restrict__ dx, float* __restrict__ dw_part, int rows,
                                                               int H) {
   __shared__ float sm[32];
-  float dw_acc[MAXV][8];
+  float dw_acc[MAXV][8], fw[MAXV][8];
 #pragma unroll
-  for (int v = 0; v < MAXV; ++v)
+  for (int v = 0; v < MAXV; ++v) {
+    const int c = (v * THREADS + threadIdx.x) * 8;
+    if (c < H) load8<T>(w + c, fw[v]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) dw_acc[v][i] = 0.f;
+  }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const T* xr = x + (size_t)row * H;
     const T* gr = dy + (size_t)row * H;
     const float rs = rstd[row];
+    float fx[MAXV][8], fg[MAXV][8];
     float dot = 0.f;
 #pragma unroll
     for (int v = 0; v < MAXV; ++v) {
       const int c = (v * THREADS + threadIdx.x) * 8;
       if (c < H) {
-        float fx[8], fg[8], fw[8];
-        load8<T>(xr + c, fx);
-        load8<T>(gr + c, fg);
-        load8<T>(w + c, fw);
+        load8<T>(xr + c, fx[v]);
+        load8<T>(gr + c, fg[v]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float xh = fx[i] * rs;
-          dot += fg[i] * fw[i] * xh;
-          dw_acc[v][i] += fg[i] * xh;
+          const float xh = fx[v][i] * rs;
+          dot += fg[v][i] * fw[v][i] * xh;
+          dw_acc[v][i] += fg[v][i] * xh;
         }
       }
     }
@@ -151,23 +156,45 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_bwd_kernel(const T* __restric
     for (int v = 0; v < MAXV; ++v) {
       const int c = (v * THREADS + threadIdx.x) * 8;
       if (c < H) {
-        float fx[8], fg[8], fw[8], o[8];
-        load8<T>(xr + c, fx);
-        load8<T>(gr + c, fg);
-        load8<T>(w + c, fw);
+        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rs * (fg[i] * fw[i] - fx[i] * rs * dot);
+        for (int i = 0; i < 8; ++i) o[i] = rs * (fg[v][i] * fw[v][i] - fx[v][i] * rs * dot);
         store8<T>(dxr + c, o);
       }
     }
   }
+  float* part = dw_part + (size_t)blockIdx.x * H;
 #pragma unroll
   for (int v = 0; v < MAXV; ++v) {
     const int c = (v * THREADS + threadIdx.x) * 8;
     if (c < H) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(dw + c + i, dw_acc[v][i]);
+      *reinterpret_cast<float4*>(part + c) = make_float4(dw_acc[v][0], dw_acc[v][1], dw_acc[v][2], dw_acc[v][3]);
+      *reinterpret_cast<float4*>(part + c + 4) = make_float4(dw_acc[v][4], dw_acc[v][5], dw_acc[v][6], dw_acc[v][7]);
     }
+  }
+}
+
+// out[c] = sum_r part[r, c] in a fixed order: thread (x) owns 4 columns, the CTA's y-slices split the rows and are
+// combined through shared memory in slice order
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ part, float* __restrict__ out, int R, int H) {
+  __shared__ float4 sm[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < H) {
+    for (int r = threadIdx.y; r < R; r += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(part + (size_t)r * H + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < H) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) {
+      const float4 v = sm[y][threadIdx.x];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + c) = acc;
   }
 }
 
@@ -568,17 +595,18 @@ std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, c
   const int rows = x.size(0), H = x.size(1);
   c10::cuda::CUDAGuard guard(x.device());
   auto dx = at::empty_like(x);
-  auto dw = at::zeros({H}, x.options().dtype(at::kFloat));
+  auto dw = at::empty({H}, x.options().dtype(at::kFloat));
   auto stream = at::cuda::getCurrentCUDAStream();
   constexpr int TH = 256;
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  const int grid = std::min(rows, sms * 4);
+  const int grid = std::max(1, std::min(rows, sms * 2));
+  auto dw_part = at::empty({grid, H}, x.options().dtype(at::kFloat));
   const int need_v = (H + TH * 8 - 1) / (TH * 8);
   TORCH_CHECK(need_v <= 8, "rmsnorm_bwd: hidden size too large");
 #define RUN(T, MAXV)                                                                                          \
   rmsnorm_bwd_kernel<T, TH, MAXV><<<grid, TH, 0, stream>>>((const T*)dy.data_ptr(), (const T*)x.data_ptr(),     \
                                                             (const T*)w.data_ptr(), rstd.data_ptr<float>(),      \
-                                                            (T*)dx.data_ptr(), dw.data_ptr<float>(), rows, H)
+                                                            (T*)dx.data_ptr(), dw_part.data_ptr<float>(), rows, H)
   if (x.scalar_type() == at::kBFloat16) {
     if (need_v <= 1) RUN(__nv_bfloat16, 1); else if (need_v <= 2) RUN(__nv_bfloat16, 2);
     else if (need_v <= 4) RUN(__nv_bfloat16, 4); else RUN(__nv_bfloat16, 8);
@@ -587,6 +615,8 @@ std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, c
     else if (need_v <= 4) RUN(float, 4); else RUN(float, 8);
   }
 #undef RUN
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  colsum_kernel<<<(H + 127) / 128, dim3(32, 8), 0, stream>>>(dw_part.data_ptr<float>(), dw.data_ptr<float>(), grid, H);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {dx, dw};
 }

@@ -19,7 +19,7 @@
 //
 //   warps 0..3   compute (P, dS) + final dK / dV epilogue        warps 4..7   dQ writers
 //   warp  8      TMA producer (K, V once; Q_i, dO_i, LSE_i, Delta_i through a 3-stage ring)
-//   warp  9      tcgen05 issuer                                   warps 10,11  pad the third warpgroup (setmaxnreg)
+//   warps 9, 10  tcgen05 issuers (A: S^T, dP^T, dV;  B: dK, dQ^T)  warp 11       pads the third warpgroup (setmaxnreg)
 // Tensor memory (512 columns): [0,64) S^T/P^T even, [64,128) S^T/P^T odd, [128,192) dP^T, [192,256) dQ^T,
 // [256,384) dV, [384,512) dK.
 // A small pre-pass produces, per (batch, head, query):  -LSE log2(e)  and  -Delta scale  with Delta = rowsum(dO o O).
@@ -164,13 +164,13 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   uint64_t* ring_empty = bars + 4;     // [NS]
   uint64_t* s_full = bars + 7;         // [2]
   uint64_t* dp_full = bars + 9;        // 1
-  uint64_t* p_full = bars + 10;        // 1   (4 warps arrive)
-  uint64_t* ds_full = bars + 11;       // [2] (4 warps arrive)
-  uint64_t* ds_free = bars + 13;       // [2]
-  uint64_t* dq_full = bars + 15;       // 1
-  uint64_t* dq_free = bars + 16;       // 1   (4 warps arrive)
-  uint64_t* dkv_full = bars + 17;      // 1
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* p_full = bars + 10;        // [2] (4 warps arrive; one per S^T buffer so that no waiter lags two phases)
+  uint64_t* ds_full = bars + 12;       // [2] (4 warps arrive)
+  uint64_t* ds_free = bars + 14;       // [2]
+  uint64_t* dq_full = bars + 16;       // 1
+  uint64_t* dq_free = bars + 17;       // 1   (4 warps arrive)
+  uint64_t* dkv_full = bars + 18;      // 1   (both MMA issuers commit)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
 
   // key block 0 has the longest walk: key blocks vary SLOWEST in launch order (longest-processing-time-first over the
   // whole grid), heads and batches fastest
@@ -192,13 +192,14 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
     tma_prefetch_desc(&tma_dqh); tma_prefetch_desc(&tma_dk); tma_prefetch_desc(&tma_dv);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 2); }   // both MMA issuers release a stage
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 4); mbar_init(&ds_free[i], 1); }
     mbar_init(dp_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(&p_full[0], 4);
+    mbar_init(&p_full[1], 4);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 4);
-    mbar_init(dkv_full, 1);
+    mbar_init(dkv_full, 2);                      // the last dV (issuer A) and the last dK (issuer B)
     fence_barrier_init();
   }
   if (warp_idx == 9) {
@@ -236,82 +237,81 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       }
     }
   } else if (warp_idx == 9) {
-    // =========================== MMA issuer ===========================
+    // =========================== MMA issuer A: S^T, dP^T, dV (one elected thread runs the whole loop) ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, false, false);     // S^T, dP^T   [128 x 64], K = 128
-    constexpr uint32_t idesc_dv = make_idesc_bf16(128, D, false, true);      // dV (A in TMEM), dK   [128 x 128], K = 64
-    constexpr uint32_t idesc_dq = make_idesc_bf16(128, BQ, true, true);      // dQ^T        [128 x 64], K = 128
-    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_base = smem_u32(sQ), do_base = smem_u32(sdO);
-    const uint32_t ds_base = smem_u32(sdS);
-    auto issue_s = [&](int t) {          // S^T(t) -> buffer t & 1
-      const int st = t % NS;
-      mbar_wait(&ring_full[st], (t / NS) & 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
+    if (elect_one() && steps > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, false, false);     // S^T, dP^T   [128 x 64], K = 128
+      constexpr uint32_t idesc_dv = make_idesc_bf16(128, D, false, true);      // dV (A in TMEM)  [128 x 128], K = 64
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_base = smem_u32(sQ), do_base = smem_u32(sdO);
+      auto issue_s = [&](int t) {          // S^T(t) -> buffer t & 1
+        const int st = t % NS;
+        mbar_wait(&ring_full[st], (t / NS) & 1);
         const uint32_t q_addr = q_base + st * Q_TILE;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           umma_f16<1>(tmem_base + (t & 1) * BQ, desc_k(k_addr, kk, KV_CHUNK), desc_k(q_addr, kk, Q_CHUNK), idesc_s, kk != 0);
         umma_commit(&s_full[t & 1]);
-      }
-      __syncwarp();
-    };
-    auto issue_dp = [&](int t) {         // dP^T(t); the ring stage has been waited for by issue_s(t)
-      const int st = t % NS;
-      if (elect_one()) {
-        const uint32_t do_addr = do_base + st * Q_TILE;
+      };
+      auto issue_dp = [&](int t) {         // dP^T(t); the ring stage has been waited for by issue_s(t)
+        const uint32_t do_addr = do_base + (t % NS) * Q_TILE;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           umma_f16<1>(tmem_dp, desc_k(v_addr, kk, KV_CHUNK), desc_k(do_addr, kk, Q_CHUNK), idesc_s, kk != 0);
         umma_commit(dp_full);
-      }
-      __syncwarp();
-    };
-    mbar_wait(kv_full, 0);
-    if (steps > 0) {
+      };
+      mbar_wait(kv_full, 0);
       issue_s(0);
       issue_dp(0);
-    }
-    for (int t = 0; t < steps; ++t) {
-      const int st = t % NS, b = t & 1;
-      if (t + 1 < steps) issue_s(t + 1);
-      // dV += P^T dO
-      mbar_wait(p_full, t & 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
+      for (int t = 0; t < steps; ++t) {
+        const int st = t % NS, b = t & 1;
+        if (t + 1 < steps) issue_s(t + 1);         // buffer (t+1) & 1: its P^T(t-1) was consumed by dV(t-1), issued earlier by this thread
+        mbar_wait(&p_full[b], (t >> 1) & 1);
+        tcgen05_fence_after();
         const uint32_t do_addr = do_base + st * Q_TILE;
 #pragma unroll
-        for (int kk = 0; kk < BQ / 16; ++kk)
+        for (int kk = 0; kk < BQ / 16; ++kk)       // dV += P^T dO
           umma_f16_ts(tmem_dv, tmem_base + b * BQ + kk * 8, desc_mn(do_addr, kk, Q_CHUNK), idesc_dv, (t | kk) != 0);
+        umma_commit(&ring_empty[st]);              // this issuer's reads of ring stage st (S, dP, dV) are done when this fires
+        if (t + 1 == steps) umma_commit(dkv_full);
+        if (t + 1 < steps) {
+          mbar_wait(&ds_full[b], (t >> 1) & 1);    // the compute warps have read dP^T(t)
+          tcgen05_fence_after();
+          issue_dp(t + 1);
+        }
       }
-      __syncwarp();
-      mbar_wait(&ds_full[b], (t >> 1) & 1);     // dS^T(t) is in shared memory, dP^T(t) has been read
-      tcgen05_fence_after();
-      if (t + 1 < steps) issue_dp(t + 1);
-      mbar_wait(dq_free, (t & 1) ^ 1);          // dQ^T(t-1) has left tensor memory
-      tcgen05_fence_after();
-      if (elect_one()) {
+    }
+  } else if (warp_idx == 10) {
+    // =========================== MMA issuer B: dK, dQ^T ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (elect_one() && steps > 0) {
+      constexpr uint32_t idesc_dk = make_idesc_bf16(128, D, false, true);      // dK   [128 x 128], K = 64
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, BQ, true, true);      // dQ^T [128 x 64], K = 128
+      const uint32_t k_addr = smem_u32(sK), q_base = smem_u32(sQ), ds_base = smem_u32(sdS);
+      mbar_wait(kv_full, 0);
+      for (int t = 0; t < steps; ++t) {
+        const int st = t % NS, b = t & 1;
+        mbar_wait(&ds_full[b], (t >> 1) & 1);      // dS^T(t) is in shared memory (its ring stage landed long before)
         const uint32_t q_addr = q_base + st * Q_TILE, ds_addr = ds_base + b * DS_TILE;
 #pragma unroll
-        for (int kk = 0; kk < BQ / 16; ++kk)     // dK += dS^T Q   (reduction over the 64 queries)
-          umma_f16<1>(tmem_dk, desc_k(ds_addr, kk, DS_TILE), desc_mn(q_addr, kk, Q_CHUNK), idesc_dv, (t | kk) != 0);
+        for (int kk = 0; kk < BQ / 16; ++kk)       // dK += dS^T Q   (reduction over the 64 queries)
+          umma_f16<1>(tmem_dk, desc_k(ds_addr, kk, DS_TILE), desc_mn(q_addr, kk, Q_CHUNK), idesc_dk, (t | kk) != 0);
+        mbar_wait(dq_free, (t & 1) ^ 1);           // dQ^T(t-1) has left tensor memory
+        tcgen05_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)     // dQ^T = K^T dS^T   (reduction over the 128 keys)
+        for (int kk = 0; kk < BN / 16; ++kk)       // dQ^T = K^T dS^T   (reduction over the 128 keys)
           umma_f16<1>(tmem_dq, desc_mn(k_addr, kk, KV_CHUNK), desc_mn(ds_addr, kk, DS_TILE), idesc_dq, kk != 0);
         umma_commit(dq_full);
         umma_commit(&ring_empty[st]);
         umma_commit(&ds_free[b]);
         if (t + 1 == steps) umma_commit(dkv_full);
       }
-      __syncwarp();
     }
-  } else if (warp_idx >= 10) {
+  } else if (warp_idx >= 11) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   } else if (warp_idx >= 4) {
     // =========================== dQ writers (thread = head-dim index) ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
     const uint32_t qd = warp_idx & 3;
-    const uint32_t dcol = qd * 32 + lane;
     const uint32_t lane_off = (qd * 32u) << 16;
     // every warp owns one staging chunk (its 32 head-dim columns x 64 queries, 8 KB) and reduces it on its own: no
     // cross-warp barrier.  The chunk is written and reduced in two halves of 32 queries so that the stores of one half
@@ -401,7 +401,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[b]);
       // ---- dS^T = P^T o (dP^T - Delta) * scale ----
       mbar_wait(dp_full, t & 1);
       tcgen05_fence_after();

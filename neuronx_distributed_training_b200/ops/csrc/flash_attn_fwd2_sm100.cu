@@ -2,21 +2,26 @@
 // window, or full attention).  This is the kernel on the training path (reference call site: the NKI flash kernel at
 // src/neuronx_distributed_training/models/hf_models/modeling_llama.py:482-489).
 //
-// One CTA = 256 query rows (two 128-row tiles) of one (batch, head).  The two tiles ping-pong over the tensor core: while
-// the softmax warps of one tile work on S_j, the MMA warp computes the other tile's scores / P·V products.
+// One CTA = 256 query rows (two 128-row tiles) of one (batch, head), walking over the keys in blocks of 64.
 //
 //   warps 0..3   softmax + epilogue of tile 0   (thread r owns query row r = TMEM lane r)
 //   warps 4..7   softmax + epilogue of tile 1
 //   warp  8      TMA producer: Q0, Q1, then K_j / V_j tiles (128 keys each) through ONE five-slot ring
 //                (order K_0 V_0 K_1 V_1 ...; every tile is used by both query tiles before its slot is released)
-//   warp  9      tcgen05 issuer          (warps 10, 11 only pad the third warpgroup for setmaxnreg)
+//   warps 9, 10  tcgen05 issuers, one per query tile   (warp 11 only pads the third warpgroup for setmaxnreg)
 //
-// Tensor memory (512 columns): [0,128) S0, [128,256) S1, [256,384) O0, [384,512) O1.  P never touches shared memory:
-// the softmax thread overwrites the first 64 columns of its own S row with the bf16-packed probabilities
-// (tcgen05.st) and the P·V product reads its A operand straight from tensor memory (tcgen05.mma with [tmem] A).
-// Since QK(t, j+1) is issued after PV(t, j) and tcgen05.mma executes in issue order, "S_{j+1} is ready" also means
-// "PV_j has retired": the softmax thread may rescale O in place (LAZY rescaling: only when the running maximum grows
-// by more than 2^8, which is exact after the final 1/l normalisation) without any extra barrier.
+// Tensor memory (512 columns): per tile t two score buffers S_t[0], S_t[1] of 64 columns ([128 t, 128 t + 128)) and the
+// output accumulator O_t ([256 + 128 t, ...)).  P never touches shared memory: the softmax thread overwrites the first
+// 32 columns of the score buffer it just read with the bf16-packed probabilities (tcgen05.st) and the P·V product reads
+// its A operand straight from tensor memory (tcgen05.mma with [tmem] A).
+// Because the scores are DOUBLE BUFFERED, QK(t, i+2) only has to follow PV(t, i) (which frees the buffer), so the tensor
+// core computes the scores of the next two key blocks while the softmax warps are still exponentiating block i: the
+// serial chain "softmax -> P·V -> next QK^T -> softmax" of a single-buffer design (measured with the in-kernel timeline:
+// 1450 of 3450 cycles per block pair) is off the critical path.  Each query tile has its own issuer thread, so neither
+// tile ever waits for the other's probabilities.  A quarter of the exponentials run as a cubic polynomial on the FMA
+// pipe (exp2_poly2) to take load off the MUFU unit, which both softmax warpgroups share.
+// LAZY rescaling: O is only rescaled when the running maximum grows by more than 2^8 (exact after the final 1/l
+// normalisation); the rescaling thread first waits for the previous P·V of its tile (pv_done).
 // The softmax inner loop uses the packed fp32 pipe (FFMA2 / FADD2), three-input maxima (FMNMX3) and ex2.approx.
 //
 // Output: O [B,S,Hq,D] bf16 and LSE [B,Hq,S] fp32 (natural log), consumed by the backward kernels.
@@ -32,7 +37,8 @@ namespace fa2 {
 using namespace sm100;
 
 constexpr int BM = 128;          // query rows per tile (two tiles per CTA)
-constexpr int BN = 128;          // keys per block
+constexpr int BN = 128;          // keys per K / V tile in shared memory
+constexpr int BK = 64;           // keys per softmax block (half a tile)
 constexpr int D = 128;           // head dim
 constexpr int TILE_BYTES = 128 * 128 * 2;     // one [128 x 128] bf16 tile = two 16 KB swizzle chunks
 constexpr int CHUNK_BYTES = 128 * 64 * 2;     // [128 rows x 64 cols] bf16
@@ -97,6 +103,29 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// exp2 of a packed pair on the FMA / ALU pipes (Cody-Waite range reduction + cubic minimax polynomial on [-0.5, 0.5],
+// max relative error 7.7e-5 -- far below the bf16 rounding of P).  Inputs are clamped at -126 (also maps -inf to ~0).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& r0, float& r1) {
+  float a, b;
+  unpack2(x2, a, b);
+  x2 = pack2(fmaxf(a, -126.f), fmaxf(b, -126.f));
+  const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+  const uint64_t one = pack2(1.f, 1.f), none = pack2(-1.f, -1.f);
+  const uint64_t xr = fadd2(x2, magic);                 // round(x) in the low mantissa bits
+  const uint64_t n = ffma2(xr, one, nmagic);            // round(x) as a float
+  const uint64_t f = ffma2(n, none, x2);                // x - round(x)  in [-0.5, 0.5]
+  uint64_t q = ffma2(f, pack2(0.05508868f, 0.05508868f), pack2(0.24260405f, 0.24260405f));
+  q = ffma2(q, f, pack2(0.69327623f, 0.69327623f));
+  q = ffma2(q, f, pack2(0.99992895f, 0.99992895f));
+  float p0, p1, x0, x1;
+  unpack2(q, p0, p1);
+  unpack2(xr, x0, x1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(x0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(x1) << 23));
+}
+
+// EMU = how many of every four column pairs take the polynomial exp2 (FMA pipe) instead of MUFU.EX2
+template <int EMU>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o, const Params p) {
@@ -109,11 +138,14 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   uint64_t* q_full = bars;                          // [2]
   uint64_t* kv_full = bars + 2;                     // [5]
   uint64_t* kv_empty = bars + 7;                    // [5]
-  uint64_t* s_full = bars + 12;                     // [2]  S_t(j) is in TMEM (and PV_t(j-1) has retired)
-  uint64_t* p_full = bars + 14;                     // [2]  P_t(j) is in TMEM, O_t has been rescaled if necessary
-  uint64_t* o_full = bars + 16;                     // [2]  last PV of tile t has retired
-  uint64_t* turn = bars + 18;                       // [2]  exp-phase hand-over between the two softmax warpgroups
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* s_full = bars + 12;                     // [2 tiles][2 buffers]  S_t(i) is in TMEM buffer i & 1
+  // P_t(i) is in TMEM buffer i & 1 (O_t rescaled if necessary).  One barrier PER BUFFER: the softmax warps may publish
+  // block i+1 before the issuer has looked at block i, and a parity wait is only sound while the waiter lags its
+  // barrier by at most one phase.
+  uint64_t* p_full = bars + 16;                     // [2 tiles][2 buffers]
+  uint64_t* pv_done = bars + 20;                    // [2]  PV_t(i) has retired (one phase per block)
+  uint64_t* o_full = bars + 22;                     // [2]  the LAST P·V of tile t has retired (single use)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
 
   // heavy (late) query blocks first; heads vary fastest so that concurrently running CTAs have equal lengths and the
   // heads of one GQA group share their K/V tiles in L2
@@ -124,8 +156,9 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   const int qa0 = p.q_off + q0;                                        // absolute position of the CTA's first query
   const int j_lo = (p.window > 0) ? max(0, (qa0 - p.window + 1) / BN) : 0;
   const int j_hi = p.causal ? qa0 / BN + 1 : p.Sk / BN - 1;            // inclusive, for tile 1
-  const int n = j_hi - j_lo + 1;                                       // key blocks of tile 1
-  const int n0 = p.causal ? n - 1 : n;                                 // key blocks of tile 0 (its diagonal is one earlier)
+  const int n = j_hi - j_lo + 1;                                       // K / V tiles (128 keys) of query tile 1
+  const int n0 = p.causal ? n - 1 : n;                                 // ... of query tile 0 (its diagonal is one earlier)
+  const int N1 = 2 * n, N0 = 2 * n0;                                   // 64-key softmax blocks per query tile
   const int row_base = batch * p.S;                                    // row of query 0 of this batch in the [B*S, Hq*D] views
   const int krow_base = batch * p.Sk;                                  // row of key 0 of this batch in the [B*Sk, Hk*D] views
 
@@ -133,14 +166,16 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_o);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_full[2 * i], 1);
+      mbar_init(&s_full[2 * i + 1], 1);
+      mbar_init(&p_full[2 * i], 4);
+      mbar_init(&p_full[2 * i + 1], 4);
+      mbar_init(&pv_done[i], 1);
       mbar_init(&o_full[i], 1);
-      mbar_init(&turn[i], 4);
     }
     for (int i = 0; i < KV_SLOTS; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);       // one release per query tile
     }
     fence_barrier_init();
   }
@@ -184,61 +219,58 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         load_kv(&tma_v, j_lo + i);
       }
     }
-  } else if (warp_idx == 9) {
-    // =========================== MMA issuer ===========================
+  } else if (warp_idx == 9 || warp_idx == 10) {
+    // =========================== MMA issuers: warp 9 -> query tile 0, warp 10 -> query tile 1 ===========================
+    // One elected thread per tile runs the whole chain  wait P_t(i) -> PV_t(i) -> QK_t(i+2).  Two independent issuers keep
+    // the per-instruction overhead (barrier polls, descriptor arithmetic, commits) of the 64-key blocks off the critical
+    // path: measured with one in-order issuer for both tiles, the issue loop itself took 1935 cycles per block pair
+    // against 1024 cycles of tensor work.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-    constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BN, false, false);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, false, true);
-    const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV);
-    // ring position of K_i is 2i, of V_i is 2i + 1
-    auto wait_kv = [&](int u) { mbar_wait(&kv_full[u % KV_SLOTS], (u / KV_SLOTS) & 1); };
-    auto issue_qk = [&](int t, int i, bool release_k) {
-      const int u = 2 * i;
-      wait_kv(u);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t k_addr = kv_addr + (u % KV_SLOTS) * TILE_BYTES;
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BK, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, false, true);
+      const int t = warp_idx - 9;
+      const int nt = t == 0 ? N0 : N1;
+      const uint32_t q_addr = smem_u32(sQ) + t * TILE_BYTES, kv_addr = smem_u32(sKV);
+      const uint32_t tS = tmem_base + t * 128, tO = tmem_base + 256 + t * D;
+      const bool stamp_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+      // a K / V tile that query tile 0 never touches (the last one under causal masking) is released twice by tile 1
+      auto release = [&](int u) {
+        umma_commit(&kv_empty[u % KV_SLOTS]);
+        if (t == 1 && (u >> 1) >= n0) umma_commit(&kv_empty[u % KV_SLOTS]);
+      };
+      auto issue_qk = [&](int i) {
+        const int u = 2 * (i >> 1), half = i & 1;
+        if (half == 0) mbar_wait(&kv_full[u % KV_SLOTS], (u / KV_SLOTS) & 1);
+        // rows [64 half, 64 half + 64) of both 64-column chunks of the K tile
+        const uint32_t k_addr = kv_addr + (u % KV_SLOTS) * TILE_BYTES + half * (BK * 128);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16<1>(tmem_base + t * BN, desc_kmajor(q_addr + t * TILE_BYTES, kk), desc_kmajor(k_addr, kk), idesc_qk,
-                      kk != 0);
-        umma_commit(&s_full[t]);
-        if (release_k) umma_commit(&kv_empty[u % KV_SLOTS]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int t, int i, bool release_v, bool last) {
-      const int u = 2 * i + 1;
-      mbar_wait(&p_full[t], i & 1);
-      const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && i < 128;
-      if (stamp) p.dbg[(2 * 128 + i) * 4 + 2 * t] = clock64();        // MMA warp saw P_t(i)
-      wait_kv(u);
-      tcgen05_fence_after();
-      if (elect_one()) {
+          umma_f16<1>(tS + half * BK, desc_kmajor(q_addr, kk), desc_kmajor(k_addr, kk), idesc_qk, kk != 0);
+        umma_commit(&s_full[2 * t + half]);
+        if (half == 1) release(u);
+      };
+      mbar_wait(&q_full[t], 0);
+      issue_qk(0);
+      issue_qk(1);
+      for (int i = 0; i < nt; ++i) {
+        const int u = 2 * (i >> 1) + 1, half = i & 1;
+        mbar_wait(&p_full[2 * t + half], (i >> 1) & 1);
+        if (stamp_cta && i < 128) p.dbg[(2 * 128 + i) * 4 + 2 * t] = clock64();        // issuer saw P_t(i)
+        if (half == 0) mbar_wait(&kv_full[u % KV_SLOTS], (u / KV_SLOTS) & 1);
+        tcgen05_fence_after();
         const uint32_t v_addr = kv_addr + (u % KV_SLOTS) * TILE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)
-          umma_f16_ts(tmem_base + 256 + t * D, tmem_base + t * BN + kk * 8, desc_mnmajor(v_addr, kk), idesc_pv,
-                      (i | kk) != 0);
-        if (release_v) umma_commit(&kv_empty[u % KV_SLOTS]);
-        if (last) umma_commit(&o_full[t]);
+        for (int kk = 0; kk < BK / 16; ++kk)
+          umma_f16_ts(tO, tS + half * BK + kk * 8, desc_mnmajor(v_addr, 4 * half + kk), idesc_pv, (i | kk) != 0);
+        umma_commit(&pv_done[t]);
+        if (i + 1 == nt) umma_commit(&o_full[t]);
+        if (half == 1) release(u);
+        if (i + 2 < nt) issue_qk(i + 2);
+        if (stamp_cta && i < 128) p.dbg[(2 * 128 + i) * 4 + 2 * t + 1] = clock64();    // PV_t(i) and QK_t(i+2) issued
       }
-      __syncwarp();
-      if (stamp) p.dbg[(2 * 128 + i) * 4 + 2 * t + 1] = clock64();    // PV_t(i) issued
-    };
-    mbar_wait(&q_full[0], 0);
-    issue_qk(0, 0, false);
-    mbar_wait(&q_full[1], 0);
-    issue_qk(1, 0, true);
-    for (int i = 0; i < n; ++i) {
-      if (i < n0) {
-        issue_pv(0, i, false, i + 1 == n0);
-        if (i + 1 < n0) issue_qk(0, i + 1, false);
-      }
-      issue_pv(1, i, true, i + 1 == n);
-      if (i + 1 < n) issue_qk(1, i + 1, true);
     }
-  } else if (warp_idx >= 10) {
+  } else if (warp_idx >= 11) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   } else {
     // =========================== softmax + epilogue (thread = query row) ===========================
@@ -247,40 +279,38 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     const uint32_t qd = warp_idx & 3;                // TMEM lane quadrant
     const uint32_t row = qd * 32 + lane;
     const uint32_t lane_off = (qd * 32u) << 16;
-    const uint32_t tS = tmem_base + lane_off + t * BN;
+    const uint32_t tS = tmem_base + lane_off + t * 128;
     const uint32_t tO = tmem_base + lane_off + 256 + t * D;
-    const int q_pos = qa0 + t * BM + (int)row;        // absolute position (mask arithmetic)
-    const int nt = t == 0 ? n0 : n;
-    const int j_diag = qa0 / BN + t;
+    const int q_tile0 = qa0 + t * BM;                 // absolute position of the tile's first query
+    const int q_pos = q_tile0 + (int)row;             // absolute position (mask arithmetic)
+    const int nt = t == 0 ? N0 : N1;
     const float sc = p.scale_log2;
     float m_used = -INFINITY;                        // raw (unscaled) score domain
     uint64_t l2 = pack2(0.f, 0.f);                   // two partial row sums
     for (int i = 0; i < nt; ++i) {
-      const int j = j_lo + i;
-      mbar_wait(&s_full[t], i & 1);
+      const int b = i & 1;
+      const int k0 = j_lo * BN + i * BK;             // first key of this block
+      mbar_wait(&s_full[2 * t + b], (i >> 1) & 1);
       tcgen05_fence_after();
       const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && qd == 0 && i < 128;
       if (stamp) p.dbg[(t * 128 + i) * 4 + 0] = clock64();            // S_t(i) observed
-      uint32_t sr[4][32];                            // the fp32 score row (raw bits), 4 x 32 columns
-      tmem_ld_32x32b_x32(tS + 0, sr[0]);
-      tmem_ld_32x32b_x32(tS + 32, sr[1]);
-      tmem_ld_32x32b_x32(tS + 64, sr[2]);
-      tmem_ld_32x32b_x32(tS + 96, sr[3]);
+      uint32_t sr[2][32];                            // the fp32 score row (raw bits), 2 x 32 columns
+      tmem_ld_32x32b_x32(tS + b * BK, sr[0]);
+      tmem_ld_32x32b_x32(tS + b * BK + 32, sr[1]);
       tmem_ld_wait();
-      const bool need_mask = (p.causal && j == j_diag) || (p.window > 0 && j * BN <= q_pos - p.window);
+      const bool need_mask = (p.causal && k0 + BK - 1 > q_tile0) || (p.window > 0 && k0 <= q_pos - p.window);
       if (need_mask) {
-        const int k0 = j * BN;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int kpos = k0 + c * 32 + e;
             if ((p.causal && kpos > q_pos) || (p.window > 0 && kpos <= q_pos - p.window)) sr[c][e] = 0xff800000u;  // -inf
           }
       }
-      float mx[4];
+      float mx[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float a0 = fmax3(__uint_as_float(sr[c][0]), __uint_as_float(sr[c][1]), __uint_as_float(sr[c][2]));
         float a1 = fmax3(__uint_as_float(sr[c][3]), __uint_as_float(sr[c][4]), __uint_as_float(sr[c][5]));
 #pragma unroll
@@ -291,7 +321,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         // columns 30, 31 are left by the loop above (6 + 4*6 = 30)
         mx[c] = fmax3(a0, a1, fmaxf(__uint_as_float(sr[c][30]), __uint_as_float(sr[c][31])));
       }
-      const float m_new = fmaxf(fmax3(m_used, mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      const float m_new = fmax3(m_used, mx[0], mx[1]);
       const bool grow = (m_new - m_used) * sc > RESCALE_THRESHOLD;      // true on the first block (m_used = -inf)
       if (__any_sync(0xffffffffu, grow)) {
         const float alpha = (m_used == -INFINITY) ? 0.f : ex2((m_used - m_new) * sc);
@@ -299,6 +329,10 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         l2 = fmul2(l2, a2);
         m_used = m_new;
         if (i > 0) {
+          // O_t is only stable once the previous P·V of this tile has retired.  (S_t(i) has been seen, so PV_t(<= i-2) are
+          // done and the barrier is at most one phase behind the parity waited for.)
+          mbar_wait(&pv_done[t], (i - 1) & 1);
+          tcgen05_fence_after();
 #pragma unroll
           for (int c = 0; c < D / 32; ++c) {
             uint32_t v[32];
@@ -318,46 +352,42 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           }
         }
       }
-      // The exponentials of the two query tiles take turns (tile 0 block i, tile 1 block i, tile 0 block i+1, ...), the
-      // order in which the MMA warp serves them.  Without the hand-over both warpgroups share the MUFU pipe, the
-      // higher-numbered warps win the issue arbitration and overtake tile 0, and the tensor core -- which needs P0 first
-      // -- idles until the preempted tile finishes.  Loading S and the row maximum above stay outside the turn.
-      if (t == 0) {
-        if (i > 0) mbar_wait(&turn[0], (i - 1) & 1);
-      } else if (i < n0) {
-        mbar_wait(&turn[1], i & 1);
-      }
-      if (stamp) p.dbg[(t * 128 + i) * 4 + 1] = clock64();            // turn acquired: exponentials start
+      if (stamp) p.dbg[(t * 128 + i) * 4 + 1] = clock64();            // exponentials start
       // a row can still be fully masked so far (sliding window): keep exp2(-inf - 0) = 0 instead of NaN
       const float m_sc = (m_used == -INFINITY) ? 0.f : m_used * sc;
       const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_sc, -m_sc);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           float x0, x1;
-          unpack2(ffma2(pack2(__uint_as_float(sr[c][2 * e]), __uint_as_float(sr[c][2 * e + 1])), sc2, nm2), x0, x1);
-          x0 = ex2(x0);
-          x1 = ex2(x1);
+          const uint64_t xs = ffma2(pack2(__uint_as_float(sr[c][2 * e]), __uint_as_float(sr[c][2 * e + 1])), sc2, nm2);
+          if ((e & 3) < EMU) {
+            exp2_poly2(xs, x0, x1);
+          } else {
+            unpack2(xs, x0, x1);
+            x0 = ex2(x0);
+            x1 = ex2(x1);
+          }
           l2 = fadd2(l2, pack2(x0, x1));
           pk[e] = pack_bf16x2(x0, x1);
         }
-        tmem_st_32x32b_x16(tS + c * 16, pk);
+        tmem_st_32x32b_x16(tS + b * BK + c * 16, pk);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&turn[t ^ 1]);
-      if (stamp) p.dbg[(t * 128 + i) * 4 + 2] = clock64();            // exponentials issued, turn handed over
+      if (stamp) p.dbg[(t * 128 + i) * 4 + 2] = clock64();            // exponentials issued
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(&p_full[2 * t + b]);
       if (stamp) p.dbg[(t * 128 + i) * 4 + 3] = clock64();            // P_t(i) published
     }
     // ---------------- epilogue: O / l -> bf16 -> smem (the Q tile is free now) -> TMA store; LSE ----------------
     float l_lo, l_hi;
     unpack2(l2, l_lo, l_hi);
     const float l = l_lo + l_hi;
+    // (pv_done cannot be used here: a parity wait is only sound when the waiter lags the barrier by at most one phase,
+    // and after the loop this thread may be zero, one or two P·V products behind; o_full is armed once.)
     mbar_wait(&o_full[t], 0);
     tcgen05_fence_after();
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
@@ -438,13 +468,14 @@ std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k
   p.scale_log2 = (float)(scale * 1.4426950408889634);
   p.lse = lse.data_ptr<float>();
   p.dbg = g_fwd2_dbg;
+  constexpr int EMU = 1;      // 25 % of the exponentials on the FMA pipe (measured: 0 / 25 / 50 % -> 1292 / 1297 / 1257 TFLOP/s)
   static bool once = false;
   if (!once) {
-    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd2_kernel<EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     once = true;
   }
   dim3 grid(Hq * B, p.num_q_pairs);
-  flash_fwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  flash_fwd2_kernel<EMU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, lse};
 }

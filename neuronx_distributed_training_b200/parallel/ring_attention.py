@@ -24,7 +24,6 @@ tile (peer memory bypasses the local L2), which is why the gather is done once u
 from __future__ import annotations
 
 import math
-import os
 from typing import List, Optional
 
 import torch

@@ -5,8 +5,10 @@ lightning_modules/model/base.py:374-381): takes the whole per-DP-rank global bat
 ``num_microbatches``, runs the schedule with activations/grads exchanged between adjacent stages and
 returns the loss on the last stage (0 elsewhere; the caller all-reduces over the PP group).
 
-P2P stays on NCCL (``batch_isend_irecv``) and is issued on a dedicated communication stream so that the
-transfer of microbatch *k* overlaps the compute of microbatch *k+1*.
+P2P stays on NCCL (``batch_isend_irecv``) and is issued on a dedicated communication stream.  A round that only SENDS
+never blocks the compute stream (the tensor is kept alive with ``record_stream``), so the transfer of microbatch *k*
+overlaps the compute of microbatch *k+1*; the compute stream waits for a round only when it carries a receive, i.e. when
+the next kernel really consumes the incoming tensor.
 """
 from __future__ import annotations
 
@@ -34,17 +36,21 @@ class P2PCommunicator:
     def _buf(self):
         return torch.empty(self.shape, dtype=self.dtype, device=self.device)
 
-    def _run(self, ops: List[dist.P2POp]):
+    def _run(self, ops: List[dist.P2POp], has_recv: bool, sent: Tuple[torch.Tensor, ...] = ()):
         if not ops:
             return
         if self.stream is not None:
-            # order after the producer on the compute stream, run on the comm stream, then make the
-            # compute stream wait only when the received tensor is consumed
+            # order after the producer on the compute stream and run on the comm stream
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 for r in dist.batch_isend_irecv(ops):
-                    r.wait()
-            torch.cuda.current_stream().wait_stream(self.stream)
+                    r.wait()                     # stream-level dependency for NCCL work, the host does not block
+            for t in sent:
+                t.record_stream(self.stream)     # the allocator must not recycle a buffer the transfer still reads
+            if has_recv:
+                # the very next kernel consumes the received tensor: the compute stream waits here.  Send-only rounds
+                # return immediately and overlap with whatever the compute stream does next.
+                torch.cuda.current_stream().wait_stream(self.stream)
         else:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
@@ -55,18 +61,20 @@ class P2PCommunicator:
         # Ordering matters when prev == next (pipeline size 2 with virtual stages): messages between one
         # pair of ranks are matched in issue order, so receives must mirror the peer's send order
         # (gradients first, then activations).
-        ops, from_prev, from_next = [], None, None
+        ops, from_prev, from_next, sent = [], None, None, []
         if send_prev is not None:
-            ops.append(dist.P2POp(dist.isend, send_prev.contiguous(), self.prev, self.group))
+            sent.append(send_prev.contiguous())
+            ops.append(dist.P2POp(dist.isend, sent[-1], self.prev, self.group))
         if send_next is not None:
-            ops.append(dist.P2POp(dist.isend, send_next.contiguous(), self.next, self.group))
+            sent.append(send_next.contiguous())
+            ops.append(dist.P2POp(dist.isend, sent[-1], self.next, self.group))
         if recv_next:
             from_next = self._buf()
             ops.append(dist.P2POp(dist.irecv, from_next, self.next, self.group))
         if recv_prev:
             from_prev = self._buf()
             ops.append(dist.P2POp(dist.irecv, from_prev, self.prev, self.group))
-        self._run(ops)
+        self._run(ops, recv_prev or recv_next, tuple(sent))
         return from_prev, from_next
 
     # convenience wrappers that respect the first/last stage

@@ -10,7 +10,7 @@ and padded keys are masked out.  Works for the HF-Llama and HF-Mixtral families 
 from __future__ import annotations
 
 import contextlib
-from typing import List, Optional, Sequence, Union
+from typing import List, Optional, Sequence
 
 import torch
 import torch.nn.functional as F

@@ -16,10 +16,10 @@ C.flash_fwd2_set_debug(torch.empty(0, dtype=torch.int64, device="cuda"))
 d = dbg.cpu().view(3, 128, 4)
 t0 = d[0, 0, 0].item()
 print("block | WG0: S seen, exp start, exp end, P pub | WG1: same | MMA: P0 seen, PV0 issued, P1 seen, PV1 issued   (cycles since WG0's first S)")
-for i in list(range(0, 6)) + list(range(30, 36)) + list(range(58, 64)):
+for i in list(range(0, 6)) + list(range(60, 66)) + list(range(120, 128)):
     row = [d[r, i, c].item() - t0 if d[r, i, c].item() else -1 for r in range(3) for c in range(4)]
     print(i, row[0:4], row[4:8], row[8:12])
-n = 60
+n = 120
 per = (d[0, n, 0].item() - d[0, 4, 0].item()) / (n - 4)
 e0 = sum(d[0, i, 2].item() - d[0, i, 1].item() for i in range(4, n)) / (n - 4)
 e1 = sum(d[1, i, 2].item() - d[1, i, 1].item() for i in range(4, n)) / (n - 4)
@@ -27,5 +27,5 @@ l0 = sum(d[0, i, 1].item() - d[0, i, 0].item() for i in range(4, n)) / (n - 4)
 l1 = sum(d[1, i, 1].item() - d[1, i, 0].item() for i in range(4, n)) / (n - 4)
 w0 = sum(d[0, i + 1, 0].item() - d[0, i, 3].item() for i in range(4, n)) / (n - 4)
 w1 = sum(d[1, i + 1, 0].item() - d[1, i, 3].item() for i in range(4, n)) / (n - 4)
-print(f"period per key block {per:.0f} cycles (tensor work 2048); exp phase WG0 {e0:.0f} WG1 {e1:.0f}; S-seen->exp-start WG0 {l0:.0f} WG1 {l1:.0f}; "
+print(f"period per 64-key block {per:.0f} cycles (tensor work 1024); exp phase WG0 {e0:.0f} WG1 {e1:.0f}; S-seen->exp-start WG0 {l0:.0f} WG1 {l1:.0f}; "
       f"P-published->next-S-seen WG0 {w0:.0f} WG1 {w1:.0f}")
