@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--tp", type=int, default=0, help="tensor-parallel size (default: all GPUs, the headline config)")
     ap.add_argument("--pp", type=int, default=1, help="pipeline-parallel size (BASELINE config 3: --model llama2_7b "
                                                       "--tp 2 --pp 2 on 8 GPUs)")
+    ap.add_argument("--overlap", action="store_true", help="two-stream micro-batches on the NCCL tensor-parallel path "
+                    "(model.fusions.microbatch_overlap): collectives of one micro-batch overlap the GEMMs of the other")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -141,6 +143,9 @@ def main():
     from neuronx_distributed_training_b200.trainer.hf_llama_module import HFLlamaModule
     from neuronx_distributed_training_b200.data.base import SyntheticTokenDataset, default_collate, pin_batch
 
+    if args.overlap:
+        os.environ["NXDT_MB_OVERLAP"] = "1"
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")      # the collectives live in the SMs the capped GEMM grid leaves free
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -41,7 +41,7 @@ void zero1_adam_push(std::vector<int64_t> grads, std::vector<int64_t> params, st
                      const at::Tensor& clip, bool sr, int64_t seed, at::Tensor done_ctr);
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
-             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr, std::vector<int64_t> aflag_peer);
+             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr);
 void tp_barrier(int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t rank, int64_t tp, int64_t epoch_ptr);
 void grouped_gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, const at::Tensor& block_expert, bool b_kmajor);
 void grouped_wgrad(const at::Tensor& x, const at::Tensor& dy, at::Tensor& out, const at::Tensor& offsets, bool accumulate);
@@ -58,13 +58,13 @@ std::vector<at::Tensor> bias_dropout_add_fwd(const at::Tensor& x, const c10::opt
 at::Tensor dropout_bwd(const at::Tensor& dout, const at::Tensor& mask, double p);
 at::Tensor embedding_fwd(const at::Tensor& ids, const at::Tensor& w, int64_t vocab_start, bool seq_first);
 void embedding_bwd_(at::Tensor dw, const at::Tensor& ids, const at::Tensor& g, int64_t vocab_start, bool seq_first);
-std::vector<at::Tensor> flash_attn_bwd_preview(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k,
-                                               const at::Tensor& v, const at::Tensor& out, const at::Tensor& lse,
-                                               bool causal, int64_t window, double scale);
 std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                                        const at::Tensor& out, const at::Tensor& lse, bool causal, int64_t window, double scale,
                                        int64_t q_offset);
+void gemm_set_cta_limit(int64_t n);
+int64_t gemm_get_cta_limit();
 void flash_fwd2_set_debug(const at::Tensor& t);
+void flash_bwd2_set_debug(const at::Tensor& t);
 std::vector<at::Tensor> fp8_quantize_rows(const at::Tensor& x);
 std::vector<at::Tensor> fp8_quantize_cols_transposed(const at::Tensor& x);
 void gemm_fp8(const at::Tensor& a_q, const at::Tensor& a_scale, const at::Tensor& b_q, const at::Tensor& b_scale,
@@ -72,6 +72,8 @@ void gemm_fp8(const at::Tensor& a_q, const at::Tensor& a_scale, const at::Tensor
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
+  m.def("gemm_set_cta_limit", &gemm_set_cta_limit, "cap the persistent GEMM grid (0 = one CTA per SM): leaves SMs to concurrent collectives");
+  m.def("gemm_get_cta_limit", &gemm_get_cta_limit);
   m.def("gemm_fp8", &gemm_fp8, "preview: e4m3 tcgen05 GEMM (kind::f8f6f4) with per-row scales of both operands");
   m.def("fp8_quantize_rows", &fp8_quantize_rows, "bf16 [R,C] -> e4m3 bytes + one fp32 scale per row");
   m.def("fp8_quantize_cols_transposed", &fp8_quantize_cols_transposed,
@@ -91,13 +93,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("flash_attn_fwd", &flash_attn_fwd, "tcgen05 flash attention forward (head_dim 128); q_offset / longer k, v: context parallelism",
         py::arg("q"), py::arg("k"), py::arg("v"), py::arg("causal"), py::arg("window"), py::arg("scale"), py::arg("q_offset") = 0);
   m.def("flash_fwd2_set_debug", &flash_fwd2_set_debug, "in-kernel clock64 timeline of CTA (0,0) of the forward kernel");
+  m.def("flash_bwd2_set_debug", &flash_bwd2_set_debug, "in-kernel clock64 timeline of CTA (0,0) of the backward kernel");
   m.def("flash_attn_fwd1", &flash_attn_fwd1, "single-tile forward kernel (any multiple of 128)");
   m.def("flash_attn_bwd", &flash_attn_bwd,
         "tcgen05 flash attention backward: transposed scores, P^T in TMEM, software-pipelined (training path)",
         py::arg("dout"), py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("causal"),
         py::arg("window"), py::arg("scale"), py::arg("q_offset") = 0);
-  m.def("flash_attn_bwd_preview", &flash_attn_bwd_preview,
-        "tcgen05 causal flash attention backward (preview: compiled, not yet validated on hardware)");
   m.def("ag_gemm", &ag_gemm, "fused all-gather -> tcgen05 GEMM over peer memory");
   m.def("ag_only", &ag_only);
   m.def("fused_tp_set_debug", &fused_tp_set_debug);

@@ -17,9 +17,12 @@
 // The five GEMMs of step t are software-pipelined against the compute warps: S^T(t+1) is issued before dV(t), and
 // dP^T(t+1) as soon as dS^T(t) exists, so the tensor core always has the next scores ready while the exponentials run.
 //
-//   warps 0..3   compute (P, dS) + final dK / dV epilogue        warps 4..7   dQ writers
-//   warp  8      TMA producer (K, V once; Q_i, dO_i, LSE_i, Delta_i through a 3-stage ring)
-//   warps 9, 10  tcgen05 issuers (A: S^T, dP^T, dV;  B: dK, dQ^T)  warp 11       pads the third warpgroup (setmaxnreg)
+//   warps 0..7   compute (P, dS): two warpgroups, each takes 32 of the 64 query columns of every key row (the in-kernel
+//                timeline showed ONE compute warpgroup to be the critical path: 2260 cycles per step against 1280 cycles
+//                of tensor work); they also write dV (warpgroup 0) and dK (warpgroup 1) at the end
+//   warps 8..11  dQ writers
+//   warp  12     TMA producer (K, V once; Q_i, dO_i, LSE_i, Delta_i through a 3-stage ring)
+//   warps 13, 14 tcgen05 issuers (A: S^T, dP^T, dV;  B: dK, dQ^T)  warp 15       pads the fourth warpgroup (setmaxnreg)
 // Tensor memory (512 columns): [0,64) S^T/P^T even, [64,128) S^T/P^T odd, [128,192) dP^T, [192,256) dQ^T,
 // [256,384) dV, [384,512) dK.
 // A small pre-pass produces, per (batch, head, query):  -LSE log2(e)  and  -Delta scale  with Delta = rowsum(dO o O).
@@ -46,7 +49,7 @@ constexpr int DQ_STAGE = 64 * 128 * 4;        // fp32 [64 q x 128 d] as four [64
 constexpr int DQ_CHUNK = 64 * 32 * 4;
 constexpr int NS = 3;                         // Q / dO ring stages
 constexpr int STAT_BYTES = 2 * BQ * 4;        // per stage: 64 x (-LSE log2 e), 64 x (-Delta scale)
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 512;
 constexpr int SMEM_BYTES = 2 * KV_TILE + NS * 2 * Q_TILE + 2 * DS_TILE + DQ_STAGE + NS * STAT_BYTES + 256 + 1024;
 
 struct Params {
@@ -60,6 +63,7 @@ struct Params {
   float scale_log2;        // scale * log2(e)
   const float* nlse2;      // [B, Hq, S]  -LSE * log2(e)   (-inf for rows without any visible key)
   const float* nds;        // [B, Hq, S]  -Delta * scale
+  long long* dbg;          // optional in-kernel timeline of CTA (0, 0): [4 roles][256 steps][4 stamps] of clock64 (else nullptr)
 };
 
 // ---- shared-memory matrix descriptors (128B swizzle); `rows_chunk_bytes` = bytes of one 64-column chunk of the tile ----
@@ -188,21 +192,21 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   const int row_base = batch * p.S;
   const int krow_base = batch * p.Sk;
 
-  if (warp_idx == 8 && elect_one()) {
+  if (warp_idx == 12 && elect_one()) {
     tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
     tma_prefetch_desc(&tma_dqh); tma_prefetch_desc(&tma_dk); tma_prefetch_desc(&tma_dv);
     mbar_init(kv_full, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 2); }   // both MMA issuers release a stage
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 4); mbar_init(&ds_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 8); mbar_init(&ds_free[i], 1); }
     mbar_init(dp_full, 1);
-    mbar_init(&p_full[0], 4);
-    mbar_init(&p_full[1], 4);
+    mbar_init(&p_full[0], 8);
+    mbar_init(&p_full[1], 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 4);
     mbar_init(dkv_full, 2);                      // the last dV (issuer A) and the last dK (issuer B)
     fence_barrier_init();
   }
-  if (warp_idx == 9) {
+  if (warp_idx == 13) {
     tmem_alloc<1>(tmem_ptr, 512);
     tmem_relinquish<1>();
   }
@@ -212,9 +216,9 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 192, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
 
-  if (warp_idx == 8) {
+  if (warp_idx == 12) {
     // =========================== TMA producer ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * KV_TILE);
       tma_load_2d(sK, &tma_k, kv_full, kv_head * D, krow_base + k0);
@@ -236,9 +240,9 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         bulk_g2s(sStat + st * 2 * BQ + BQ, p.nds + stat, BQ * 4, &ring_full[st]);
       }
     }
-  } else if (warp_idx == 9) {
+  } else if (warp_idx == 13) {
     // =========================== MMA issuer A: S^T, dP^T, dV (one elected thread runs the whole loop) ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (elect_one() && steps > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, false, false);     // S^T, dP^T   [128 x 64], K = 128
       constexpr uint32_t idesc_dv = make_idesc_bf16(128, D, false, true);      // dV (A in TMEM)  [128 x 128], K = 64
@@ -265,24 +269,30 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       for (int t = 0; t < steps; ++t) {
         const int st = t % NS, b = t & 1;
         if (t + 1 < steps) issue_s(t + 1);         // buffer (t+1) & 1: its P^T(t-1) was consumed by dV(t-1), issued earlier by this thread
+        const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < 256;
+        if (stamp) p.dbg[(2 * 256 + t) * 4 + 0] = clock64();        // A: S^T(t+1) issued, waiting for P^T(t)
         mbar_wait(&p_full[b], (t >> 1) & 1);
         tcgen05_fence_after();
+        if (stamp) p.dbg[(2 * 256 + t) * 4 + 1] = clock64();        // A: P^T(t) seen
         const uint32_t do_addr = do_base + st * Q_TILE;
 #pragma unroll
         for (int kk = 0; kk < BQ / 16; ++kk)       // dV += P^T dO
-          umma_f16_ts(tmem_dv, tmem_base + b * BQ + kk * 8, desc_mn(do_addr, kk, Q_CHUNK), idesc_dv, (t | kk) != 0);
+          umma_f16_ts(tmem_dv, tmem_base + b * BQ + (kk >> 1) * 32 + (kk & 1) * 8, desc_mn(do_addr, kk, Q_CHUNK), idesc_dv,
+                      (t | kk) != 0);     // P^T of query half h sits at columns [32 h, 32 h + 16) of the buffer
         umma_commit(&ring_empty[st]);              // this issuer's reads of ring stage st (S, dP, dV) are done when this fires
         if (t + 1 == steps) umma_commit(dkv_full);
+        if (stamp) p.dbg[(2 * 256 + t) * 4 + 2] = clock64();        // A: dV(t) issued
         if (t + 1 < steps) {
           mbar_wait(&ds_full[b], (t >> 1) & 1);    // the compute warps have read dP^T(t)
           tcgen05_fence_after();
           issue_dp(t + 1);
         }
+        if (stamp) p.dbg[(2 * 256 + t) * 4 + 3] = clock64();        // A: dP^T(t+1) issued
       }
     }
-  } else if (warp_idx == 10) {
+  } else if (warp_idx == 14) {
     // =========================== MMA issuer B: dK, dQ^T ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (elect_one() && steps > 0) {
       constexpr uint32_t idesc_dk = make_idesc_bf16(128, D, false, true);      // dK   [128 x 128], K = 64
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, BQ, true, true);      // dQ^T [128 x 64], K = 128
@@ -291,12 +301,16 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       for (int t = 0; t < steps; ++t) {
         const int st = t % NS, b = t & 1;
         mbar_wait(&ds_full[b], (t >> 1) & 1);      // dS^T(t) is in shared memory (its ring stage landed long before)
+        const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < 256;
+        if (stamp) p.dbg[(3 * 256 + t) * 4 + 0] = clock64();        // B: dS^T(t) seen
         const uint32_t q_addr = q_base + st * Q_TILE, ds_addr = ds_base + b * DS_TILE;
 #pragma unroll
         for (int kk = 0; kk < BQ / 16; ++kk)       // dK += dS^T Q   (reduction over the 64 queries)
           umma_f16<1>(tmem_dk, desc_k(ds_addr, kk, DS_TILE), desc_mn(q_addr, kk, Q_CHUNK), idesc_dk, (t | kk) != 0);
+        if (stamp) p.dbg[(3 * 256 + t) * 4 + 1] = clock64();        // B: dK(t) issued
         mbar_wait(dq_free, (t & 1) ^ 1);           // dQ^T(t-1) has left tensor memory
         tcgen05_fence_after();
+        if (stamp) p.dbg[(3 * 256 + t) * 4 + 2] = clock64();        // B: dQ^T buffer free
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)       // dQ^T = K^T dS^T   (reduction over the 128 keys)
           umma_f16<1>(tmem_dq, desc_mn(k_addr, kk, KV_CHUNK), desc_mn(ds_addr, kk, DS_TILE), idesc_dq, kk != 0);
@@ -304,13 +318,14 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         umma_commit(&ring_empty[st]);
         umma_commit(&ds_free[b]);
         if (t + 1 == steps) umma_commit(dkv_full);
+        if (stamp) p.dbg[(3 * 256 + t) * 4 + 3] = clock64();        // B: dQ^T(t) issued
       }
     }
-  } else if (warp_idx >= 11) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-  } else if (warp_idx >= 4) {
+  } else if (warp_idx >= 15) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else if (warp_idx >= 8) {
     // =========================== dQ writers (thread = head-dim index) ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     const uint32_t qd = warp_idx & 3;
     const uint32_t lane_off = (qd * 32u) << 16;
     // every warp owns one staging chunk (its 32 head-dim columns x 64 queries, 8 KB) and reduces it on its own: no
@@ -323,6 +338,8 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       const int q0 = (i_lo + t % n_i) * BQ;
       mbar_wait(dq_full, t & 1);
       tcgen05_fence_after();
+      const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 256 && t < 256;
+      if (stamp) p.dbg[(1 * 256 + t) * 4 + 0] = clock64();          // dQ^T(t) seen
       uint32_t v[2][32];
       tmem_ld_32x32b_x32(tmem_dq + lane_off, v[0]);
       tmem_ld_32x32b_x32(tmem_dq + lane_off + 32, v[1]);
@@ -330,6 +347,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
+      if (stamp) p.dbg[(1 * 256 + t) * 4 + 1] = clock64();          // dQ^T(t) in registers, TMEM released
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         // the reduce that read this half one step ago must have finished with it (at most one newer group in flight)
@@ -343,12 +361,18 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           tma_reduce_add_2d(&tma_dqh, chunk + h * (DQ_CHUNK / 2), head * D + qd * 32, row_base + q0 + h * 32);
           tma_store_commit();
         }
+        if (stamp) p.dbg[(1 * 256 + t) * 4 + 2 + h] = clock64();    // half h staged and its reduce issued
       }
     }
     if (lane == 0) tma_store_wait<0>();
   } else {
-    // =========================== compute: P^T, dS^T (thread = key row) ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // =========================== compute: P^T, dS^T (thread = key row x half of the query columns) ===========================
+    // Two warpgroups split the 64 query columns of a step: two warps per scheduler hide each other's TMEM / shared-memory
+    // / MUFU latencies.  (Measured alternatives: one warpgroup doing all 64 columns 996 TFLOP/s; a two-stage pipeline
+    // P -> dS over the two warpgroups 735 TFLOP/s; this column split 1034 TFLOP/s.)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    constexpr int HQ = BQ / 2;                       // query columns per thread
+    const uint32_t h = warp_idx >> 2;                // which half of the query columns (warpgroup 0 / 1)
     const uint32_t qd = warp_idx & 3;
     const uint32_t row = qd * 32 + lane;
     const uint32_t lane_off = (qd * 32u) << 16;
@@ -357,94 +381,91 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     for (int t = 0; t < steps; ++t) {
       const int st = t % NS, b = t & 1;
       const int q0 = (i_lo + t % n_i) * BQ;
-      const uint32_t nl_addr = smem_u32(sStat) + st * STAT_BYTES, nd_addr = nl_addr + BQ * 4;
+      const uint32_t nl_addr = smem_u32(sStat) + st * STAT_BYTES + h * (HQ * 4), nd_addr = nl_addr + BQ * 4;
       mbar_wait(&ring_full[st], (t / NS) & 1);              // LSE / Delta of this chunk are in shared memory
       mbar_wait(&s_full[b], (t >> 1) & 1);
       tcgen05_fence_after();
-      uint32_t sr[2][32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + b * BQ, sr[0]);
-      tmem_ld_32x32b_x32(tmem_base + lane_off + b * BQ + 32, sr[1]);
+      const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && t < 256;
+      if (stamp) p.dbg[(0 * 256 + t) * 4 + 0] = clock64();          // S^T(t) seen
+      uint32_t sr[HQ];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + b * BQ + h * HQ, sr);
       tmem_ld_wait();
       // masks: causal -> key after the query; window -> key at or before (query - window)
-      const int qa0 = p.q_off + q0;                          // absolute position of the chunk's first query
-      const bool need_mask = (p.causal && qa0 < k0 + BN) || (p.window > 0 && k0 <= qa0 + BQ - 1 - p.window);
-      float pf[BQ];
+      const int qa0 = p.q_off + q0 + (int)h * HQ;            // absolute position of this thread's first query
+      const bool need_mask = (p.causal && qa0 < k0 + BN) || (p.window > 0 && k0 <= qa0 + HQ - 1 - p.window);
+      float pf[HQ];
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 nl = ld_shared_f4(nl_addr + (h * 8 + g) * 16);
-          float x0, x1, x2, x3;
-          unpack2(ffma2(pack2(__uint_as_float(sr[h][4 * g]), __uint_as_float(sr[h][4 * g + 1])), sc2, pack2(nl.x, nl.y)), x0, x1);
-          unpack2(ffma2(pack2(__uint_as_float(sr[h][4 * g + 2]), __uint_as_float(sr[h][4 * g + 3])), sc2, pack2(nl.z, nl.w)), x2, x3);
-          pf[h * 32 + 4 * g + 0] = ex2(x0);
-          pf[h * 32 + 4 * g + 1] = ex2(x1);
-          pf[h * 32 + 4 * g + 2] = ex2(x2);
-          pf[h * 32 + 4 * g + 3] = ex2(x3);
-        }
+      for (int g = 0; g < HQ / 4; ++g) {
+        const float4 nl = ld_shared_f4(nl_addr + g * 16);
+        float x0, x1, x2, x3;
+        unpack2(ffma2(pack2(__uint_as_float(sr[4 * g]), __uint_as_float(sr[4 * g + 1])), sc2, pack2(nl.x, nl.y)), x0, x1);
+        unpack2(ffma2(pack2(__uint_as_float(sr[4 * g + 2]), __uint_as_float(sr[4 * g + 3])), sc2, pack2(nl.z, nl.w)), x2, x3);
+        pf[4 * g + 0] = ex2(x0);
+        pf[4 * g + 1] = ex2(x1);
+        pf[4 * g + 2] = ex2(x2);
+        pf[4 * g + 3] = ex2(x3);
+      }
       if (need_mask) {
 #pragma unroll
-        for (int c = 0; c < BQ; ++c) {
+        for (int c = 0; c < HQ; ++c) {
           const int q_pos = qa0 + c;
           if ((p.causal && kpos > q_pos) || (p.window > 0 && kpos <= q_pos - p.window)) pf[c] = 0.f;
         }
       }
       {
-        uint32_t pk[2][16];
+        uint32_t pk[HQ / 2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int e = 0; e < 16; ++e) pk[h][e] = pack_bf16x2(pf[h * 32 + 2 * e], pf[h * 32 + 2 * e + 1]);
-        tmem_st_32x32b_x16(tmem_base + lane_off + b * BQ, pk[0]);
-        tmem_st_32x32b_x16(tmem_base + lane_off + b * BQ + 16, pk[1]);
+        for (int e = 0; e < HQ / 2; ++e) pk[e] = pack_bf16x2(pf[2 * e], pf[2 * e + 1]);
+        // The packed P^T of this half goes over the first 16 of ITS OWN 32 score columns ([32 h, 32 h + 16)): the other
+        // warpgroup may still be reading its half of S^T.  The dV product addresses the two halves separately.
+        tmem_st_32x32b_x16(tmem_base + lane_off + b * BQ + h * HQ, pk);
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      if (stamp) p.dbg[(0 * 256 + t) * 4 + 1] = clock64();          // P^T(t) published
       // ---- dS^T = P^T o (dP^T - Delta) * scale ----
       mbar_wait(dp_full, t & 1);
       tcgen05_fence_after();
-      uint32_t dr[2][32];
-      tmem_ld_32x32b_x32(tmem_dp + lane_off, dr[0]);
-      tmem_ld_32x32b_x32(tmem_dp + lane_off + 32, dr[1]);
+      if (stamp) p.dbg[(0 * 256 + t) * 4 + 2] = clock64();          // dP^T(t) seen
+      uint32_t dr[HQ];
+      tmem_ld_32x32b_x32(tmem_dp + lane_off + h * HQ, dr);
       tmem_ld_wait();
       mbar_wait(&ds_free[b], ((t >> 1) & 1) ^ 1);          // the MMAs that read this dS^T buffer two steps ago have retired
       const uint32_t dsrow = smem_u32(sdS) + b * DS_TILE + row * 128;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {                       // 8 queries = one 16-byte group
-          const float4 nda = ld_shared_f4(nd_addr + (h * 8 + 2 * g) * 16), ndb = ld_shared_f4(nd_addr + (h * 8 + 2 * g + 1) * 16);
-          const int c = h * 32 + 8 * g;
-          float e[8];
-          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 0]), __uint_as_float(dr[h][8 * g + 1])), scl2, pack2(nda.x, nda.y)),
-                        pack2(pf[c + 0], pf[c + 1])), e[0], e[1]);
-          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 2]), __uint_as_float(dr[h][8 * g + 3])), scl2, pack2(nda.z, nda.w)),
-                        pack2(pf[c + 2], pf[c + 3])), e[2], e[3]);
-          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 4]), __uint_as_float(dr[h][8 * g + 5])), scl2, pack2(ndb.x, ndb.y)),
-                        pack2(pf[c + 4], pf[c + 5])), e[4], e[5]);
-          unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[h][8 * g + 6]), __uint_as_float(dr[h][8 * g + 7])), scl2, pack2(ndb.z, ndb.w)),
-                        pack2(pf[c + 6], pf[c + 7])), e[6], e[7]);
-          uint4 o;
-          o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
-          o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
-          const int g16 = h * 4 + g;                        // 16-byte group 0..7 within the 128-byte row
-          st_shared_v4(dsrow + ((g16 ^ (row & 7)) * 16), o);
-        }
+      for (int g = 0; g < HQ / 8; ++g) {                    // 8 queries = one 16-byte group
+        const float4 nda = ld_shared_f4(nd_addr + (2 * g) * 16), ndb = ld_shared_f4(nd_addr + (2 * g + 1) * 16);
+        const int c = 8 * g;
+        float e[8];
+        unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[c + 0]), __uint_as_float(dr[c + 1])), scl2, pack2(nda.x, nda.y)),
+                      pack2(pf[c + 0], pf[c + 1])), e[0], e[1]);
+        unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[c + 2]), __uint_as_float(dr[c + 3])), scl2, pack2(nda.z, nda.w)),
+                      pack2(pf[c + 2], pf[c + 3])), e[2], e[3]);
+        unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[c + 4]), __uint_as_float(dr[c + 5])), scl2, pack2(ndb.x, ndb.y)),
+                      pack2(pf[c + 4], pf[c + 5])), e[4], e[5]);
+        unpack2(fmul2(ffma2(pack2(__uint_as_float(dr[c + 6]), __uint_as_float(dr[c + 7])), scl2, pack2(ndb.z, ndb.w)),
+                      pack2(pf[c + 6], pf[c + 7])), e[6], e[7]);
+        uint4 o;
+        o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+        o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+        const int g16 = (int)h * (HQ / 8) + g;              // 16-byte group 0..7 within the 128-byte row
+        st_shared_v4(dsrow + ((g16 ^ (row & 7)) * 16), o);
+      }
       tcgen05_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[b]);
+      if (stamp) p.dbg[(0 * 256 + t) * 4 + 3] = clock64();          // dS^T(t) published
     }
-    // ---------------- dV_j, dK_j: TMEM -> bf16 -> smem (the V / K tiles are free) -> TMA store ----------------
+    // ---------------- warpgroup 0: dV_j, warpgroup 1: dK_j: TMEM -> bf16 -> smem (the V / K tile is free) -> TMA store ----------------
     if (steps > 0) mbar_wait(dkv_full, 0);
     else mbar_wait(kv_full, 0);                  // no step ran: the accumulators were never written, the result is zero
     tcgen05_fence_after();
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t src = which == 0 ? tmem_dv : tmem_dk;
-      const uint32_t orow = smem_u32(which == 0 ? sV : sK) + row * 128;
+    {
+      const uint32_t src = h == 0 ? tmem_dv : tmem_dk;
+      const uint32_t orow = smem_u32(h == 0 ? sV : sK) + row * 128;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -469,25 +490,34 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     }
     tcgen05_fence_before();
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 0) {
-      tma_store_2d(&tma_dv, sV, kv_head * D, krow_base + k0);
-      tma_store_2d(&tma_dv, sV + KV_CHUNK, kv_head * D + 64, krow_base + k0);
-      tma_store_2d(&tma_dk, sK, kv_head * D, krow_base + k0);
-      tma_store_2d(&tma_dk, sK + KV_CHUNK, kv_head * D + 64, krow_base + k0);
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+    if ((threadIdx.x & 127) == 0) {
+      if (h == 0) {
+        tma_store_2d(&tma_dv, sV, kv_head * D, krow_base + k0);
+        tma_store_2d(&tma_dv, sV + KV_CHUNK, kv_head * D + 64, krow_base + k0);
+      } else {
+        tma_store_2d(&tma_dk, sK, kv_head * D, krow_base + k0);
+        tma_store_2d(&tma_dk, sK + KV_CHUNK, kv_head * D + 64, krow_base + k0);
+      }
       tma_store_commit();
       tma_store_wait<0>();
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp_idx == 9) {
+  if (warp_idx == 13) {
     tcgen05_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
 }
 
 }  // namespace fab2
+
+static long long* g_bwd2_dbg = nullptr;
+// int64 tensor of >= 4 * 256 * 4 elements on the device: the next launches record the timeline of CTA (0, 0); empty -> off
+void flash_bwd2_set_debug(const at::Tensor& t) {
+  g_bwd2_dbg = t.numel() >= 4 * 256 * 4 ? reinterpret_cast<long long*>(t.data_ptr<int64_t>()) : nullptr;
+}
 
 // dout / q / out [B,S,Hq,128], k / v [B,Sk,Hk,128] bf16 contiguous (Sk >= q_offset + S: gathered keys under context
 // parallelism, query i at absolute position q_offset + i), lse [B,Hq,S] fp32 (natural log, from the forward).
@@ -540,6 +570,7 @@ std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor&
   p.scale_log2 = (float)(scale * 1.4426950408889634);
   p.nlse2 = nlse2;
   p.nds = nds;
+  p.dbg = g_bwd2_dbg;
   static bool once = false;
   if (!once) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

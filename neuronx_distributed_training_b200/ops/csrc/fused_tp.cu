@@ -279,28 +279,15 @@ struct RsArgs {
   uint32_t epoch;
   const uint32_t* epoch_ptr;
   int rank, tp, rows_per_rank, N, num_n_blocks;
-  int self_reset;                      // 1: the last reducer of a row-block zeroes its arrival counter (no host-side clear)
-  // Arrival FLAGS instead of counters (aflag_peer[0] != nullptr): one epoch-valued word per (row-block, source rank,
-  // n-tile) in the owner's workspace.  Nothing is ever cleared or counted, a word only grows, so the protocol needs no
-  // memset in front of the kernel and a reducer can start on a 256-column chunk as soon as ITS tp tiles have landed.
-  uint32_t* aflag_peer[MAX_TP];
-  const uint32_t* aflag_local;
-  // Blocked staging layout (NXDT_RS_BLOCKED=1, needs N % 64 == 0): a slab is [row-block][64-column chunk] blocks of
-  // 16 KB, each the raw 128B-swizzled shared-memory image of a [128 x 64] bf16 chunk, written with one contiguous bulk
-  // copy over NVLink; the reduce phase applies the same XOR when it reads.
-  int blocked;
 };
 
 struct RsMaps {
   CUtensorMap m[MAX_TP];   // one store map per destination rank: its staging buffer [tp * rows_per_rank, N]
 };
 
-// EXP = false: the validated default protocol (arrival counters cleared in front of the kernel, 2-D TMA stores into the
-// row-major staging slab).  EXP = true: the experimental switches (self-resetting counters, arrival flags, blocked slab
-// layout) are compiled in and selected at run time; keeping them out of the default instantiation keeps its code
-// generation identical to the measured kernel.
-template <bool EXP>
-struct RsGateT {
+// Protocol: arrival counters (one per row-block of the owner) cleared in front of the kernel, partial tiles stored with
+// 2-D TMA into the owner's row-major staging slab, `red.release.sys` on the counter once a tile's stores have drained.
+struct RsGate {
   RsArgs a;
   const CUtensorMap* maps;
   __device__ __forceinline__ void wait_m(int) const {}
@@ -321,29 +308,19 @@ struct RsGateT {
     const int d = m_blk / bpr;
     return a.rank * a.rows_per_rank + (m_blk - d * bpr) * 128;
   }
-  __device__ __forceinline__ uint8_t* peer_chunk(int m_blk, int cn) const {
-    if constexpr (!EXP) return nullptr;
-    if (!a.blocked) return nullptr;
-    const int bpr = a.rows_per_rank / 128;
-    const int d = m_blk / bpr;
-    const size_t blk = ((size_t)a.rank * bpr + (m_blk - d * bpr)) * (size_t)(a.N / 64) + (size_t)(cn / 64);
-    return reinterpret_cast<uint8_t*>(a.stage_peer[d]) + blk * 16384;
-  }
+  __device__ __forceinline__ uint8_t* peer_chunk(int, int) const { return nullptr; }     // always the TMA-store path
   __device__ __forceinline__ void tile_done(int m_blk, int n_blk) const {
     const int bpr = a.rows_per_rank / 128;
     const int d = m_blk / bpr;
-    if (EXP && a.aflag_peer[0] != nullptr)
-      st_release_sys(a.aflag_peer[d] + ((size_t)(m_blk - d * bpr) * a.tp + a.rank) * a.num_n_blocks + n_blk, a.epoch);
-    else
-      red_add_release_sys(a.counter_peer[d] + (m_blk - d * bpr), 1u);
+    (void)n_blk;
+    red_add_release_sys(a.counter_peer[d] + (m_blk - d * bpr), 1u);
   }
 };
 
-template <bool B_MN, bool EXP>
+template <bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ RsMaps maps, const Params p, const RsArgs rs_in) {
-  using RsGate = RsGateT<EXP>;
   extern __shared__ uint8_t smem_raw[];
   RsArgs rs = rs_in;
   if (rs.epoch_ptr != nullptr) rs.epoch = ld_acquire_gpu(rs.epoch_ptr);
@@ -359,15 +336,7 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t target = (uint32_t)(rs.tp * rs.num_n_blocks);
   for (int item = blockIdx.x; item < bpr * n_chunks; item += gridDim.x) {
     const int rb = item / n_chunks, nc = item - rb * n_chunks;
-    if (EXP && rs.aflag_local != nullptr) {
-      static_assert(BLOCK_N == 256, "one reduce chunk == one n-tile");
-      // the tp partial tiles (rb, nc): one lane per source rank
-      if ((int)threadIdx.x < rs.tp)
-        spin_until_ge_sys(rs.aflag_local + ((size_t)rb * rs.tp + threadIdx.x) * rs.num_n_blocks + nc, rs.epoch, 200,
-                          0x600u | (uint32_t)rs.rank);
-    } else if (threadIdx.x == 0) {
-      spin_until_ge_sys(rs.counter_local + rb, target, 200, 0x400u | (uint32_t)rs.rank);
-    }
+    if (threadIdx.x == 0) spin_until_ge_sys(rs.counter_local + rb, target, 200, 0x400u | (uint32_t)rs.rank);
     __syncthreads();
     // 128 rows x 32 sixteen-byte columns per item; every thread keeps 4 independent outputs in flight and issues all
     // tp x 4 slab loads before the adds (the loads are L2 / HBM latency bound otherwise)
@@ -381,17 +350,8 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool ok = u < 128 * 32 && col < rs.N;
 #pragma unroll
         for (int sl = 0; sl < MAX_TP; ++sl)
-          if (ok && sl < rs.tp) {
-            if (EXP && rs.blocked) {
-              const int unit = u & 31;                              // 16-byte unit within the 256 columns of this item
-              const size_t blk = ((size_t)sl * bpr + rb) * (size_t)(rs.N / 64) + (size_t)(nc * 4 + (unit >> 3));
-              const uint8_t* src = reinterpret_cast<const uint8_t*>(rs.stage_local) + blk * 16384 + r * 128 +
-                                   (((unit & 7) ^ (r & 7)) * 16);
-              v[i][sl] = __ldcg(reinterpret_cast<const uint4*>(src));
-            } else {
-              v[i][sl] = __ldcg(reinterpret_cast<const uint4*>(rs.stage_local + ((size_t)sl * rs.rows_per_rank + rb * 128 + r) * rs.N + col));
-            }
-          }
+          if (ok && sl < rs.tp)
+            v[i][sl] = __ldcg(reinterpret_cast<const uint4*>(rs.stage_local + ((size_t)sl * rs.rows_per_rank + rb * 128 + r) * rs.N + col));
       }
 #pragma unroll
       for (int i = 0; i < ILP; ++i) {
@@ -420,17 +380,6 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
     __syncthreads();
-    if (EXP && rs.self_reset && threadIdx.x == 0) {
-      // counter_local[512 + rb] counts the reducers that are done with row-block rb; the last one re-arms both counters.
-      // Safe: arrivals of the next call that uses this parity are only sent after my next handshake, i.e. after this
-      // kernel has completed.
-      const uint32_t done = atomicAdd(rs.counter_local + 512 + rb, 1u);
-      if (done == (uint32_t)(n_chunks - 1)) {
-        rs.counter_local[512 + rb] = 0u;
-        __threadfence();
-        rs.counter_local[rb] = 0u;
-      }
-    }
   }
   dbg_stamp(3);
 }
@@ -438,12 +387,6 @@ gemm_rs_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // Device-resident epoch: incremented by a one-thread kernel in stream order right before every fused op, so that a
 // captured CUDA graph advances the cross-GPU protocol on every replay (a host-passed epoch would be baked in).
 __global__ void bump_epoch_kernel(uint32_t* epoch) { *epoch = *epoch + 1u; }
-// same, and clears the reduce-scatter arrival counters of this call (instead of a memset, so that the clear is an
-// ordinary kernel node in stream / graph order)
-__global__ void bump_epoch_clear_kernel(uint32_t* epoch, uint32_t* counters, int n) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) counters[i] = 0u;
-  if (threadIdx.x == 0) *epoch = *epoch + 1u;
-}
 
 // All-peer barrier at the epoch held in `epoch_ptr`: every rank has finished everything it enqueued before this
 // kernel once the kernel completes on all ranks.  Placed at CUDA-graph boundaries, where the double-buffer parity of
@@ -580,7 +523,7 @@ void ag_only(at::Tensor xg, const at::Tensor& x_local, std::vector<int64_t> xg_p
 // out[rows_per_rank, N] = reduce_scatter_rows( a[M_total, K] * op(b) )
 void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vector<int64_t> stage_peer,
              std::vector<int64_t> counter_peer, int64_t hs_local_ptr, std::vector<int64_t> hs_peer, int64_t epoch,
-             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr, std::vector<int64_t> aflag_peer) {
+             int64_t rank, int64_t tp, bool b_kmajor, int64_t epoch_ptr) {
   using namespace fused;
   TORCH_CHECK(a.is_cuda() && a.is_contiguous() && b.is_contiguous() && out.is_contiguous());
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16);
@@ -615,52 +558,13 @@ void gemm_rs(const at::Tensor& a, const at::Tensor& b, at::Tensor out, std::vect
   // while I am still computing, and what the others need from me is produced in ring order
   p.m_first = ((rank + 1) % tp) * (rows_per_rank / 128);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  // NXDT_RS_CLEAR_KERNEL=1 (experiment for the graph-replay investigation, docs/ROUND2_PLAN.md): clear the counters
-  // with a kernel node instead of a memset node
-  static const bool clear_with_kernel = [] {
-    const char* e = std::getenv("NXDT_RS_CLEAR_KERNEL");
-    return e != nullptr && e[0] == '1';
-  }();
-  // NXDT_RS_SELF_RESET=1 (second experiment): no clear at all, the kernel re-arms its counters itself
-  static const bool self_reset = [] {
-    const char* e = std::getenv("NXDT_RS_SELF_RESET");
-    return e != nullptr && e[0] == '1';
-  }();
-  rs.self_reset = self_reset ? 1 : 0;
-  TORCH_CHECK(!self_reset || rows_per_rank / 128 <= 512, "self-resetting counters support up to 512 row-blocks per rank");
-  static const bool blocked_env = [] {
-    const char* e = std::getenv("NXDT_RS_BLOCKED");
-    return e != nullptr && e[0] == '1';
-  }();
-  rs.blocked = (blocked_env && N % 64 == 0) ? 1 : 0;
-  const bool arrive_flags = !aflag_peer.empty();
-  for (int d = 0; d < MAX_TP; ++d) rs.aflag_peer[d] = nullptr;
-  rs.aflag_local = nullptr;
-  if (arrive_flags) {
-    TORCH_CHECK(epoch_ptr != 0 || epoch > 0, "arrival flags need a protocol epoch");
-    fill_ptrs(aflag_peer, tp, (void**)rs.aflag_peer);
-    rs.aflag_local = rs.aflag_peer[rank];
-    rs.self_reset = 0;
-  }
-  if (self_reset || arrive_flags) {
-    if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
-  } else if (epoch_ptr != 0 && clear_with_kernel) {
-    bump_epoch_clear_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr), rs.counter_local,
-                                                   rows_per_rank / 128);
-  } else {
-    if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
-    C10_CUDA_CHECK(cudaMemsetAsync(rs.counter_local, 0, sizeof(uint32_t) * (rows_per_rank / 128), stream));
-  }
+  if (epoch_ptr != 0) bump_epoch_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(epoch_ptr));
+  C10_CUDA_CHECK(cudaMemsetAsync(rs.counter_local, 0, sizeof(uint32_t) * (rows_per_rank / 128), stream));
   auto run = [&](auto kern) {
     set_smem(kern);
     kern<<<sms, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, maps, p, rs);
   };
-  const bool experimental = rs.self_reset || rs.blocked || arrive_flags;
-  if (experimental) {
-    if (b_kmajor) run(gemm_rs_kernel<false, true>); else run(gemm_rs_kernel<true, true>);
-  } else {
-    if (b_kmajor) run(gemm_rs_kernel<false, false>); else run(gemm_rs_kernel<true, false>);
-  }
+  if (b_kmajor) run(gemm_rs_kernel<false>); else run(gemm_rs_kernel<true>);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

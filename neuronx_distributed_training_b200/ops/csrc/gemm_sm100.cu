@@ -64,6 +64,12 @@ CUtensorMap make_out_map(void* out, int M, int N, bool f32) {
 
 }  // namespace gemm100
 
+// Upper bound on the CTAs of the persistent GEMM grid (0 = one per SM).  The two-stream micro-batch mode lowers it so
+// that a collective of the other stream finds free SMs WHILE a GEMM runs instead of queueing behind its 148 resident CTAs.
+static int g_gemm_cta_limit = 0;
+void gemm_set_cta_limit(int64_t n) { g_gemm_cta_limit = (int)n; }
+int64_t gemm_get_cta_limit() { return g_gemm_cta_limit; }
+
 // out (+)= op(a) op(b).  a_kmajor: a is [M,K] else [K,M];  b_kmajor: b is [N,K] else [K,N]; out is [M,N].
 void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, bool a_kmajor, bool b_kmajor, bool accumulate) {
   using namespace gemm100;
@@ -86,7 +92,7 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, bool a_kmaj
   CUtensorMap tc = make_out_map(out.data_ptr(), M, N, f32);
   Params p = make_params(M, N, K);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  const int grid = std::min(p.num_tiles, sms);
+  const int grid = std::min(p.num_tiles, g_gemm_cta_limit > 0 ? std::min(g_gemm_cta_limit, sms) : sms);
   const int kind = f32 ? (accumulate ? OUT_F32_ADD : OUT_F32_STORE) : (accumulate ? OUT_BF16_ADD : OUT_BF16_STORE);
 #define DISPATCH(AMN, BMN)                                                                      \
   switch (kind) {                                                                               \

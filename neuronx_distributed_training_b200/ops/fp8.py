@@ -21,7 +21,12 @@ from typing import Optional, Tuple
 import torch
 
 E4M3_MAX = 448.0
-_STATE = {"enabled": os.environ.get("NXDT_FP8", "0") == "1"}
+_STATE = {"enabled": os.environ.get("NXDT_FP8", "0") == "1", "native": True}
+
+
+def use_native_kernels(flag: bool) -> None:
+    """Tests only: False routes quantisation and the GEMM through the PyTorch float8 reference of the same recipe."""
+    _STATE["native"] = bool(flag)
 
 
 def set_enabled(flag: bool) -> None:
@@ -34,7 +39,7 @@ def enabled() -> bool:
 
 def _native(x: torch.Tensor):
     from . import C, _use_native
-    if x.is_cuda and x.dtype == torch.bfloat16 and os.environ.get("NXDT_FP8_NATIVE", "0") == "1" and _use_native(x) \
+    if x.is_cuda and x.dtype == torch.bfloat16 and _STATE["native"] and _use_native(x) \
             and hasattr(C(), "gemm_fp8"):
         return C()
     return None
@@ -76,7 +81,7 @@ def gemm(a_q: torch.Tensor, a_scale: torch.Tensor, b_q: torch.Tensor, b_scale: t
         out = torch.empty(M, N, dtype=out_dtype, device=a_q.device)
         accumulate = False
     from . import C, _use_native, _count
-    if a_q.is_cuda and os.environ.get("NXDT_FP8_NATIVE", "0") == "1" and _use_native(a_q) and hasattr(C(), "gemm_fp8") \
+    if a_q.is_cuda and _STATE["native"] and _use_native(a_q) and hasattr(C(), "gemm_fp8") \
             and a_q.shape[1] % 16 == 0 and N % 8 == 0 and out.is_contiguous() and out.dtype in (torch.bfloat16, torch.float32):
         _count()
         C().gemm_fp8(a_q.contiguous(), a_scale.contiguous(), b_q.contiguous(), b_scale.contiguous(), out, accumulate)

@@ -58,12 +58,7 @@ class FusedTP:
         s0 = x0 + 2 * self.max_shard_bytes
         self.stage_off = [s0, s0 + self.max_stage_bytes]
         self.push = os.environ.get("NXDT_AG_MODE", "pull") == "push"
-        # NXDT_RS_ARRIVE_FLAGS=1: reduce-scatter arrivals are epoch-valued flags (one word per row-block x source rank x
-        # n-tile) instead of counters that have to be cleared in front of every call -- see RsArgs in fused_tp.cu
-        self.arrive_flags = os.environ.get("NXDT_RS_ARRIVE_FLAGS", "0") == "1"
-        self.aflag_off = self.stage_off[1] + self.max_stage_bytes
-        self.aflag_bytes = _align(max(self.max_stage_bytes // (128 * 256 * 2) * 4 * 2, 1 << 16))
-        total = self.aflag_off + self.aflag_bytes
+        total = self.stage_off[1] + self.max_stage_bytes
         try:
             import warnings
             with warnings.catch_warnings():
@@ -221,11 +216,8 @@ class FusedTP:
         out = torch.empty(rows, N, dtype=a2d.dtype, device=a2d.device)
         hs_local, hs_peer = self._hs()
         ops._count()
-        aflags: List[int] = []
-        if self.arrive_flags and (M // 128) * ((N + 255) // 256) * 4 <= self.aflag_bytes:
-            aflags = [p + self.aflag_off for p in self.base_ptrs]
         ops.C().gemm_rs(a2d.contiguous(), w, out, stage, cnt, hs_local, hs_peer, epoch, self.rank, self.tp, trans_b,
-                        self._epoch_ptr, aflags)
+                        self._epoch_ptr)
         return out
 
 

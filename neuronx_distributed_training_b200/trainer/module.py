@@ -87,8 +87,10 @@ class BaseModelModule:
         self.cuda_graph_warmup_steps = int(os.environ.get("NXDT_CUDA_GRAPH_WARMUP", "1"))
         self._mb_graph = None
         self._eager_train_steps = 0
-        # EXPERIMENTAL (written after round 1's GPU budget, unvalidated): issue pairs of micro-batches on two CUDA streams
-        # so that the tensor-parallel collectives of one overlap the compute of the other
+        # two-stream micro-batches (model.fusions.microbatch_overlap / NXDT_MB_OVERLAP): pairs of micro-batches are issued on
+        # two CUDA streams so that the tensor-parallel collectives of one overlap the compute of the other.  The persistent
+        # GEMM grid is capped (``comm_sms`` SMs stay free) so that a collective does not queue behind a resident GEMM.
+        self.comm_sms = int(fus.get("comm_sms", os.environ.get("NXDT_COMM_SMS", 16)))
         env = os.environ.get("NXDT_MB_OVERLAP")
         self.use_mb_overlap = (bool(fus.get("microbatch_overlap", False)) if env is None else env == "1") \
             and self.device.type == "cuda" and self.dims.pp == 1 and not self.use_cuda_graph
@@ -326,6 +328,10 @@ class BaseModelModule:
         main = torch.cuda.current_stream()
         if self._mb_streams is None:
             self._mb_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            C = ops.C()
+            if C is not None and hasattr(C, "gemm_set_cta_limit") and self.comm_sms > 0:
+                sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+                C.gemm_set_cta_limit(max(1, sms - self.comm_sms))
         streams = self._mb_streams
         partial = [torch.zeros((), dtype=torch.float32, device=self.device) for _ in streams]
         for s in streams:

@@ -1,5 +1,5 @@
-"""Bandwidth of the flat AdamW step and of sq_norm (run once plain and once with NXDT_ADAM_V2=1; numerics of the variant are
-covered by `pytest tests/test_kernels_gpu.py -k adamw_flat` under the same environment variable)."""
+"""Bandwidth of the flat AdamW step and of sq_norm (numerics are
+covered by `pytest tests/test_kernels_gpu.py -k adamw_flat`)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
@@ -17,7 +17,7 @@ e0.record()
 for i in range(4, 9): step(i)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"adamw_flat ({'v2' if os.environ.get('NXDT_ADAM_V2') == '1' else 'v1'}): {ms:.3f} ms per 2^30 params, {30 * n / ms / 1e9:.2f} TB/s", flush=True)
+print(f"adamw_flat: {ms:.3f} ms per 2^30 params, {30 * n / ms / 1e9:.2f} TB/s", flush=True)
 for _ in range(3): ops.sq_norm(g)
 torch.cuda.synchronize(); e0.record()
 for _ in range(5): ops.sq_norm(g)

@@ -1,4 +1,4 @@
-"""Numerics + timing driver for the PREVIEW tcgen05 flash-attention backward (single GPU).
+"""Numerics + timing driver for the tcgen05 flash-attention backward (single GPU).
 
     python tests/gpu_checks/check_flash_bwd.py            # small shapes vs fp32 eager reference, then Llama-3-8B shape timing
 """
@@ -79,6 +79,4 @@ if __name__ == "__main__":
     one(1, 512, 4, 2, 0, causal=False)
     one(2, 1024, 2, 1, 0, causal=False)
     timing()
-    if os.environ.get("CHECK_PREVIEW"):
-        timing("flash_attn_bwd_preview")
     print("FLASH_BWD_OK")

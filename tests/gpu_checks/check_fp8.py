@@ -1,11 +1,10 @@
-"""Numerics + timing driver for the PREVIEW fp8 (e4m3) tcgen05 GEMM and its quantisation kernels (single GPU).
+"""Numerics + timing driver for the fp8 (e4m3) tcgen05 GEMM and its quantisation kernels (single GPU).
 
-Compares the native kernels (NXDT_FP8_NATIVE=1) with the PyTorch float8 reference of the same recipe and with the fp32
+Compares the native kernels with the PyTorch float8 reference of the same recipe and with the fp32
 product, then times the Llama-3-8B shapes against the bf16 kernel."""
 import os
 import sys
 
-os.environ["NXDT_FP8_NATIVE"] = "1"
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -24,9 +23,9 @@ def numerics():
         x = (torch.randn(M, K, device="cuda") * torch.rand(M, 1, device="cuda") * 4).bfloat16()
         w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
         q, s = C.fp8_quantize_rows(x)
-        os.environ["NXDT_FP8_NATIVE"] = "0"
+        fp8.use_native_kernels(False)
         q_ref, s_ref = fp8.quantize_rows(x)
-        os.environ["NXDT_FP8_NATIVE"] = "1"
+        fp8.use_native_kernels(True)
         assert torch.allclose(s, s_ref, rtol=1e-6), "row scales differ"
         # the kernel multiplies by 1/scale, the reference divides: values on a rounding boundary may land on the adjacent
         # e4m3 code.  Allow <= 0.5 % such elements, each exactly one code apart.
@@ -34,9 +33,9 @@ def numerics():
         step = (q.view(torch.uint8).int() - q_ref.view(torch.uint8).int()).abs().max().item()
         assert mism < 5e-3 and step <= 1, f"quantised bytes differ on {mism:.2%} of the elements, max code distance {step}"
         qt, st = C.fp8_quantize_cols_transposed(x)
-        os.environ["NXDT_FP8_NATIVE"] = "0"
+        fp8.use_native_kernels(False)
         qt_ref, st_ref = fp8.quantize_cols_transposed(x)
-        os.environ["NXDT_FP8_NATIVE"] = "1"
+        fp8.use_native_kernels(True)
         assert torch.allclose(st, st_ref, rtol=1e-6) and (qt != qt_ref).float().mean().item() < 5e-3
         wq, ws = C.fp8_quantize_rows(w)
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)

@@ -8,7 +8,6 @@ import torch, torch.distributed as dist
 from neuronx_distributed_training_b200 import ops
 from neuronx_distributed_training_b200.parallel import state as ps
 from neuronx_distributed_training_b200.parallel.fused import enable_fused_tp
-from neuronx_distributed_training_b200.parallel.layers import shard_master_weight
 from neuronx_distributed_training_b200.models.llama import LlamaConfig, LlamaForCausalLM
 
 ps.init_distributed("nccl")
@@ -24,11 +23,14 @@ g = torch.Generator().manual_seed(5)
 ids = torch.randint(0, 8192, (2, S), generator=g).to(dev)
 
 
-def run(tp_size, sp):
+def build(tp_size, sp):
     ps.destroy_model_parallel()
     ps.initialize_model_parallel(tp_size, 1, 1)
     torch.manual_seed(11)
-    m = LlamaForCausalLM(LlamaConfig(**base, sequence_parallel_enabled=sp), device=dev)
+    return LlamaForCausalLM(LlamaConfig(**base, sequence_parallel_enabled=sp, qkv_linear=True, fuse_qkv=True), device=dev)
+
+
+def fwd_bwd(m, tp_size):
     n_fused = enable_fused_tp(m, seq_len=S, micro_batch=2) if (FUSED and tp_size > 1) else 0
     ops.reset_native_launch_count()
     loss, _ = m(input_ids=ids, labels=ids)
@@ -39,23 +41,36 @@ def run(tp_size, sp):
         gr = (p.main_grad if getattr(p, "main_grad", None) is not None else p.grad).float().clone()
         if tp_size > 1 and getattr(p, "sequence_parallel_enabled", False):
             dist.all_reduce(gr)                  # each TP rank saw S/TP of the tokens (the optimizer does this sum)
-        grads[n] = (gr, bool(getattr(p, "tensor_model_parallel", False)), getattr(p, "partition_dim", -1),
-                    getattr(p, "partition_stride", 1))
+        grads[n] = gr
     return loss.detach().float().clone(), grads, n_fused, ops.native_launch_count()
 
 
-loss_tp, g_tp, n_fused, launches = run(TP, True)
+# The SAME weights in both layouts: the TP=1 model's state goes through the checkpoint converter (framework -> full HF
+# naming -> TP shards), i.e. the code path a user takes to re-shard a checkpoint; gradients are compared the same way.
+from neuronx_distributed_training_b200.checkpoint.converter import CheckpointConverterBase
+ccfg = {"num_attention_heads": base["num_attention_heads"], "num_key_value_heads": base["num_key_value_heads"],
+        "hidden_size": base["hidden_size"], "head_dim": base["head_dim"], "num_hidden_layers": base["num_hidden_layers"]}
+conv1 = CheckpointConverterBase(tp_size=1, pp_size=1, model_style="hf", config=ccfg, kv_size_multiplier=1, fuse_qkv=True, qkv_linear=True)
+convN = CheckpointConverterBase(tp_size=TP, pp_size=1, model_style="hf", config=ccfg, kv_size_multiplier=1, fuse_qkv=True, qkv_linear=True)
+ref = build(1, False)
+loss_1, g_1, _, _ = fwd_bwd(ref, 1)
+full_w = conv1.unshard([[{n: p.detach() for n, p in ref.named_parameters()}]])
+full_g = conv1.unshard([[g_1]])
+del ref
+m = build(TP, True)
 tpr = ps.get_tensor_model_parallel_rank()
-loss_1, g_1, _, _ = run(1, False)
+missing = m.load_state_dict(convN.shard_for_rank(full_w, tpr, 0), strict=False)
+assert not missing.missing_keys, missing.missing_keys
+loss_tp, g_tp, n_fused, launches = fwd_bwd(m, TP)
+want_g = convN.shard_for_rank(full_g, tpr, 0)
 bad = []
 rel_loss = abs(loss_tp.item() - loss_1.item()) / abs(loss_1.item())
 if rel_loss > 1e-3:
     bad.append(f"loss {loss_tp.item()} vs {loss_1.item()}")
 worst_cos, worst_norm = 1.0, 0.0
-assert set(g_tp) == set(g_1)
-for n, (gr, is_tp, dim, stride) in g_tp.items():
-    want = g_1[n][0]
-    want = shard_master_weight(want, dim, TP, tpr, stride) if is_tp else want
+assert set(g_tp) == set(want_g), sorted(set(g_tp) ^ set(want_g))[:6]
+for n, gr in g_tp.items():
+    want = want_g[n].to(gr.device).float()
     cos = torch.nn.functional.cosine_similarity(gr.flatten(), want.flatten(), dim=0).item()
     nr = (gr.norm() / want.norm().clamp_min(1e-12)).item()
     worst_cos, worst_norm = min(worst_cos, cos), max(worst_norm, abs(nr - 1))
