@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--tp", type=int, default=0, help="tensor-parallel size (default: all GPUs, the headline config)")
     ap.add_argument("--pp", type=int, default=1, help="pipeline-parallel size (BASELINE config 3: --model llama2_7b "
                                                       "--tp 2 --pp 2 on 8 GPUs)")
+    ap.add_argument("--cp", type=int, default=1, help="context-parallel size (long-context runs: --seq-len 32768 --tp 4 --cp 2)")
+    ap.add_argument("--fp8", action="store_true", help="BASELINE config 4: linear-layer GEMMs on the e4m3 tcgen05 kernel "
+                    "(model.fusions.fp8_gemm; 1xK row / column block scales, fp32 accumulation)")
     ap.add_argument("--overlap", action="store_true", help="two-stream micro-batches on the NCCL tensor-parallel path "
                     "(model.fusions.microbatch_overlap): collectives of one micro-batch overlap the GEMMs of the other")
     ap.add_argument("--no-e2e", action="store_true")
@@ -156,9 +159,10 @@ def main():
         ps.init_distributed("nccl")
     tp = args.tp or world
     pp = args.pp
-    assert world % (tp * pp) == 0, f"world {world} not divisible by tp*pp = {tp * pp}"
-    dp = world // (tp * pp)
-    ps.initialize_model_parallel(tensor_model_parallel_size=tp, pipeline_model_parallel_size=pp)
+    cp = args.cp
+    assert world % (tp * pp * cp) == 0, f"world {world} not divisible by tp*pp*cp = {tp * pp * cp}"
+    dp = world // (tp * pp * cp)
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp, pipeline_model_parallel_size=pp, context_parallel_size=cp)
     if args.impl == "baseline":
         ops.set_backend("torch")
     recompute = args.recompute
@@ -196,14 +200,15 @@ def main():
                     "gradient_clip_val": 1.0},
         "exp_manager": {"create_checkpoint_callback": False, "create_tensorboard_logger": False},
         "distributed_strategy": {"tensor_model_parallel_size": tp, "pipeline_model_parallel_size": pp,
-                                 "zero1": True, "sequence_parallel": tp > 1, "kv_replicator": 1},
+                                 "context_parallel_size": cp, "zero1": True, "sequence_parallel": tp > 1, "kv_replicator": 1},
         "data": {"micro_batch_size": 1, "global_batch_size": args.global_batch, "synthetic": True},
         "model": {"model_config": args.model, "encoder_seq_length": args.seq_len,
                   "max_position_embeddings": args.seq_len, **({"num_layers": args.layers} if args.layers else {}),
                   "qkv_linear": True,
                   "fuse_qkv": True, "activations_checkpoint_granularity": gran,
                   "activations_checkpoint_recompute": rec_list,
-                  "fusions": {"flash_attention": True, "linear_cross_entropy": True},
+                  "fusions": {"flash_attention": cp == 1, "ring_attention": cp > 1, "linear_cross_entropy": True,
+                              "fp8_gemm": bool(args.fp8)},
                   "optim": {"name": "adamw_fp32OptState", "lr": 1.5e-4, "weight_decay": 0.01, "betas": [0.9, 0.999],
                             "sched": {"name": "LinearAnnealingWithWarmUp", "warmup_steps": 100, "max_steps": 100000}}},
         "precision": {"type": "mixed_precision"},
@@ -285,14 +290,15 @@ def main():
                       + " training tokens/sec (whole job, device-timed, max over ranks)",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+            "vs_baseline": None,
+            "dtype": "fp8 e4m3 linear GEMMs (1xK block scales, fp32 accumulate), bf16 elsewhere" if args.fp8 else "bf16", "data": "synthetic tokens, random-init weights",
             "impl": args.impl,
             "config": {"model": (args.model.replace("_", "-") if args.layers in (0, hf.num_hidden_layers)
                                  else f"{args.model.replace('_', '-')}-{args.layers}L"),
                        "global_batch": args.global_batch, "micro_batch": 1,
                        "seq_len": args.seq_len,
                        "parallelism": f"tp{tp}" + ("+sp" if tp > 1 else "") + (f"+pp{pp}" if pp > 1 else "")
-                                      + (f"+dp{dp}(zero1)" if dp > 1 else ""),
+                                      + (f"+cp{cp}" if cp > 1 else "") + (f"+dp{dp}(zero1)" if dp > 1 else ""),
                        "precision": "bf16 compute, fp32 master weights + fp32 grad accumulation, AdamW fp32 state",
                        "recompute": recompute, "l2_policy": "inputs larger than L2 (weights+activations >> 126 MB per step)",
                        "peak_mem_gb": round(mem_gb, 1), "final_loss": float(loss),

@@ -38,7 +38,7 @@ class MixtralConfig(LlamaConfig):
 
 def initialize_mixtral_moe_layer(config: MixtralConfig, device=None) -> MoE:
     rk = dict(num_experts=config.num_local_experts, top_k=config.num_experts_per_tok, hidden_size=config.hidden_size,
-              act_fn=config.router_activation, device=device)
+              act_fn=config.router_activation, device=device, dtype=config.dtype)
     router = RouterSinkhorn(**rk, sinkhorn_iterations=config.sinkhorn_iterations, sinkhorn_tol=config.sinkhorn_tol) \
         if config.routing_algorithm == "sinkhorn" else RouterTopK(**rk)
     experts = ExpertMLPs(config.num_local_experts, config.hidden_size, config.intermediate_size, glu=config.glu_mlp,

@@ -41,6 +41,10 @@ def load_balancing_loss_func(router_logits, num_experts: int, top_k: int) -> tor
     return (tokens_per_expert * router_prob_per_expert.unsqueeze(0)).sum() * num_experts
 
 
+# how often the grouped (one-launch-for-all-experts) tcgen05 path ran: lets tests assert it was taken
+_GROUPED_CALLS = {"n": 0}
+
+
 class RouterBase(nn.Module):
     def __init__(self, num_experts: int, top_k: int, hidden_size: int, act_fn: str = "softmax", dtype=torch.float32,
                  device=None, sequence_parallel_enabled: bool = False):
@@ -152,6 +156,7 @@ class ExpertMLPs(nn.Module):
         dev = x_sorted.device
         counts = tokens_per_expert if torch.is_tensor(tokens_per_expert) else torch.tensor(list(tokens_per_expert))
         counts = counts.to(dev)
+        _GROUPED_CALLS["n"] += 1
         n = x_sorted.shape[0]
         dest, block_expert, offsets, t_cap = ops.grouped_layout(counts, n)
         xp = x_sorted.new_zeros(t_cap, x_sorted.shape[1]).index_copy(0, dest, x_sorted)
@@ -339,7 +344,8 @@ class NeuronSwitchMLP(nn.Module):
     def __init__(self, cfg, device=None):
         super().__init__()
         rk = dict(num_experts=cfg.num_moe_experts, top_k=cfg.moe_top_k, hidden_size=cfg.hidden_size,
-                  act_fn=cfg.moe_router_activation, device=device)
+                  act_fn=cfg.moe_router_activation, device=device, dtype=cfg.params_dtype)   # stored in the model dtype (the flat
+        # optimizer buffers hold one dtype); the routing math itself runs in fp32 (RouterBase.logits)
         if cfg.moe_routing_algorithm == "sinkhorn":
             router = RouterSinkhorn(**rk, sinkhorn_iterations=cfg.moe_sinkhorn_iterations, sinkhorn_tol=cfg.moe_sinkhorn_tol)
         else:

@@ -63,6 +63,8 @@ struct Params {
   float scale_log2;        // scale * log2(e)
   const float* nlse2;      // [B, Hq, S]  -LSE * log2(e)   (-inf for rows without any visible key)
   const float* nds;        // [B, Hq, S]  -Delta * scale
+  int split_heads;         // 1: one CTA per (key block, QUERY head); dK / dV are written per query head and summed over the
+                           //    GQA group afterwards.  Used when (KV heads x batches x key blocks) would not fill the GPU.
   long long* dbg;          // optional in-kernel timeline of CTA (0, 0): [4 roles][256 steps][4 stamps] of clock64 (else nullptr)
 };
 
@@ -179,8 +181,12 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   // key block 0 has the longest walk: key blocks vary SLOWEST in launch order (longest-processing-time-first over the
   // whole grid), heads and batches fastest
   const int j = blockIdx.y;
-  const int kv_head = blockIdx.x % p.Hk, batch = blockIdx.x / p.Hk;
-  const int rep = p.Hq / p.Hk;
+  const int groups = p.split_heads ? p.Hq : p.Hk;             // CTAs per (batch, key block)
+  const int grp = blockIdx.x % groups, batch = blockIdx.x / groups;
+  const int kv_head = p.split_heads ? grp / (p.Hq / p.Hk) : grp;
+  const int rep = p.split_heads ? 1 : p.Hq / p.Hk;            // query heads this CTA walks over
+  const int head0 = p.split_heads ? grp : kv_head * rep;      // first of them
+  const int out_col = grp * D;                                // column of this CTA's dK / dV tile in the output views
   const int k0 = j * BN;
   const int n_chunks = p.S / BQ;
   // local 64-query chunks whose (absolute) positions q_off + 64 i .. can see keys of this block
@@ -227,7 +233,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tma_load_2d(sV + KV_CHUNK, &tma_v, kv_full, kv_head * D + 64, krow_base + k0);
       for (int t = 0; t < steps; ++t) {
         const int st = t % NS;
-        const int head = kv_head * rep + t / n_i;
+        const int head = head0 + t / n_i;
         const int q0 = (i_lo + t % n_i) * BQ;
         mbar_wait(&ring_empty[st], ((t / NS) & 1) ^ 1);
         mbar_expect_tx(&ring_full[st], 2 * Q_TILE + STAT_BYTES);
@@ -334,7 +340,7 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     const uint32_t my = smem_u32(sdQ) + qd * DQ_CHUNK + lane * 4;     // row = query (128 bytes), column = lane
     const uint8_t* chunk = sdQ + qd * DQ_CHUNK;
     for (int t = 0; t < steps; ++t) {
-      const int head = kv_head * rep + t / n_i;
+      const int head = head0 + t / n_i;
       const int q0 = (i_lo + t % n_i) * BQ;
       mbar_wait(dq_full, t & 1);
       tcgen05_fence_after();
@@ -493,11 +499,11 @@ flash_bwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
     if ((threadIdx.x & 127) == 0) {
       if (h == 0) {
-        tma_store_2d(&tma_dv, sV, kv_head * D, krow_base + k0);
-        tma_store_2d(&tma_dv, sV + KV_CHUNK, kv_head * D + 64, krow_base + k0);
+        tma_store_2d(&tma_dv, sV, out_col, krow_base + k0);
+        tma_store_2d(&tma_dv, sV + KV_CHUNK, out_col + 64, krow_base + k0);
       } else {
-        tma_store_2d(&tma_dk, sK, kv_head * D, krow_base + k0);
-        tma_store_2d(&tma_dk, sK + KV_CHUNK, kv_head * D + 64, krow_base + k0);
+        tma_store_2d(&tma_dk, sK, out_col, krow_base + k0);
+        tma_store_2d(&tma_dk, sK + KV_CHUNK, out_col + 64, krow_base + k0);
       }
       tma_store_commit();
       tma_store_wait<0>();
@@ -552,15 +558,20 @@ std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor&
   auto dq_acc = at::empty({B, S, Hq, D}, q.options().dtype(at::kFloat));
   C10_CUDA_CHECK(cudaMemsetAsync(dq_acc.data_ptr(), 0, dq_acc.numel() * sizeof(float), stream));
   auto dq = at::empty_like(q);
-  auto dk = at::empty_like(k), dv = at::empty_like(v);
+  // few KV heads per GPU (tensor parallelism): one CTA per (key block, KV head) would leave most SMs idle and the longest
+  // walk (key block 0, all heads of the group) would be the whole kernel: split the walks per query head instead
+  const bool split = Hq > Hk && (int64_t)Hk * B * (Sk / BN) < 2 * (int64_t)sms;
+  auto dk = split ? at::empty({B, Sk, Hq, D}, k.options()) : at::empty_like(k);
+  auto dv = split ? at::empty({B, Sk, Hq, D}, v.options()) : at::empty_like(v);
+  const int Ho = split ? Hq : Hk;             // heads of the dK / dV views the kernel writes
   const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const uint64_t rows = (uint64_t)B * S, krows = (uint64_t)B * Sk;
   CUtensorMap tq = tma::make_2d(q.data_ptr(), BF, 2, rows, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, BQ, 64);
   CUtensorMap tdo = tma::make_2d(dout.data_ptr(), BF, 2, rows, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, BQ, 64);
   CUtensorMap tk = tma::make_2d(k.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
   CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
-  CUtensorMap tdk = tma::make_2d(dk.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
-  CUtensorMap tdv = tma::make_2d(dv.data_ptr(), BF, 2, krows, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
+  CUtensorMap tdk = tma::make_2d(dk.data_ptr(), BF, 2, krows, (uint64_t)Ho * D, (uint64_t)Ho * D * 2, 128, 64);
+  CUtensorMap tdv = tma::make_2d(dv.data_ptr(), BF, 2, krows, (uint64_t)Ho * D, (uint64_t)Ho * D * 2, 128, 64);
   CUtensorMap tdq = tma::make_2d(dq_acc.data_ptr(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, (uint64_t)Hq * D,
                                  (uint64_t)Hq * D * 4, BQ / 2, 32, /*swizzle128=*/false);   // half chunk: 32 q x 32 d
   Params p;
@@ -570,13 +581,14 @@ std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor&
   p.scale_log2 = (float)(scale * 1.4426950408889634);
   p.nlse2 = nlse2;
   p.nds = nds;
+  p.split_heads = split ? 1 : 0;
   p.dbg = g_bwd2_dbg;
   static bool once = false;
   if (!once) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     once = true;
   }
-  dim3 grid(Hk * B, p.num_kblocks);     // heads x batches fastest, key block 0 (longest query walk) first
+  dim3 grid(Ho * B, p.num_kblocks);     // heads x batches fastest, key block 0 (longest query walk) first
   flash_bwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   {
@@ -584,6 +596,11 @@ std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor&
     const int grid2 = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)sms * 16);
     flash_bwd2_cast_kernel<<<grid2, 256, 0, stream>>>((const float4*)dq_acc.data_ptr(), (uint2*)dq.data_ptr(), n4);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
+  }
+  if (split) {      // sum the per-query-head partials of every GQA group (fp32 accumulation)
+    const int r = Hq / Hk;
+    dk = dk.view({B, Sk, Hk, r, D}).sum(3, /*keepdim=*/false, at::kFloat).to(at::kBFloat16);
+    dv = dv.view({B, Sk, Hk, r, D}).sum(3, /*keepdim=*/false, at::kFloat).to(at::kBFloat16);
   }
   return {dq, dk, dv};
 }

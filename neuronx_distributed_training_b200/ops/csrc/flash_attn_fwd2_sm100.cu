@@ -51,7 +51,7 @@ struct Params {
   int B, S, Hq, Hk;      // S = number of (local) queries per batch entry
   int Sk;                // number of keys per batch entry (>= S under context parallelism: the gathered sequence)
   int q_off;             // absolute position of query row 0 relative to key 0 (multiple of 128; context-parallel rank offset)
-  int num_q_pairs;       // S / 256
+  int num_q_units;       // S / (128 * tiles per CTA)
   int window;            // 0 = none; otherwise keys with k <= q - window are masked
   int causal;            // 1: keys after the query are masked; 0: full attention
   float scale_log2;      // softmax scale * log2(e)
@@ -125,7 +125,10 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& r0, float& r1) {
 }
 
 // EMU = how many of every four column pairs take the polynomial exp2 (FMA pipe) instead of MUFU.EX2
-template <int EMU>
+// NT  = query tiles per CTA: 2 (ping-pong, the fast configuration) or 1.  With few heads per GPU (tensor parallelism) the
+//       grid of two-tile CTAs is a single unbalanced wave -- 128 CTAs on 148 SMs whose longest member is 2.2x the mean --
+//       so small grids launch twice as many one-tile CTAs (one softmax warpgroup and one issuer stay idle).
+template <int EMU, int NT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o, const Params p) {
@@ -149,15 +152,15 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 
   // heavy (late) query blocks first; heads vary fastest so that concurrently running CTAs have equal lengths and the
   // heads of one GQA group share their K/V tiles in L2
-  const int qp = p.num_q_pairs - 1 - (int)blockIdx.y;
+  const int qp = p.num_q_units - 1 - (int)blockIdx.y;
   const int head = blockIdx.x % p.Hq, batch = blockIdx.x / p.Hq;
   const int kv_head = head / (p.Hq / p.Hk);
-  const int q0 = qp * 2 * BM;
+  const int q0 = qp * NT * BM;
   const int qa0 = p.q_off + q0;                                        // absolute position of the CTA's first query
   const int j_lo = (p.window > 0) ? max(0, (qa0 - p.window + 1) / BN) : 0;
-  const int j_hi = p.causal ? qa0 / BN + 1 : p.Sk / BN - 1;            // inclusive, for tile 1
-  const int n = j_hi - j_lo + 1;                                       // K / V tiles (128 keys) of query tile 1
-  const int n0 = p.causal ? n - 1 : n;                                 // ... of query tile 0 (its diagonal is one earlier)
+  const int j_hi = p.causal ? qa0 / BN + (NT - 1) : p.Sk / BN - 1;     // inclusive, for the LAST query tile of the CTA
+  const int n = j_hi - j_lo + 1;                                       // K / V tiles (128 keys) of the last query tile
+  const int n0 = (p.causal && NT == 2) ? n - 1 : n;                    // ... of query tile 0 (its diagonal is one earlier)
   const int N1 = 2 * n, N0 = 2 * n0;                                   // 64-key softmax blocks per query tile
   const int row_base = batch * p.S;                                    // row of query 0 of this batch in the [B*S, Hq*D] views
   const int krow_base = batch * p.Sk;                                  // row of key 0 of this batch in the [B*Sk, Hk*D] views
@@ -175,7 +178,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     }
     for (int i = 0; i < KV_SLOTS; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);       // one release per query tile
+      mbar_init(&kv_empty[i], NT);      // one release per query tile
     }
     fence_barrier_init();
   }
@@ -212,14 +215,14 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       };
       load_q(0);
       load_kv(&tma_k, j_lo);
-      load_q(1);
+      if (NT == 2) load_q(1);
       load_kv(&tma_v, j_lo);
       for (int i = 1; i < n; ++i) {
         load_kv(&tma_k, j_lo + i);
         load_kv(&tma_v, j_lo + i);
       }
     }
-  } else if (warp_idx == 9 || warp_idx == 10) {
+  } else if (warp_idx == 9 || (NT == 2 && warp_idx == 10)) {
     // =========================== MMA issuers: warp 9 -> query tile 0, warp 10 -> query tile 1 ===========================
     // One elected thread per tile runs the whole chain  wait P_t(i) -> PV_t(i) -> QK_t(i+2).  Two independent issuers keep
     // the per-instruction overhead (barrier polls, descriptor arithmetic, commits) of the 64-key blocks off the critical
@@ -230,14 +233,14 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BK, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, false, true);
       const int t = warp_idx - 9;
-      const int nt = t == 0 ? N0 : N1;
+      const int nt = (t == 0 && NT == 2) ? N0 : N1;
       const uint32_t q_addr = smem_u32(sQ) + t * TILE_BYTES, kv_addr = smem_u32(sKV);
       const uint32_t tS = tmem_base + t * 128, tO = tmem_base + 256 + t * D;
       const bool stamp_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
       // a K / V tile that query tile 0 never touches (the last one under causal masking) is released twice by tile 1
       auto release = [&](int u) {
         umma_commit(&kv_empty[u % KV_SLOTS]);
-        if (t == 1 && (u >> 1) >= n0) umma_commit(&kv_empty[u % KV_SLOTS]);
+        if (NT == 2 && t == 1 && (u >> 1) >= n0) umma_commit(&kv_empty[u % KV_SLOTS]);
       };
       auto issue_qk = [&](int i) {
         const int u = 2 * (i >> 1), half = i & 1;
@@ -270,8 +273,8 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         if (stamp_cta && i < 128) p.dbg[(2 * 128 + i) * 4 + 2 * t + 1] = clock64();    // PV_t(i) and QK_t(i+2) issued
       }
     }
-  } else if (warp_idx >= 11) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  } else if (warp_idx >= 10 || (NT == 1 && warp_idx >= 4)) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // idle warps (with NT == 1 also the second softmax warpgroup)
   } else {
     // =========================== softmax + epilogue (thread = query row) ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
@@ -283,7 +286,7 @@ flash_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     const uint32_t tO = tmem_base + lane_off + 256 + t * D;
     const int q_tile0 = qa0 + t * BM;                 // absolute position of the tile's first query
     const int q_pos = q_tile0 + (int)row;             // absolute position (mask arithmetic)
-    const int nt = t == 0 ? N0 : N1;
+    const int nt = (t == 0 && NT == 2) ? N0 : N1;
     const float sc = p.scale_log2;
     float m_used = -INFINITY;                        // raw (unscaled) score domain
     uint64_t l2 = pack2(0.f, 0.f);                   // two partial row sums
@@ -450,7 +453,7 @@ std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k
   const int B = q.size(0), S = q.size(1), Hq = q.size(2), Hk = k.size(2);
   const int Sk = k.size(1);
   TORCH_CHECK(v.size(1) == Sk && v.size(2) == Hk && Hq % Hk == 0 && k.size(0) == B && v.size(0) == B);
-  TORCH_CHECK(S % (2 * BM) == 0, "flash_attn_fwd2: the query length must be a multiple of 256");
+  TORCH_CHECK(S % BM == 0, "flash_attn_fwd2: the query length must be a multiple of 128");
   TORCH_CHECK(Sk % BN == 0 && q_offset % BN == 0 && q_offset >= 0 && q_offset + S <= Sk,
               "flash_attn_fwd2: keys must cover [0, q_offset + S) in whole blocks of 128");
   c10::cuda::CUDAGuard guard(q.device());
@@ -463,7 +466,7 @@ std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k
   CUtensorMap tv = tma::make_2d(v.data_ptr(), BF, 2, (uint64_t)B * Sk, (uint64_t)Hk * D, (uint64_t)Hk * D * 2, 128, 64);
   CUtensorMap to = tma::make_2d(out.data_ptr(), BF, 2, (uint64_t)B * S, (uint64_t)Hq * D, (uint64_t)Hq * D * 2, 128, 64);
   Params p;
-  p.B = B; p.S = S; p.Sk = Sk; p.q_off = (int)q_offset; p.Hq = Hq; p.Hk = Hk; p.num_q_pairs = S / (2 * BM); p.window = (int)window;
+  p.B = B; p.S = S; p.Sk = Sk; p.q_off = (int)q_offset; p.Hq = Hq; p.Hk = Hk; p.window = (int)window;
   p.causal = causal ? 1 : 0;
   p.scale_log2 = (float)(scale * 1.4426950408889634);
   p.lse = lse.data_ptr<float>();
@@ -471,11 +474,18 @@ std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k
   constexpr int EMU = 1;      // 25 % of the exponentials on the FMA pipe (measured: 0 / 25 / 50 % -> 1292 / 1297 / 1257 TFLOP/s)
   static bool once = false;
   if (!once) {
-    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd2_kernel<EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd2_kernel<EMU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(flash_fwd2_kernel<EMU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     once = true;
   }
-  dim3 grid(Hq * B, p.num_q_pairs);
-  flash_fwd2_kernel<EMU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  // two-tile CTAs need an even number of 128-row tiles and enough CTAs to balance: below two CTAs per SM the longest
+  // (last) query pair dominates the single wave, and one-tile CTAs halve that critical path
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const bool two_tiles = S % (2 * BM) == 0 && (int64_t)Hq * B * (S / (2 * BM)) >= 2 * (int64_t)sms;
+  p.num_q_units = S / (BM * (two_tiles ? 2 : 1));
+  dim3 grid(Hq * B, p.num_q_units);
+  if (two_tiles) flash_fwd2_kernel<EMU, 2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  else flash_fwd2_kernel<EMU, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   return {out, lse};
 }

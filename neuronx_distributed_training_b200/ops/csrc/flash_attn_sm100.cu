@@ -331,14 +331,11 @@ std::vector<at::Tensor> flash_attn_fwd2(const at::Tensor& q, const at::Tensor& k
 std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
                                         int64_t window, double scale);
 
-// sequence lengths that are a multiple of 256 take the two-tile ping-pong kernel (flash_attn_fwd2_sm100.cu), the
-// remaining multiples of 128 the single-tile kernel below
+// every supported shape runs the ping-pong kernel of flash_attn_fwd2_sm100.cu (two query tiles per CTA, or one when the
+// grid would be too small / the tile count is odd); the single-tile round-1 kernel below stays as `flash_attn_fwd1`
 std::vector<at::Tensor> flash_attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,
                                        int64_t window, double scale, int64_t q_offset) {
-  if (q.dim() == 4 && q.size(1) % 256 == 0) return flash_attn_fwd2(q, k, v, causal, window, scale, q_offset);
-  TORCH_CHECK(q_offset == 0 && k.size(1) == q.size(1), "flash_attn_fwd: a query offset / longer key sequence needs a query "
-              "length that is a multiple of 256");
-  return flash_attn_fwd1(q, k, v, causal, window, scale);
+  return flash_attn_fwd2(q, k, v, causal, window, scale, q_offset);
 }
 
 std::vector<at::Tensor> flash_attn_fwd1(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal,

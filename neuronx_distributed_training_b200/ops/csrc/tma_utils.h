@@ -26,6 +26,23 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled is a DRIVER call and needs a current context on the calling thread.  Threads that never made a
+// runtime call for their device (an autograd / pipeline worker whose device is the default device 0: the c10 device guard
+// skips cudaSetDevice when the index does not change) have none and get CUDA_ERROR_INVALID_CONTEXT (201): bind the primary
+// context with a runtime call and encode again.
+template <typename... A>
+inline CUresult encode_with_context(A... a) {
+  CUresult r = get_encode_fn()(a...);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(dev);
+    cudaFree(nullptr);
+    r = get_encode_fn()(a...);
+  }
+  return r;
+}
+
 // 2-D row-major tensor [rows, cols] with `row_pitch_bytes`; box = {box_cols, box_rows}; 128B swizzle when
 // box_cols * elem_size == 128, otherwise no swizzle.
 inline CUtensorMap make_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
@@ -35,7 +52,8 @@ inline CUtensorMap make_2d(const void* base, CUtensorMapDataType dt, int elem_by
   cuuint64_t strides[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode_fn()(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = encode_with_context(&m, dt, (cuuint32_t)2, const_cast<void*>(base), (const cuuint64_t*)dims, (const cuuint64_t*)strides,
+                                   (const cuuint32_t*)box, (const cuuint32_t*)estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE,
                                swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -55,7 +73,8 @@ inline CUtensorMap make_3d(const void* base, CUtensorMapDataType dt, uint64_t d0
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = get_encode_fn()(&m, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = encode_with_context(&m, dt, (cuuint32_t)3, const_cast<void*>(base), (const cuuint64_t*)dims, (const cuuint64_t*)strides,
+                                   (const cuuint32_t*)box, (const cuuint32_t*)estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE,
                                swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -70,11 +70,36 @@ def timing(fn="flash_attn_bwd"):
     torch.cuda.synchronize()
     ms2 = s.elapsed_time(e) / 10
     print(f"SDPA (cuDNN) backward: {ms2:.3f} ms, {flops / ms2 / 1e9:.0f} TFLOP/s", flush=True)
+    # the per-GPU shape under TP = 8 (4 query heads, 1 KV head): walks split per query head
+    q8, k8, v8, do8 = q[:, :, :4].contiguous(), k[:, :, :1].contiguous(), v[:, :, :1].contiguous(), do[:, :, :4].contiguous()
+    o8, l8 = C.flash_attn_fwd(q8, k8, v8, True, 0, scale)
+    for _ in range(3):
+        bwd(do8, q8, k8, v8, o8, l8, True, 0, scale)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(10):
+        bwd(do8, q8, k8, v8, o8, l8, True, 0, scale)
+    e.record()
+    torch.cuda.synchronize()
+    ms8 = s.elapsed_time(e) / 10
+    qq, kk, vv = (t.clone().requires_grad_(True) for t in (q8, k8, v8))
+    o = torch.nn.functional.scaled_dot_product_attention(qq.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), is_causal=True, enable_gqa=True)
+    g8 = do8.transpose(1, 2)
+    for _ in range(3):
+        torch.autograd.grad(o, (qq, kk, vv), g8, retain_graph=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(10):
+        torch.autograd.grad(o, (qq, kk, vv), g8, retain_graph=True)
+    e.record()
+    torch.cuda.synchronize()
+    ms8s = s.elapsed_time(e) / 10
+    print(f"{fn} backward at TP8 (4/1 heads): {ms8:.3f} ms, {flops / 8 / ms8 / 1e9:.0f} TFLOP/s | SDPA {ms8s:.3f} ms, {flops / 8 / ms8s / 1e9:.0f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":
     for cfg in [(1, 128, 1, 1, 0), (1, 256, 2, 1, 0), (2, 512, 4, 2, 0), (1, 1024, 8, 2, 0), (1, 1024, 4, 4, 300),
-                (1, 2048, 4, 1, 0), (1, 2048, 2, 2, 500)]:
+                (1, 2048, 4, 1, 0), (1, 2048, 2, 2, 500), (2, 4096, 16, 8, 0)]:    # the last one: one CTA per KV head (no split)
         one(*cfg)
     one(1, 512, 4, 2, 0, causal=False)
     one(2, 1024, 2, 1, 0, causal=False)

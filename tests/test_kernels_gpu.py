@@ -169,6 +169,8 @@ def test_flash_attn_fwd(C, B, S, Hq, Hk, window):
     (1, 2048, 4, 1, 700, True),     # sliding window across several key blocks
     (1, 1024, 4, 4, 100, True),     # window shorter than a block
     (2, 512, 4, 2, 0, False),       # full attention (off-diagonal blocks of context parallelism)
+    (2, 2048, 32, 8, 0, True),      # grid large enough for the two-tile forward CTAs (smaller grids use one tile per CTA)
+    (2, 4096, 16, 8, 0, True),      # ... and for one backward CTA per KV head (smaller grids split the walks per query head)
 ])
 def test_flash_attention_forward_backward(C, B, S, Hq, Hk, window, causal):
     """``ops.flash_attention`` (the call the model makes): native tcgen05 forward AND backward through autograd, against
