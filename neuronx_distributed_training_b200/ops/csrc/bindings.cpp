@@ -61,6 +61,10 @@ void embedding_bwd_(at::Tensor dw, const at::Tensor& ids, const at::Tensor& g, i
 std::vector<at::Tensor> flash_attn_bwd(const at::Tensor& dout, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                                        const at::Tensor& out, const at::Tensor& lse, bool causal, int64_t window, double scale,
                                        int64_t q_offset);
+void gemm_mxfp8(const at::Tensor& a_q, const at::Tensor& sfa, const at::Tensor& b_q, const at::Tensor& sfb, at::Tensor& out,
+                bool accumulate);
+std::vector<at::Tensor> mx_quantize_rows(const at::Tensor& x);
+std::vector<at::Tensor> mx_quantize_cols_transposed(const at::Tensor& x);
 void gemm_set_cta_limit(int64_t n);
 int64_t gemm_get_cta_limit();
 void flash_fwd2_set_debug(const at::Tensor& t);
@@ -74,6 +78,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
   m.def("gemm_set_cta_limit", &gemm_set_cta_limit, "cap the persistent GEMM grid (0 = one CTA per SM): leaves SMs to concurrent collectives");
   m.def("gemm_get_cta_limit", &gemm_get_cta_limit);
+  m.def("gemm_mxfp8", &gemm_mxfp8,
+        "MX block-scaled e4m3 GEMM: tcgen05.mma.kind::mxf8f6f4.block_scale, 1x32 E8M0 scale factors staged in tensor memory");
+  m.def("mx_quantize_rows", &mx_quantize_rows, "bf16 [R,C] -> e4m3 + packed E8M0 1x32 block scales along C");
+  m.def("mx_quantize_cols_transposed", &mx_quantize_cols_transposed, "bf16 [R,C] -> e4m3 of x^T [C,R] + packed scales along R");
   m.def("gemm_fp8", &gemm_fp8, "preview: e4m3 tcgen05 GEMM (kind::f8f6f4) with per-row scales of both operands");
   m.def("fp8_quantize_rows", &fp8_quantize_rows, "bf16 [R,C] -> e4m3 bytes + one fp32 scale per row");
   m.def("fp8_quantize_cols_transposed", &fp8_quantize_cols_transposed,

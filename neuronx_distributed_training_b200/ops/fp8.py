@@ -138,8 +138,8 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] 
 
 # ================================================================================================================
 # MX (micro-scaling) variant: one power-of-two scale (E8M0 byte) per 1 x 32 block along the reduction dimension -- the
-# format `tcgen05.mma.kind::mxf8f6f4.block_scale` consumes.  Reference implementation + the scale-factor packing the
-# tensor core expects; the CUDA kernel for it is not written yet (docs/ROUND2_PLAN.md §4).
+# format `tcgen05.mma.kind::mxf8f6f4.block_scale` consumes.  Reference implementation, the scale-factor packing the tensor
+# core expects, and the dispatch to the native kernel (`csrc/gemm_mxfp8_sm100.cu`: scale factors staged in tensor memory).
 # ================================================================================================================
 MX_BLOCK = 32
 
@@ -185,3 +185,26 @@ def unpack_mx_scales(packed: torch.Tensor, R: int, KB: int) -> torch.Tensor:
     rt, kt, _ = packed.shape
     t = packed.reshape(rt, kt, 32, 4, 4).permute(0, 3, 2, 1, 4).reshape(rt * 128, kt * 4)
     return t[:R, :KB].contiguous()
+
+
+def gemm_mx(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: torch.Tensor, out: Optional[torch.Tensor] = None,
+            accumulate: bool = False, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """out[M, N] (+)= MX(a_q, a_sf) @ MX(b_q, b_sf)^T with PACKED scale tiles (``pack_mx_scales``): the block-scaled tensor-core
+    kernel on the GPU (M, K multiples of 128), the dequantise-and-matmul reference elsewhere."""
+    M, K = a_q.shape
+    N = b_q.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a_q.device)
+        accumulate = False
+    from . import C, _use_native, _count
+    if a_q.is_cuda and _STATE["native"] and _use_native(a_q) and hasattr(C(), "gemm_mxfp8") and M % 128 == 0 and K % 128 == 0 \
+            and N % 8 == 0 and out.is_contiguous() and (out.dtype == torch.float32 or (out.dtype == torch.bfloat16 and not accumulate)):
+        _count()
+        C().gemm_mxfp8(a_q.contiguous(), a_sf.contiguous(), b_q.contiguous(), b_sf.contiguous(), out, accumulate)
+        return out
+    r = gemm_mx_reference(a_q, unpack_mx_scales(a_sf, M, K // MX_BLOCK), b_q, unpack_mx_scales(b_sf, N, K // MX_BLOCK), torch.float32)
+    if accumulate:
+        out.add_(r.to(out.dtype))
+    else:
+        out.copy_(r.to(out.dtype))
+    return out
