@@ -21,7 +21,20 @@ from typing import Optional, Tuple
 import torch
 
 E4M3_MAX = 448.0
-_STATE = {"enabled": os.environ.get("NXDT_FP8", "0") == "1", "native": True}
+# recipe: "mx"  = 1 x 32 blocks with E8M0 scales, scaled INSIDE the tensor core (tcgen05.mma.kind::mxf8f6f4.block_scale);
+#         "row" = one fp32 scale per 1 x K row block, applied in the GEMM epilogue (kind::f8f6f4)
+_STATE = {"enabled": os.environ.get("NXDT_FP8", "0") == "1", "native": True, "recipe": os.environ.get("NXDT_FP8_RECIPE", "mx")}
+
+
+def set_recipe(name: str) -> None:
+    if name not in ("mx", "row"):
+        raise ValueError(f"fp8 recipe must be 'mx' or 'row', got {name!r}")
+    _STATE["recipe"] = name
+    clear_cache()
+
+
+def recipe() -> str:
+    return _STATE["recipe"]
 
 
 def use_native_kernels(flag: bool) -> None:
@@ -106,7 +119,12 @@ def _cached(w: torch.Tensor, kind: str):
     ver = w._version
     if hit is not None and hit[0] == ver and hit[1] == w.data_ptr():
         return hit[2]
-    val = quantize_rows(w) if kind == "rows" else quantize_cols_transposed(w)
+    if kind == "mx_rows":
+        val = mx_quantize_rows(w)
+    elif kind == "mx_colsT":
+        val = mx_quantize_cols_transposed(w)
+    else:
+        val = quantize_rows(w) if kind == "rows" else quantize_cols_transposed(w)
     _WCACHE[key] = (ver, w.data_ptr(), val)
     return val
 
@@ -115,8 +133,17 @@ def clear_cache() -> None:
     _WCACHE.clear()
 
 
+def _mx_ok(*dims: int) -> bool:
+    """MX operands: rows and reduction length of both operands must be multiples of 128 (whole scale tiles)."""
+    return _STATE["recipe"] == "mx" and all(d % 128 == 0 for d in dims)
+
+
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [M, K] @ w [N, K]^T"""
+    if _mx_ok(x.shape[0], x.shape[1], w.shape[0]):
+        xq, xs = mx_quantize_rows(x)
+        wq, ws = _cached(w, "mx_rows")
+        return gemm_mx(xq, xs, wq, ws, out=out, out_dtype=x.dtype)
     xq, xs = quantize_rows(x)
     wq, ws = _cached(w, "rows")
     return gemm(xq, xs, wq, ws, out=out, out_dtype=x.dtype)
@@ -124,6 +151,10 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = N
 
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dy [M, N] @ w [N, K]"""
+    if _mx_ok(dy.shape[0], dy.shape[1], w.shape[1]):
+        gq, gs = mx_quantize_rows(dy)
+        wq, ws = _cached(w, "mx_colsT")               # [K, N], blocks along N
+        return gemm_mx(gq, gs, wq, ws, out=out, out_dtype=dy.dtype)
     gq, gs = quantize_rows(dy)
     wq, ws = _cached(w, "colsT")                  # [K, N], scale per input feature k
     return gemm(gq, gs, wq, ws, out=out, out_dtype=dy.dtype)
@@ -131,6 +162,10 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] 
 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """dy [M, N]^T @ x [M, K] -> [N, K]"""
+    if _mx_ok(dy.shape[0], dy.shape[1], x.shape[1]) and (out is None or out.dtype == torch.float32 or not accumulate):
+        gq, gs = mx_quantize_cols_transposed(dy)  # [N, M], blocks along the tokens
+        xq, xs = mx_quantize_cols_transposed(x)   # [K, M]
+        return gemm_mx(gq, gs, xq, xs, out=out, accumulate=accumulate, out_dtype=dy.dtype)
     gq, gs = quantize_cols_transposed(dy)         # [N, M]
     xq, xs = quantize_cols_transposed(x)          # [K, M]
     return gemm(gq, gs, xq, xs, out=out, accumulate=accumulate, out_dtype=dy.dtype)
@@ -155,6 +190,36 @@ def quantize_mx(x: torch.Tensor):
     e = torch.where(amax > 0, torch.ceil(torch.log2(amax / E4M3_MAX)), torch.zeros_like(amax)).clamp(-127, 127)
     q = (xb / torch.exp2(e)[..., None]).to(torch.float8_e4m3fn)
     return q.reshape(R, C).view(torch.uint8), (e + 127).to(torch.uint8)
+
+
+def _mx_native(x: torch.Tensor):
+    from . import C, _use_native
+    if x.is_cuda and x.dtype == torch.bfloat16 and _STATE["native"] and _use_native(x) and hasattr(C(), "mx_quantize_rows"):
+        return C()
+    return None
+
+
+def mx_quantize_rows(x: torch.Tensor):
+    """x [R, C] (C % 128 == 0) -> (e4m3 bytes [R, C], PACKED scale tiles): blocks along C.  Native kernel on the GPU."""
+    c = _mx_native(x)
+    if c is not None and x.is_contiguous() and x.shape[1] % 128 == 0:
+        from . import _count
+        _count()
+        q, sf = c.mx_quantize_rows(x)
+        return q, sf
+    q, s = quantize_mx(x)
+    return q, pack_mx_scales(s)
+
+
+def mx_quantize_cols_transposed(x: torch.Tensor):
+    """x [R, C] (R % 128 == 0) -> (e4m3 bytes of x^T [C, R], PACKED scale tiles): blocks along R."""
+    c = _mx_native(x)
+    if c is not None and x.is_contiguous() and x.shape[0] % 128 == 0 and x.shape[1] % 8 == 0:
+        from . import _count
+        _count()
+        q, sf = c.mx_quantize_cols_transposed(x)
+        return q, sf
+    return mx_quantize_rows(x.t().contiguous())
 
 
 def dequantize_mx(q: torch.Tensor, scale_e8m0: torch.Tensor) -> torch.Tensor:

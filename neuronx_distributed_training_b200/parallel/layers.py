@@ -158,7 +158,7 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         # fp8 linears (model.fusions.fp8_gemm): quantise the LOCAL rows, all-gather e4m3 bytes + one fp32 scale per row
         # (half the NVLink traffic of the bf16 gather, and no rank re-quantises rows it does not own), then the fp8 GEMM.
         # Per-row scales make this bit-identical to gather-then-quantise.  The bf16 fused kernels stand aside.
-        fp8_gather = ops.fp8.enabled() and sequence_parallel and tp > 1 and x2d.dtype in (torch.bfloat16, torch.float32) \
+        fp8_gather = ops.fp8.enabled() and ops.fp8.recipe() == "row" and sequence_parallel and tp > 1 and x2d.dtype in (torch.bfloat16, torch.float32) \
             and os.environ.get("NXDT_FP8_GATHER", "1") != "0"
         if fp8_gather:
             xq, xs = ops.fp8.quantize_rows(x2d.contiguous())

@@ -123,6 +123,8 @@ class BaseModelModule:
         if "fp8_gemm" in fus or str(self.cfg.get("precision", Config({})).get("gemm_dtype", "")).lower() in ("fp8", "e4m3"):
             # linear-layer GEMMs in e4m3 with row / column block scales (ops/fp8.py); LM head, attention, norms stay bf16
             ops.fp8.set_enabled(bool(fus.get("fp8_gemm", True)))
+            if "fp8_recipe" in fus:            # "mx" (default: 1x32 E8M0 blocks, scaled in the tensor core) | "row" (1xK fp32 scales)
+                ops.fp8.set_recipe(str(fus.get("fp8_recipe")))
         if "keep_gathered_input" in fus:
             from ..parallel.layers import set_keep_gathered_input
             set_keep_gathered_input(bool(fus.get("keep_gathered_input")))

@@ -128,3 +128,33 @@ def test_mx_block_scaled_reference_and_scale_packing():
         assert int(tile[(rr % 32) * 16 + (rr // 32) * 4 + kb % 4]) == int(s[r, kb])
     assert torch.equal(fp8.unpack_mx_scales(packed, 200, 8), s)
     assert int(packed[1, 0, (100 % 32) * 16 + (100 // 32) * 4]) == 127     # row 228 does not exist: neutral scale
+
+
+def test_mx_recipe_linear_layer_gemms_against_fp32():
+    """recipe "mx" (1 x 32 E8M0 blocks): forward, dgrad and wgrad of a linear layer through the MX path (reference
+    implementation on the CPU, the block-scaled tensor-core kernel on the GPU) stay within fp8 error of the fp32 products,
+    and the packed scale tiles round-trip."""
+    import torch
+    from neuronx_distributed_training_b200.ops import fp8
+    torch.manual_seed(0)
+    M, N, K = 256, 384, 128
+    x = torch.randn(M, K) * torch.exp(torch.randn(M, 1))
+    w = torch.randn(N, K) * 0.05
+    dy = torch.randn(M, N) * 0.1
+    prev = fp8.recipe()
+    fp8.set_recipe("mx")
+    try:
+        assert fp8._mx_ok(M, K, N)
+        y = fp8.linear_fwd(x, w)
+        dx = fp8.linear_dgrad(dy, w)
+        dw = fp8.linear_wgrad(dy, x)
+    finally:
+        fp8.set_recipe(prev)
+    def rel(a, b): return ((a.float() - b).norm() / b.norm()).item()
+    assert rel(y, x @ w.t()) < 0.05 and rel(dx, dy @ w) < 0.05 and rel(dw, dy.t() @ x) < 0.05
+    q, s = fp8.quantize_mx(x)
+    assert torch.equal(fp8.unpack_mx_scales(fp8.pack_mx_scales(s), M, K // 32), s)
+    # every block is representable: amax / 2^e <= 448, and the scale is the smallest such power of two
+    xb = x.reshape(M, K // 32, 32).abs().amax(-1)
+    e = s.float() - 127
+    assert (xb / torch.exp2(e) <= 448.0 + 1e-3).all() and ((xb / torch.exp2(e - 1) > 448.0) | (xb == 0)).all()
