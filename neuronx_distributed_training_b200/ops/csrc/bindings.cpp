@@ -3,6 +3,8 @@
 #include <vector>
 
 void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, bool a_kmajor, bool b_kmajor, bool accumulate);
+void gemm_set_2cta(bool on);
+void gemm_2cta(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, bool a_kmajor, bool b_kmajor, bool accumulate);
 std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, const at::Tensor& w, double eps);
 std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& rstd);
 std::vector<at::Tensor> rope_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& cos, const at::Tensor& sin, bool conj);
@@ -76,6 +78,8 @@ void gemm_fp8(const at::Tensor& a_q, const at::Tensor& a_scale, const at::Tensor
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
+  m.def("gemm_2cta", &gemm_2cta, "tcgen05 cta_group::2 bf16 GEMM: a cluster of two SMs per 256x256 tile");
+  m.def("gemm_set_2cta", &gemm_set_2cta, "route gemm() through the SM-pair kernel when the shape allows (default on)");
   m.def("gemm_set_cta_limit", &gemm_set_cta_limit, "cap the persistent GEMM grid (0 = one CTA per SM): leaves SMs to concurrent collectives");
   m.def("gemm_get_cta_limit", &gemm_get_cta_limit);
   m.def("gemm_mxfp8", &gemm_mxfp8,

@@ -125,12 +125,41 @@ class BaseModelModule:
             ops.fp8.set_enabled(bool(fus.get("fp8_gemm", True)))
             if "fp8_recipe" in fus:            # "mx" (default: 1x32 E8M0 blocks, scaled in the tensor core) | "row" (1xK fp32 scales)
                 ops.fp8.set_recipe(str(fus.get("fp8_recipe")))
-        if "keep_gathered_input" in fus:
-            from ..parallel.layers import set_keep_gathered_input
-            set_keep_gathered_input(bool(fus.get("keep_gathered_input")))
         if self.model is None:
             self.model = self.build_model()
             self._maybe_enable_fused_tp()
+        self._configure_keep_gathered(fus)
+
+    def _configure_keep_gathered(self, fus) -> None:
+        """``model.fusions.keep_gathered_input``: true | false | auto (default).  Column linears of a sequence-parallel
+        layer either keep their all-gathered input for the weight gradient or gather it a second time in backward.
+        Measured on 8 x B200, Llama-3-8B, TP=8: keeping it is +8.6 % tokens/s for +3.5 GB (the layer is transfer-bound
+        at large TP).  ``auto`` keeps it when TP >= 4 and the extra activations stay below 8 % of the device memory
+        (Llama-3-70B at TP=8 would add 19 GB to a 157 GB step: stays off)."""
+        from ..parallel.layers import ColumnParallelLinear, GQAQKVColumnParallelLinear, set_keep_gathered_input
+        want = fus.get("keep_gathered_input", "auto") if "keep_gathered_input" in fus else "auto"
+        if "NXDT_KEEP_GATHERED" in os.environ:
+            want = os.environ["NXDT_KEEP_GATHERED"] == "1"
+        if isinstance(want, str):
+            want = {"true": True, "false": False}.get(want.lower(), "auto")
+        if want == "auto":
+            want = False
+            if self.device.type == "cuda" and self.dims.tp >= 4 and self.sequence_parallel and self.model is not None:
+                seq = int(self.config.get("encoder_seq_length", None) or self.cfg.data.get("seq_length", 8192))
+                tokens = self.micro_batch_size * max(1, seq // self.dims.cp)
+                in_flight = max(1, self.dims.pp)               # 1F1B holds up to pp micro-batches on the first stage
+                extra = 0
+                for m in self.model.modules():
+                    if isinstance(m, (ColumnParallelLinear, GQAQKVColumnParallelLinear)) and \
+                            getattr(m, "sequence_parallel_enabled", False):
+                        k = getattr(m, "input_size", None) or m.weight.shape[-1]
+                        extra += tokens * int(k) * 2 * (self.dims.tp - 1) // self.dims.tp
+                total = torch.cuda.get_device_properties(self.device).total_memory
+                want = extra * in_flight <= 0.08 * total
+                if ps.get_rank() == 0:
+                    log.info("keep_gathered_input=auto -> %s (%.1f GB of gathered inputs per micro-batch in flight)",
+                             want, extra / 1e9)
+        set_keep_gathered_input(bool(want))
 
     def _maybe_enable_fused_tp(self) -> int:
         """Attach the fused AG->GEMM / GEMM->RS / AG-wgrad kernels (parallel/fused.py) to the sequence-parallel linears.

@@ -25,6 +25,9 @@ KERNELS = {  # output name -> regex on the demangled kernel name
     "grouped_rows_kernel": r"grouped_rows_kernel",
     "grouped_wgrad_kernel": r"grouped_wgrad_kernel",
     "gemm_fp8_kernel": r"gemm_fp8_kernel",
+    "gemm_mxfp8_kernel": r"gemm_mxfp8_kernel",
+    "gemm2cta_kernel": r"gemm2cta::gemm2cta_kernel",
+    "mx_quantize_rows_kernel": r"mx_quantize_rows",
     "zero1_reduce_kernel": r"zero1_reduce",
     "zero1_adam_push_kernel": r"zero1_adam_push",
     "adamw_flat_kernel": r"adamw_flat_kernel",
