@@ -1,4 +1,5 @@
 // Host launcher + kernel instantiations for the sm_100a tcgen05 GEMM (see gemm_sm100.cuh).
+#include <cstdlib>
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -73,7 +74,7 @@ int64_t gemm_get_cta_limit() { return g_gemm_cta_limit; }
 // SM-pair kernel (gemm2cta_sm100.cu) for every shape with more than one 128-row / 128-column block: measured +9..18 % on the
 // K-major (forward) shapes of Llama-3-8B, equal on the MN-major ones.  gemm_set_2cta(false) forces the one-CTA kernel (A/B runs).
 void gemm_2cta(const at::Tensor& a, const at::Tensor& b, at::Tensor& out, bool a_kmajor, bool b_kmajor, bool accumulate);
-static bool g_gemm_2cta = true;
+static bool g_gemm_2cta = [] { const char* e = std::getenv("NXDT_GEMM_2CTA"); return !(e && e[0] == '0'); }();
 void gemm_set_2cta(bool on) { g_gemm_2cta = on; }
 
 // out (+)= op(a) op(b).  a_kmajor: a is [M,K] else [K,M];  b_kmajor: b is [N,K] else [K,N]; out is [M,N].

@@ -509,13 +509,19 @@ def test_whole_model_native_path_matches_library_path(C):
     assert abs(loss_n - loss_f) / abs(loss_f) < max(1e-3, 2 * abs(loss_t - loss_f) / abs(loss_f)), (loss_n, loss_t, loss_f)
     assert set(g_n) == set(g_t) == set(g_f) and g_n
     cosf = torch.nn.functional.cosine_similarity
+    bad, table = [], []
     for name in g_n:
         a, b, f = g_n[name].flatten(), g_t[name].flatten(), g_f[name].flatten()
         cos_n, cos_t = cosf(a, f, dim=0).item(), cosf(b, f, dim=0).item()
-        assert cos_n >= min(0.999, cos_t - 5e-4), (name, cos_n, cos_t)
         dev_n, dev_t = abs(a.norm().item() / f.norm().item() - 1), abs(b.norm().item() / f.norm().item() - 1)
-        assert dev_n <= max(0.02, 2.0 * dev_t + 0.01), (name, dev_n, dev_t)       # (sparse embedding rows: both bf16 paths are ~10 % off)
-        assert cosf(a, b, dim=0).item() > 0.995, name
+        cos_nt = cosf(a, b, dim=0).item()
+        row = f"{name}: cos(native,fp32)={cos_n:.5f} cos(lib,fp32)={cos_t:.5f} cos(native,lib)={cos_nt:.5f} " \
+              f"norm dev native={dev_n:.4f} lib={dev_t:.4f} finite={bool(torch.isfinite(a).all())}"
+        table.append(row)
+        # (sparse embedding rows: both bf16 paths are ~10 % off the fp32 norm)
+        if not (cos_n >= min(0.999, cos_t - 5e-4) and dev_n <= max(0.02, 2.0 * dev_t + 0.01) and cos_nt > 0.995):
+            bad.append(row)
+    assert not bad, "\n".join(["violations:"] + bad + ["all tensors:"] + table)
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 128), (384, 776, 512), (1024, 512, 1024)])
