@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--cp", type=int, default=1, help="context-parallel size (long-context runs: --seq-len 32768 --tp 4 --cp 2)")
     ap.add_argument("--fp8", action="store_true", help="BASELINE config 4: linear-layer GEMMs on the e4m3 tcgen05 kernel "
                     "(model.fusions.fp8_gemm; 1xK row / column block scales, fp32 accumulation)")
+    ap.add_argument("--nvls", action="store_true", help="model.fusions.nvls_norm_allgather: RMSNorm + sequence-parallel "
+                    "all-gather as one NVSwitch-multicast kernel for the linears the fused AG->GEMM kernel leaves on NCCL")
     ap.add_argument("--overlap", action="store_true", help="two-stream micro-batches on the NCCL tensor-parallel path "
                     "(model.fusions.microbatch_overlap): collectives of one micro-batch overlap the GEMMs of the other")
     ap.add_argument("--no-e2e", action="store_true")
@@ -208,7 +210,7 @@ def main():
                   "fuse_qkv": True, "activations_checkpoint_granularity": gran,
                   "activations_checkpoint_recompute": rec_list,
                   "fusions": {"flash_attention": cp == 1, "ring_attention": cp > 1, "linear_cross_entropy": True,
-                              "fp8_gemm": bool(args.fp8)},
+                              "fp8_gemm": bool(args.fp8), "nvls_norm_allgather": bool(args.nvls)},
                   "optim": {"name": "adamw_fp32OptState", "lr": 1.5e-4, "weight_decay": 0.01, "betas": [0.9, 0.999],
                             "sched": {"name": "LinearAnnealingWithWarmUp", "warmup_steps": 100, "max_steps": 100000}}},
         "precision": {"type": "mixed_precision"},
@@ -306,7 +308,8 @@ def main():
                        "microbatch_overlap": bool(getattr(module, "use_mb_overlap", False)),
                        "fused_tp_layers": int(getattr(module, "fused_tp_layers", 0)),
                        "fused_zero1": bool(getattr(module, "fused_zero1", False)),
-                       "keep_gathered_input": bool(_keep_gathered())},
+                       "keep_gathered_input": bool(_keep_gathered()),
+                       "nvls_norm_allgather_layers": int(getattr(module, "nvls_layers", 0))},
             "clocks": clocks, "gpu_launches": launches,
         }
         if not args.no_e2e:

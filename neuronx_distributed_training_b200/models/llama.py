@@ -179,8 +179,12 @@ class LlamaMLP(nn.Module):
         self.down_proj = RowParallelLinear(config.intermediate_size, config.hidden_size, bias=config.mlp_bias,
                                            input_is_parallel=True, init_method=init, **kw)
 
-    def forward(self, x):
-        gate_up = self.gate_up_proj(x)
+    def forward(self, x, pre_norm: Optional[nn.Module] = None):
+        # ``pre_norm``: the RMSNorm in front of the block, handed to the column linear so that norm + sequence-parallel
+        # all-gather can run as one NVLS multicast kernel (parallel/nvls.py); applied here when the linear cannot take it
+        if pre_norm is not None and type(self.gate_up_proj) is not ColumnParallelLinear:
+            x, pre_norm = pre_norm(x), None
+        gate_up = self.gate_up_proj(x, pre_norm) if pre_norm is not None else self.gate_up_proj(x)
         if self.activation_multiply.recompute_in_consumer and torch.is_grad_enabled() \
                 and type(self.down_proj) is RowParallelLinear:      # not when wrapped (e.g. LoRA)
             return self.down_proj(gate_up, pre_act="swiglu")
@@ -247,21 +251,25 @@ class LlamaAttention(nn.Module):
             raise ValueError("context parallelism requires model.fusions.ring_attention=True "
                              "(reference modeling_llama.py:280-288) or model.fusions.ulysses_attention=True")
 
-    def forward(self, hidden: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
-        # hidden: [S_local, B, H]
+    def forward(self, hidden: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
+                pre_norm: Optional[nn.Module] = None) -> torch.Tensor:
+        # hidden: [S_local, B, H]; ``pre_norm``: see LlamaMLP.forward
+        if pre_norm is not None and (self.qkv_mode not in ("gqa", "fused") or type(self.qkv_proj).__name__ not in
+                                     ("GQAQKVColumnParallelLinear", "ColumnParallelLinear")):
+            hidden, pre_norm = pre_norm(hidden), None
         if self.qkv_mode == "gqa" and self.config.fuse_qkv and not self.use_ring and not self.use_ulysses and \
                 type(self.qkv_proj).__name__ == "GQAQKVColumnParallelLinear":
             # one GEMM, then one fused kernel: split + RoPE + [S,B]->[B,S] layout, no intermediate copies
-            packed = self.qkv_proj.forward_packed(hidden)
+            packed = self.qkv_proj.forward_packed(hidden, pre_norm)
             S, B = packed.shape[0], packed.shape[1]
             q, k, v = ops.qkv_rope_split(packed, cos, sin, self.local_q_heads, self.local_kv_heads, self.head_dim)
             o = self.core_attn(q, k, v)
             o = o.transpose(0, 1).reshape(S, B, self.local_q_heads * self.head_dim)
             return self.o_proj(o)
         if self.qkv_mode == "gqa":
-            q, k, v = self.qkv_proj(hidden)
+            q, k, v = self.qkv_proj(hidden, pre_norm) if pre_norm is not None else self.qkv_proj(hidden)
         elif self.qkv_mode == "fused":
-            q, k, v = self.qkv_proj(hidden).chunk(3, dim=-1)
+            q, k, v = (self.qkv_proj(hidden, pre_norm) if pre_norm is not None else self.qkv_proj(hidden)).chunk(3, dim=-1)
         else:
             q, k, v = self.q_proj(hidden), self.k_proj(hidden), self.v_proj(hidden)
         S, B = q.shape[0], q.shape[1]
@@ -289,8 +297,13 @@ class LlamaDecoderLayer(nn.Module):
         sp = config.sequence_parallel_enabled
         self.input_layernorm = LlamaRMSNorm(config.hidden_size, config.rms_norm_eps, sp, config.dtype, device)
         self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, config.rms_norm_eps, sp, config.dtype, device)
+        self.nvls_pre_norm = False
 
     def forward(self, hidden: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+        if self.nvls_pre_norm:        # parallel/nvls.py: the norms run inside the column linears (norm + all-gather in one kernel)
+            hidden = hidden + self.self_attn(hidden, cos, sin, pre_norm=self.input_layernorm)
+            hidden = hidden + self.mlp(hidden, pre_norm=self.post_attention_layernorm)
+            return hidden
         hidden = hidden + self.self_attn(self.input_layernorm(hidden), cos, sin)
         hidden = hidden + self.mlp(self.post_attention_layernorm(hidden))
         return hidden

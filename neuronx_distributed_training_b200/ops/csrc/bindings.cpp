@@ -76,7 +76,19 @@ std::vector<at::Tensor> fp8_quantize_cols_transposed(const at::Tensor& x);
 void gemm_fp8(const at::Tensor& a_q, const at::Tensor& a_scale, const at::Tensor& b_q, const at::Tensor& b_scale,
               at::Tensor& out, bool accumulate);
 
+at::Tensor rmsnorm_allgather_mc(const at::Tensor& x, const at::Tensor& w, double eps, int64_t mc_out_ptr, int64_t rank,
+                                int64_t world, int64_t mc_flag_ptr, int64_t local_flag_ptr, int64_t counter_before);
+int64_t nvls_grid_for_rows(int64_t m);
+void nvls_allreduce(const at::Tensor& in, at::Tensor& out, int64_t local_region_ptr, int64_t mc_region_ptr, int64_t world,
+                    int64_t mc_flag_ptr, int64_t local_flag_ptr, int64_t counter_before);
+int64_t nvls_allreduce_arrivals();
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("rmsnorm_allgather_mc", &rmsnorm_allgather_mc,
+        "sequence-parallel RMSNorm whose output is multicast (multimem.st over NVSwitch) into every rank's gathered buffer");
+  m.def("nvls_grid_for_rows", &nvls_grid_for_rows);
+  m.def("nvls_allreduce", &nvls_allreduce, "one-shot fp32 sum over ranks: staging store, one barrier, multimem.ld_reduce of the whole vector");
+  m.def("nvls_allreduce_arrivals", &nvls_allreduce_arrivals);
   m.def("gemm", &gemm, "tcgen05 bf16 GEMM: out (+)= op(a) op(b)");
   m.def("gemm_2cta", &gemm_2cta, "tcgen05 cta_group::2 bf16 GEMM: a cluster of two SMs per 256x256 tile");
   m.def("gemm_set_2cta", &gemm_set_2cta, "route gemm() through the SM-pair kernel when the shape allows (default on)");

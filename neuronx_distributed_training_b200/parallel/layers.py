@@ -143,8 +143,12 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
     dW = AG_seq(X)^T dY."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, group, sequence_parallel, fused):
+    def forward(ctx, x, weight, bias, group, sequence_parallel, fused, norm_weight=None, norm_eps=0.0, nvls=None):
+        # ``nvls`` (parallel/nvls.py workspace) + ``norm_weight``: x is the UN-normalised sequence shard and the RMSNorm in
+        # front of this linear is fused with the all-gather (one multimem.st kernel writes every rank's gathered buffer)
         ctx.group, ctx.sp, ctx.fused = group, sequence_parallel, fused
+        ctx.nvls = nvls
+        ctx.norm_eps = norm_eps
         ctx.has_bias = bias is not None
         ctx.x_shape = x.shape
         tp = ps.group_size(group)
@@ -167,6 +171,14 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
             wq, ws = ops.fp8._cached(weight, "rows")
             y2d = ops.fp8.gemm(total_q, total_s, wq, ws, out_dtype=x2d.dtype)
             out_shape = (x.shape[0] * tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
+        elif sequence_parallel and tp > 1 and nvls is not None:
+            x2d = x2d if x2d.is_contiguous() else x2d.contiguous()
+            total_x, rstd = nvls.rmsnorm_all_gather(x2d, norm_weight, norm_eps)
+            y2d = ops.gemm_nt(total_x, weight)
+            if keep:
+                kept = total_x.clone()           # the gathered view lives in the double-buffered NVLS workspace
+            del total_x
+            out_shape = (x.shape[0] * tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
         elif sequence_parallel and tp > 1:
             if use_fused:
                 if keep:
@@ -188,12 +200,19 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         if bias is not None:
             y2d = y2d + bias
         ctx.kept = kept is not None
-        ctx.save_for_backward(kept if kept is not None else x, weight)
+        if nvls is not None:
+            ctx.save_for_backward(kept if kept is not None else x, weight, x2d, norm_weight, rstd)
+        else:
+            ctx.save_for_backward(kept if kept is not None else x, weight)
         return y2d.view(out_shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        nvls = getattr(ctx, "nvls", None)
+        if nvls is not None:
+            x, weight, x_raw, norm_weight, rstd = ctx.saved_tensors
+        else:
+            x, weight = ctx.saved_tensors
         group, tp = ctx.group, ps.group_size(ctx.group)
         dy2d = dy.reshape(-1, dy.shape[-1])
         x2d = x.reshape(-1, x.shape[-1])
@@ -202,6 +221,10 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         handle = None
         total_x = x2d
         kept = getattr(ctx, "kept", False)          # x2d IS the gathered input: nothing to gather, plain wgrad GEMM
+        if nvls is not None and need_dw and not kept:
+            # not kept: recompute the norm and multicast it again (the counterpart of the second all-gather)
+            total_x = nvls.rmsnorm_all_gather(x_raw, norm_weight, ctx.norm_eps)[0]
+            kept = True
         fused_wgrad = (not kept) and ctx.can_fuse and need_dw and \
             ctx.fused.prefer_ag_wgrad(x2d.shape[0], x2d.shape[1], dy2d.shape[1])
         if ctx.sp and tp > 1 and need_dw and not kept:
@@ -246,9 +269,14 @@ class _ColumnParallelLinearFn(torch.autograd.Function):
         db = dy2d.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         if rs_handle is not None:
             rs_handle.wait()
+        dnw = None
+        if nvls is not None and dx is not None:
+            # dx is the gradient of the normalised local rows: finish with the RMSNorm backward
+            dx, dnw = _rmsnorm_bwd(dx.reshape(-1, dx.shape[-1]).contiguous(), x_raw, norm_weight, rstd)
+            dnw = dnw.to(norm_weight.dtype) if ctx.needs_input_grad[6] else None
         if dx is not None:
             dx = dx.view(ctx.x_shape)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, dnw, None, None
 
 
 class _RowParallelLinearFn(torch.autograd.Function):
@@ -321,6 +349,47 @@ class _RowParallelLinearFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------------
 # modules
 # ---------------------------------------------------------------------------------------------------
+def _rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor):
+    """(dx, dw fp32) of y = x * rstd * w on 2-D rows; the native kernel on CUDA, plain math elsewhere (gloo tests)."""
+    if dy.is_cuda and ops.C() is not None and ops.get_backend() != "torch":
+        ops._count()
+        return ops.C().rmsnorm_bwd(dy, x, w, rstd)
+    xhat = x.float() * rstd.float().unsqueeze(-1)
+    g = dy.float() * w.float()
+    dx = rstd.float().unsqueeze(-1) * (g - xhat * (g * xhat).mean(-1, keepdim=True))
+    return dx.to(x.dtype), (dy.float() * xhat).sum(0)
+
+
+def _nvls_for(layer, x: torch.Tensor, pre_norm) -> Optional[object]:
+    """The NVLS workspace to use for ``pre_norm`` + this column linear, or None (plain norm, then the usual path)."""
+    nv = getattr(layer, "nvls", None)
+    if nv is None or pre_norm is None or not layer.sequence_parallel_enabled:
+        return None
+    w = getattr(pre_norm, "weight", None)
+    if w is None or not hasattr(pre_norm, "variance_epsilon") or type(pre_norm).forward is not _plain_rmsnorm_forward():
+        return None
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.shape[-1] % 256 == 0):
+        return None
+    if ops.fp8.enabled() or ops.get_backend() == "torch":
+        return None
+    rows = x.numel() // x.shape[-1]
+    if rows * nv.world * x.shape[-1] * 2 > nv.gather_bytes:
+        return None
+    f = getattr(layer, "fused", None)
+    if f is not None:
+        wt = getattr(layer, "weight", None)
+        wt = wt if wt is not None else getattr(layer, "weight_qkv", None)
+        # shapes where the fused all-gather -> GEMM kernel hides the transfer behind the math keep that kernel
+        if wt is not None and f.ok(rows, x.shape[-1], wt.shape[0]) and f.prefer_ag_gemm(rows, x.shape[-1], wt.shape[0]):
+            return None
+    return nv
+
+
+def _plain_rmsnorm_forward():
+    from .norm import RMSNorm
+    return RMSNorm.forward
+
+
 class ColumnParallelLinear(nn.Module):
     """``Y = X W^T + b`` with W split along its output dimension across the TP group."""
 
@@ -362,10 +431,20 @@ class ColumnParallelLinear(nn.Module):
             with torch.no_grad():
                 self.bias.zero_()
 
-    def forward(self, x: torch.Tensor):
+    def forward(self, x: torch.Tensor, pre_norm: Optional[nn.Module] = None):
+        """``pre_norm``: the RMSNorm module that precedes this linear.  With an NVLS workspace attached (``self.nvls``, see
+        parallel/nvls.py:enable_nvls_norm_allgather) norm + sequence-parallel all-gather run as ONE multicast kernel;
+        otherwise the norm is simply applied first."""
         bias = None if self.skip_bias_add else self.bias
-        y = _ColumnParallelLinearFn.apply(x, self.weight, bias, self.group, self.sequence_parallel_enabled,
-                                          self.fused)
+        nv = _nvls_for(self, x, pre_norm)
+        if nv is not None:
+            y = _ColumnParallelLinearFn.apply(x, self.weight, bias, self.group, True, self.fused, pre_norm.weight,
+                                              float(pre_norm.variance_epsilon), nv)
+        else:
+            if pre_norm is not None:
+                x = pre_norm(x)
+            y = _ColumnParallelLinearFn.apply(x, self.weight, bias, self.group, self.sequence_parallel_enabled,
+                                              self.fused)
         if self.gather_output:
             y = mp.gather_from_tensor_model_parallel_region(y, self.group)
         if self.skip_bias_add:
@@ -589,13 +668,27 @@ class GQAQKVColumnParallelLinear(nn.Module):
                 self.weight_k.copy_(ks.to(self.weight_k.dtype))
                 self.weight_v.copy_(vs.to(self.weight_v.dtype))
 
-    def forward_packed(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_packed(self, x: torch.Tensor, pre_norm: Optional[nn.Module] = None) -> torch.Tensor:
         """the fused projection output ``[..., q_local + 2*kv_local]`` before it is split (fuse_qkv only)"""
         assert self.fuse_qkv
+        nv = _nvls_for(self, x, pre_norm)
+        if nv is not None:
+            return _ColumnParallelLinearFn.apply(x, self.weight_qkv, self.bias_qkv, self.group, True, self.fused,
+                                                 pre_norm.weight, float(pre_norm.variance_epsilon), nv)
+        if pre_norm is not None:
+            x = pre_norm(x)
         return _ColumnParallelLinearFn.apply(x, self.weight_qkv, self.bias_qkv, self.group,
                                              self.sequence_parallel_enabled, self.fused)
 
-    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def forward(self, x: torch.Tensor, pre_norm: Optional[nn.Module] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        if self.fuse_qkv:
+            nv = _nvls_for(self, x, pre_norm)
+            if nv is not None:
+                y = _ColumnParallelLinearFn.apply(x, self.weight_qkv, self.bias_qkv, self.group, True, self.fused,
+                                                  pre_norm.weight, float(pre_norm.variance_epsilon), nv)
+                return torch.split(y, [self.q_local, self.kv_local, self.kv_local], dim=-1)
+        if pre_norm is not None:
+            x = pre_norm(x)
         if self.fuse_qkv:
             y = _ColumnParallelLinearFn.apply(x, self.weight_qkv, self.bias_qkv, self.group,
                                               self.sequence_parallel_enabled, self.fused)

@@ -129,6 +129,28 @@ class BaseModelModule:
             self.model = self.build_model()
             self._maybe_enable_fused_tp()
         self._configure_keep_gathered(fus)
+        self._maybe_enable_nvls(fus)
+
+    def _maybe_enable_nvls(self, fus) -> int:
+        """``model.fusions.nvls_norm_allgather`` (default false; ``NXDT_NVLS=1``): the sequence-parallel RMSNorm in front of
+        a column linear and the all-gather that follows run as ONE kernel that multicasts the normalised rows through the
+        NVSwitch (``multimem.st``, parallel/nvls.py) -- for the linears the fused all-gather -> GEMM kernel leaves on NCCL."""
+        want = bool(fus.get("nvls_norm_allgather", False)) if "nvls_norm_allgather" in fus else False
+        if "NXDT_NVLS" in os.environ:
+            want = os.environ["NXDT_NVLS"] == "1"
+        self.nvls_layers = 0
+        if not want or self.device.type != "cuda" or self.dims.tp < 2 or not self.sequence_parallel or self.model is None:
+            return 0
+        if self.use_cuda_graph or self.use_mb_overlap:
+            # the arrival targets are host-side counters (a replayed graph would repeat them) and the workspace is single-stream
+            log.info("nvls_norm_allgather: off with cuda_graph / microbatch_overlap")
+            return 0
+        from ..parallel.nvls import enable_nvls_norm_allgather
+        seq = int(self.config.get("encoder_seq_length", None) or self.cfg.data.get("seq_length", 8192))
+        self.nvls_layers = enable_nvls_norm_allgather(self.model, max(1, seq // self.dims.cp), self.micro_batch_size)
+        if ps.get_rank() == 0:
+            log.info("NVLS norm + all-gather attached to %d linears", self.nvls_layers)
+        return self.nvls_layers
 
     def _configure_keep_gathered(self, fus) -> None:
         """``model.fusions.keep_gathered_input``: true | false | auto (default).  Column linears of a sequence-parallel

@@ -16,6 +16,8 @@ TP = world
 dev = torch.device("cuda", torch.cuda.current_device())
 S = int(os.environ.get("SEQ", "2048"))
 FUSED = os.environ.get("FUSED", "1") == "1"
+NVLS = os.environ.get("NVLS", "0") == "1"     # RMSNorm + all-gather as one NVSwitch-multicast kernel (parallel/nvls.py)
+NVLS_KEEP = os.environ.get("NVLS_KEEP", "1") == "1"
 base = dict(vocab_size=8192, hidden_size=1024, intermediate_size=2816, num_hidden_layers=int(os.environ.get("LAYERS", "3")),
             num_attention_heads=8, num_key_value_heads=max(2, TP), head_dim=128, torch_dtype="bfloat16",
             use_cpu_initialization=True)
@@ -32,6 +34,16 @@ def build(tp_size, sp):
 
 def fwd_bwd(m, tp_size):
     n_fused = enable_fused_tp(m, seq_len=S, micro_batch=2) if (FUSED and tp_size > 1) else 0
+    if NVLS and tp_size > 1:
+        from neuronx_distributed_training_b200.parallel.nvls import enable_nvls_norm_allgather
+        from neuronx_distributed_training_b200.parallel.layers import set_keep_gathered_input
+        n_nvls = enable_nvls_norm_allgather(m, seq_len=S, micro_batch=2)
+        if n_nvls == 0:
+            if rank == 0:
+                print("NVLS_UNAVAILABLE", flush=True)
+            dist.barrier(); dist.destroy_process_group(); sys.exit(0)
+        set_keep_gathered_input(NVLS_KEEP)
+        print(f"[rank {rank}] NVLS norm + all-gather attached to {n_nvls} linears (keep gathered input: {NVLS_KEEP})", flush=True)
     ops.reset_native_launch_count()
     loss, _ = m(input_ids=ids, labels=ids)
     loss.backward()

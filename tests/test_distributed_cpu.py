@@ -36,6 +36,11 @@ def test_tensor_parallel_model_matches_single_process_gradients(tp):
     run_dist("tp_model.py", tp, {"TP": str(tp)})
 
 
+def test_norm_inside_column_linear_path_matches_norm_then_linear():
+    """parallel/nvls.py call path (RMSNorm + all-gather fused into the column linear's autograd node), emulated workspace."""
+    run_dist("nvls_pre_norm.py", 2, {"TP": "2"})
+
+
 def test_megatron_gpt_tensor_parallel_matches_single_process_gradients():
     run_dist("megatron_tp_model.py", 2, {"TP": "2"})
 

@@ -479,9 +479,13 @@ def test_parallel_embedding_module_accumulates_into_main_grad():
 def _tiny_llama_loss_and_grads(backend, device="cuda", dtype="bfloat16"):
     from neuronx_distributed_training_b200 import ops
     from neuronx_distributed_training_b200.models.llama import LlamaConfig, LlamaForCausalLM
+    from neuronx_distributed_training_b200.parallel.random import get_rng_tracker
     prev = ops.get_backend()
     ops.set_backend(backend)
     try:
+        # hermetic weights: a trainer test that ran earlier in the session leaves the tensor-parallel RNG tracker seeded, and
+        # the sharded initialisers would then draw from ITS stream (different weights for each of the three models)
+        get_rng_tracker().reset()
         torch.manual_seed(0)
         cfg = LlamaConfig(vocab_size=2048, hidden_size=512, intermediate_size=1408, num_hidden_layers=2,
                           num_attention_heads=4, num_key_value_heads=2, head_dim=128, torch_dtype=dtype,
@@ -499,9 +503,10 @@ def _tiny_llama_loss_and_grads(backend, device="cuda", dtype="bfloat16"):
 def test_whole_model_native_path_matches_library_path(C):
     """Every native op in one forward + backward (RMSNorm, fused QKV split + RoPE, flash attention fwd + bwd, SwiGLU,
     tcgen05 GEMMs for fwd / dgrad / wgrad, fused LM head + cross-entropy) against (a) the same bf16 model on the library
-    path (cuBLAS / SDPA / unfused torch ops) and (b) the fp32 model as ground truth.  Bounds per gradient tensor: cosine
-    >= 0.999 and norm within 2 % of the fp32 truth (or, where bf16 itself cannot reach that, no worse than the library
-    path by more than 5e-4 in cosine / 2x + 1 % in norm) -- tight enough to expose a 2x error in any single tensor class."""
+    path (cuBLAS / SDPA / unfused torch ops) and (b) the fp32 model as ground truth.  Bound per gradient tensor: relative
+    L2 error against the fp32 truth <= 3 %, or, for tensors where bf16 itself cannot reach that (the sparse embedding rows),
+    no worse than 1.5x the library path's error + 1 % -- a 2x (or sign, or missing-term) error in any single tensor class is
+    a relative error of ~1 and fails.  The full per-tensor table is printed on failure."""
     loss_n, g_n = _tiny_llama_loss_and_grads("auto")
     loss_t, g_t = _tiny_llama_loss_and_grads("torch")
     loss_f, g_f = _tiny_llama_loss_and_grads("torch", dtype="float32")
@@ -513,13 +518,12 @@ def test_whole_model_native_path_matches_library_path(C):
     for name in g_n:
         a, b, f = g_n[name].flatten(), g_t[name].flatten(), g_f[name].flatten()
         cos_n, cos_t = cosf(a, f, dim=0).item(), cosf(b, f, dim=0).item()
-        dev_n, dev_t = abs(a.norm().item() / f.norm().item() - 1), abs(b.norm().item() / f.norm().item() - 1)
-        cos_nt = cosf(a, b, dim=0).item()
-        row = f"{name}: cos(native,fp32)={cos_n:.5f} cos(lib,fp32)={cos_t:.5f} cos(native,lib)={cos_nt:.5f} " \
-              f"norm dev native={dev_n:.4f} lib={dev_t:.4f} finite={bool(torch.isfinite(a).all())}"
+        err_n, err_t = ((a - f).norm() / f.norm()).item(), ((b - f).norm() / f.norm()).item()
+        row = f"{name}: rel err native={err_n:.4f} lib={err_t:.4f} cos(native,fp32)={cos_n:.5f} cos(lib,fp32)={cos_t:.5f} " \
+              f"norm ratio native={a.norm().item() / f.norm().item():.4f} lib={b.norm().item() / f.norm().item():.4f} " \
+              f"finite={bool(torch.isfinite(a).all())}"
         table.append(row)
-        # (sparse embedding rows: both bf16 paths are ~10 % off the fp32 norm)
-        if not (cos_n >= min(0.999, cos_t - 5e-4) and dev_n <= max(0.02, 2.0 * dev_t + 0.01) and cos_nt > 0.995):
+        if not (err_n <= max(0.03, 1.5 * err_t + 0.01) and cos_n >= min(0.999, cos_t - 0.01)):
             bad.append(row)
     assert not bad, "\n".join(["violations:"] + bad + ["all tensors:"] + table)
 

@@ -53,6 +53,35 @@ def test_whole_model_tp2_matches_tp1_on_hardware(fused):
     print(out[-1500:])
 
 
+def test_nvls_multicast_kernels_2gpu():
+    """multimem.st RMSNorm + all-gather and multimem.ld_reduce all-reduce (ops/csrc/nvls.cu) vs NCCL; skipped on a box whose
+    symmetric allocations get no NVSwitch multicast mapping."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    try:
+        out = run_gpus("check_nvls.py", 2, "NVLS_OK")
+    except AssertionError as e:
+        if "NVLS_UNAVAILABLE" in str(e):
+            pytest.skip("no multicast mapping on this box")
+        raise
+    print(out[-1500:])
+
+
+@pytest.mark.parametrize("keep", ["1", "0"])
+def test_whole_model_tp2_with_nvls_norm_allgather_matches_tp1(keep):
+    """Same whole-model parity check as above with every RMSNorm + sequence-parallel all-gather pair running as the NVLS
+    kernel inside the column linear's autograd node (gathered input kept / re-multicast in backward)."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    try:
+        out = run_gpus("check_tp_model_gpu.py", 2, "TP_MODEL_GPU_OK", {"FUSED": "0", "NVLS": "1", "NVLS_KEEP": keep})
+    except AssertionError as e:
+        if "NVLS_UNAVAILABLE" in str(e):
+            pytest.skip("no multicast mapping on this box")
+        raise
+    print(out[-1500:])
+
+
 def test_context_parallel_attention_native_kernels_2gpu():
     """CP=2: all-gathered K/V + one offset-causal tcgen05 launch per rank (forward and backward) vs the full sequence."""
     out = run_gpus("check_cp_attention.py", 2, "CP_ATTENTION_OK")
