@@ -28,13 +28,15 @@ KERNELS = {  # output name -> regex on the demangled kernel name
     "gemm_mxfp8_kernel": r"gemm_mxfp8_kernel",
     "gemm2cta_kernel": r"gemm2cta::gemm2cta_kernel",
     "mx_quantize_rows_kernel": r"mx_quantize_rows",
+    "nvls_rmsnorm_allgather_kernel": r"nvls::rmsnorm_allgather_mc_kernel<\(int\)4, \(int\)16>",
+    "nvls_allreduce_kernel": r"nvls::nvls_allreduce_kernel",
     "zero1_reduce_kernel": r"zero1_reduce",
     "zero1_adam_push_kernel": r"zero1_adam_push",
     "adamw_flat_kernel": r"adamw_flat_kernel",
     "rmsnorm_bwd_kernel": r"rmsnorm_bwd_kernel<__nv_bfloat16, \(int\)256, \(int\)2>",
     "ce_stats_kernel": r"ce_stats_kernel",
 }
-INTERESTING = re.compile(r"\b(UTC[A-Z0-9]*|UTMA[A-Z]*|UBLKCP|LDTM|STTM|SYNCS|UCGABAR|USETMAXREG|MUFU|REDG?|ATOMG?|MULTIMEM|"
+INTERESTING = re.compile(r"\b(LDGMC|UTC[A-Z0-9]*|UTMA[A-Z]*|UBLKCP|LDTM|STTM|SYNCS|UCGABAR|USETMAXREG|MUFU|REDG?|ATOMG?|MULTIMEM|"
                          r"LDG\.E[.A-Z0-9]*\.SYS|STG\.E[.A-Z0-9]*\.SYS|LD\.E[.A-Z0-9]*\.SYS|ST\.E[.A-Z0-9]*\.SYS|FENCE|"
                          r"FFMA2|FADD2|FMUL2|FMNMX3|HMMA|MEMBAR|ELECT|LDSM|STSM)\b")
 
@@ -104,7 +106,9 @@ def main():
                  "`ops/_C.so` (`cuobjdump -sass`).  One `.sass` file per kernel: every tensor-core (`UTC*MMA` = tcgen05.mma), "
                  "tensor-memory (`LDTM` / `STTM` = tcgen05.ld / st), TMA (`UTMALDG` / `UTMASTG` / `UTMAREDG` / `UBLKCP`), mbarrier "
                  "(`SYNCS`), register-reallocation (`USETMAXREG`), packed-fp32 (`FFMA2` ...) and system-scope (peer memory) "
-                 "instruction with its address, in program order.  No `HMMA` / `HGMMA` (legacy tensor paths) appears anywhere.\n\n"
+                 "instruction with its address, in program order.  No `HMMA` / `HGMMA` (legacy tensor paths) appears anywhere.  "
+                 "NVLS: `multimem.ld_reduce` assembles to `LDGMC.E.ADD.F32x4...STRONG.SYS`; `multimem.st` / `multimem.red` assemble to "
+                 "`STG.E.128.STRONG.SYS` / `REDG.E.ADD.STRONG.SYS` on the multicast mapping (the switch replicates them).\n\n"
                  "| kernel | SASS instructions | registers | most frequent listed opcodes |\n|---|---:|---:|---|\n" + "\n".join(rows) + "\n")
 
 
