@@ -156,7 +156,7 @@ class BaseModelModule:
         """``model.fusions.keep_gathered_input``: true | false | auto (default).  Column linears of a sequence-parallel
         layer either keep their all-gathered input for the weight gradient or gather it a second time in backward.
         Measured on 8 x B200, Llama-3-8B, TP=8: keeping it is +8.6 % tokens/s for +3.5 GB (the layer is transfer-bound
-        at large TP).  ``auto`` keeps it when TP >= 4 and the extra activations stay below 8 % of the device memory
+        at large TP).  ``auto`` keeps it when TP >= 8 (the measured case) and the extra activations stay below 8 % of the device memory
         (Llama-3-70B at TP=8 would add 19 GB to a 157 GB step: stays off)."""
         from ..parallel.layers import ColumnParallelLinear, GQAQKVColumnParallelLinear, set_keep_gathered_input
         want = fus.get("keep_gathered_input", "auto") if "keep_gathered_input" in fus else "auto"
@@ -166,7 +166,7 @@ class BaseModelModule:
             want = {"true": True, "false": False}.get(want.lower(), "auto")
         if want == "auto":
             want = False
-            if self.device.type == "cuda" and self.dims.tp >= 4 and self.sequence_parallel and self.model is not None:
+            if self.device.type == "cuda" and self.dims.tp >= 8 and self.sequence_parallel and self.model is not None:
                 seq = int(self.config.get("encoder_seq_length", None) or self.cfg.data.get("seq_length", 8192))
                 tokens = self.micro_batch_size * max(1, seq // self.dims.cp)
                 in_flight = max(1, self.dims.pp)               # 1F1B holds up to pp micro-batches on the first stage
@@ -205,7 +205,7 @@ class BaseModelModule:
             return 0
         if self.use_cuda_graph and want == "auto" and os.environ.get("NXDT_CUDA_GRAPH_WITH_FUSED_TP", "0") != "1":
             log.info("cuda_graph requested: tensor-parallel collectives stay on NCCL (graph replay of the fused kernels is "
-                     "not validated yet, docs/ROUND2_PLAN.md)")
+                     "not validated yet, DESIGN.md 3.2b)")
             return 0
         try:
             from ..parallel.fused import enable_fused_tp
