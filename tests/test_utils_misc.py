@@ -167,3 +167,19 @@ def test_package_has_no_undefined_names_or_unused_imports():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "lint_names.py")], cwd=root, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_keep_gathered_input_auto_rule():
+    """model.fusions.keep_gathered_input=auto: on for Llama-3-8B at TP=8 (3.8 GB of gathered inputs), off for Llama-3-70B at
+    TP=8 (19 GB), off below TP=8 and when pipeline stages multiply the micro-batches in flight past the memory bound."""
+    from neuronx_distributed_training_b200.trainer.module import keep_gathered_auto
+    mem = 191 * 10 ** 9
+    llama8b = [4096, 4096] * 32 + [4096]           # qkv + gate_up per layer, LM head
+    keep, extra = keep_gathered_auto(8, 1, 8192, llama8b, mem)
+    assert keep and 3.5e9 < extra < 4.0e9
+    llama70b = [8192, 8192] * 80 + [8192]
+    keep, extra = keep_gathered_auto(8, 1, 8192, llama70b, mem)
+    assert not keep and 18e9 < extra < 20e9
+    assert not keep_gathered_auto(4, 1, 8192, llama8b, mem)[0]
+    assert not keep_gathered_auto(8, 8, 8192, llama8b, mem)[0]      # 8 micro-batches in flight: 30 GB > 8 %
+    assert not keep_gathered_auto(8, 1, 8192, [], mem)[0]
