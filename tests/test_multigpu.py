@@ -4,8 +4,13 @@ than they need, and otherwise launch ``torch.distributed.run`` on the check scri
 * fused AG->GEMM / GEMM->RS / AG-wgrad kernels vs fp32 matmul + exact gather,
 * fused ZeRO-1 step vs the NCCL reduce-scatter + AdamW + all-gather path,
 * the whole model at TP=2 (fused kernels, bf16, native flash attention) vs TP=1: loss within 1e-3 relative, every
-  gradient tensor cosine >= 0.999 and norm within 2 %  (same check with the NCCL-only TP path),
-* pipeline parallelism, context parallelism, expert parallelism and LoRA / DPO steps on GPUs.
+  gradient tensor cosine >= 0.999 and norm within 2 %  (same check with the NCCL-only TP path and with the NVLS
+  norm + all-gather kernel),
+* the NVLS (multimem) kernels vs NCCL,
+* context-parallel attention (gathered K/V + one offset-causal native launch) vs the full sequence.
+Pipeline parallelism on GPUs is exercised through ``bench.py --pp`` (tests/gpu_checks/COMMANDS.md); expert parallelism,
+LoRA and DPO under tensor parallelism are covered by the gloo tests (tests/test_distributed_cpu.py) and, on one GPU, by
+tests/test_families_gpu.py.
 """
 import os
 import subprocess
