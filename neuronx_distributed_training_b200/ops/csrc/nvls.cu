@@ -15,7 +15,7 @@
 //    barrier, every rank reads the whole reduced vector with multimem.ld_reduce.  One launch, no NCCL kernel: for the
 //    latency-bound tensor-parallel reductions.
 //
-// All waits are bounded (≈4 s of globaltimer) and trap instead of hanging the GPU.
+// All waits are bounded (≈20 s of globaltimer) and trap instead of hanging the GPU.
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -54,12 +54,13 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// wait until the local copy of an arrival counter reaches `target` (wrap-safe), trap after ~4 s
+// wait until the local copy of an arrival counter reaches `target` (wrap-safe), trap after ~20 s (same bound as the
+// fused TP kernels: long enough for a rank delayed by data loading, short enough that a lost peer ends the job)
 __device__ __forceinline__ void wait_counter(const uint32_t* local_flag, uint32_t target) {
   const uint64_t t0 = globaltimer_ns();
   while ((int32_t)(ld_acquire_sys_u32(local_flag) - target) < 0) {
     __nanosleep(64);
-    if (globaltimer_ns() - t0 > 4000000000ull) {
+    if (globaltimer_ns() - t0 > 20000000000ull) {
       printf("nvls: arrival counter timeout (have %u, want %u)\n", ld_acquire_sys_u32(local_flag), target);
       __trap();
     }
