@@ -98,7 +98,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         "MX block-scaled e4m3 GEMM: tcgen05.mma.kind::mxf8f6f4.block_scale, 1x32 E8M0 scale factors staged in tensor memory");
   m.def("mx_quantize_rows", &mx_quantize_rows, "bf16 [R,C] -> e4m3 + packed E8M0 1x32 block scales along C");
   m.def("mx_quantize_cols_transposed", &mx_quantize_cols_transposed, "bf16 [R,C] -> e4m3 of x^T [C,R] + packed scales along R");
-  m.def("gemm_fp8", &gemm_fp8, "preview: e4m3 tcgen05 GEMM (kind::f8f6f4) with per-row scales of both operands");
+  m.def("gemm_fp8", &gemm_fp8, "e4m3 tcgen05 GEMM (kind::f8f6f4) with per-row scales of both operands");
   m.def("fp8_quantize_rows", &fp8_quantize_rows, "bf16 [R,C] -> e4m3 bytes + one fp32 scale per row");
   m.def("fp8_quantize_cols_transposed", &fp8_quantize_cols_transposed,
         "bf16 [R,C] -> e4m3 bytes of the transpose [C,R] + one fp32 scale per original column");

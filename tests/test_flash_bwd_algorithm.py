@@ -1,7 +1,7 @@
-"""Tile-level emulation of ``flash_attn_bwd_sm100.cu`` in PyTorch: same loop structure (one 128-key block per "CTA", query
+"""Tile-level emulation of ``flash_attn_bwd2_sm100.cu`` in PyTorch: same loop structure (one 128-key block per "CTA", query
 blocks at or after it, every head of the GQA group), same formulas (exp2 domain, LSE / Delta statistics, window bounds).
-It validates the algorithm the preview kernel implements against autograd; the CUDA kernel itself is checked on the
-GPU by ``tests/gpu_checks/check_flash_bwd.py``."""
+It validates the algorithm the kernel implements against autograd on the CPU; the CUDA kernel itself is checked on the GPU by
+``tests/test_kernels_gpu.py::test_flash_attention_forward_backward`` and ``tests/gpu_checks/check_flash_bwd.py``."""
 import math
 
 import pytest

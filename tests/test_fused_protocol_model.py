@@ -33,7 +33,6 @@ class World:
         self.slab_reading = [[{}, {}] for _ in range(tp)]               # slab_reading[owner][par][rb] = epoch being reduced
         self.errors = []
         self.done = {}
-        self.aflag = [{} for _ in range(tp)]                          # aflag[owner][(rb, src, nt)] = epoch (never cleared)
 
 
 def kernel_ag(w, r, epoch, par):
@@ -64,8 +63,6 @@ def kernel_ag(w, r, epoch, par):
     return [comm()] + [gemm(c) for c in range(N_CTA)]
 
 
-SELF_RESET = {"on": False}     # protocol variant: no host-side clear, the last reducer of a row-block re-arms its counter
-ARRIVE_FLAGS = {"on": False}   # protocol variant: epoch-valued arrival flags per (row-block, source, n-tile); nothing is cleared
 
 
 def kernel_rs(w, r, epoch, par):
@@ -93,36 +90,20 @@ def kernel_rs(w, r, epoch, par):
                                 f"{w.slab_reading[owner][par][rb]} is still reducing it")
             w.slab[owner][par][(r, rb, nt)] = epoch
             yield
-            if ARRIVE_FLAGS["on"]:
-                w.aflag[owner][(rb, r, nt)] = epoch
-            else:
-                w.counter[owner][par][rb] += 1
+            w.counter[owner][par][rb] += 1
             yield
         # reduce phase
         for item in range(c, BLOCKS * NTILE, N_CTA):
             rb = item // NTILE
-            if ARRIVE_FLAGS["on"]:
-                for src in range(w.tp):                                  # only the tp tiles of MY chunk
-                    while w.aflag[r].get((rb, src, item % NTILE), 0) < epoch:
-                        yield
-            else:
-                while w.counter[r][par][rb] < target:
-                    yield
+            while w.counter[r][par][rb] < target:
+                yield
             w.slab_reading[r][par][rb] = epoch
             for src in range(w.tp):
                 for nt in range(NTILE):
-                    if ARRIVE_FLAGS["on"] and nt != item % NTILE:
-                        continue
                     if w.slab[r][par].get((src, rb, nt)) != epoch:
                         w.errors.append(f"rank {r} call {epoch}: slab tile ({src},{rb},{nt}) = {w.slab[r][par].get((src, rb, nt))}")
             yield
             w.slab_reading[r][par].pop(rb, None)
-            if SELF_RESET["on"]:
-                key = (r, par, rb)
-                w.done[key] = w.done.get(key, 0) + 1
-                if w.done[key] == NTILE:                                 # every reducer of this row-block has consumed it
-                    w.done[key] = 0
-                    w.counter[r][par][rb] = 0
     return [cta(c) for c in range(N_CTA)]
 
 
@@ -157,8 +138,7 @@ def rank_program(w, r, ops, replays, boundary_barriers):
                 w.xstage[r][par] = epoch                              # staging copy (stream order, before the kernel)
                 yield kernel_ag(w, r, epoch, par)
             else:
-                if not SELF_RESET["on"] and not ARRIVE_FLAGS["on"]:
-                    w.counter[r][par] = [0] * BLOCKS                  # memset (stream order, before the kernel)
+                w.counter[r][par] = [0] * BLOCKS                      # memset (stream order, before the kernel)
                 yield kernel_rs(w, r, epoch, par)
 
 
@@ -202,32 +182,6 @@ def test_protocol_has_no_lost_signal_or_stale_read(ops, boundary_barriers):
     for seed in range(60):
         errors = run(ops, replays, boundary_barriers, seed)
         assert not errors, errors[:3]
-
-
-@pytest.mark.parametrize("ops", [("ag", "rs"), ("rs", "rs", "rs"), ("ag", "rs", "agw", "rs", "ag")])
-def test_self_resetting_counters_variant(ops):
-    """NXDT_RS_SELF_RESET: arrivals may even precede the owner's kernel start, nothing is ever wiped."""
-    SELF_RESET["on"] = True
-    try:
-        for seed in range(60):
-            assert not run(ops, 3 if len(ops) % 2 == 0 else 1, False, seed)
-            assert not run(ops, 3, True, seed)
-    finally:
-        SELF_RESET["on"] = False
-
-
-@pytest.mark.parametrize("ops", [("ag", "rs"), ("rs", "rs", "rs"), ("ag", "rs", "agw", "rs", "ag")])
-def test_arrival_flags_variant(ops):
-    """NXDT_RS_ARRIVE_FLAGS: epoch-valued flags, no clear, reducers wait only for the tiles of their own chunk."""
-    ARRIVE_FLAGS["on"] = True
-    try:
-        for seed in range(60):
-            assert not run(ops, 3 if len(ops) % 2 == 0 else 1, False, seed)
-            assert not run(ops, 3, True, seed)
-        for seed in range(20):
-            assert not run(("ag", "rs", "rs"), 2, True, seed, tp=3)
-    finally:
-        ARRIVE_FLAGS["on"] = False
 
 
 def test_three_ranks():
