@@ -13,6 +13,8 @@
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected lane)
 //   warps 2..5  : epilogue (TMEM lane quarter = warp_idx % 4)
+// This one-CTA-per-tile body is what the fused TP kernels (fused_tp.cu), the grouped expert GEMMs and the fp8 GEMM instantiate;
+// plain `gemm()` calls with more than one 128-row / 128-column block go to the SM-pair kernel (gemm2cta_sm100.cu).
 // The optional `TileGate` hook lets the fused all-gather->GEMM kernel make the producer wait (acquire at
 // system scope) until the rows of A that a tile needs have arrived from the peer GPU.
 #pragma once
