@@ -1,7 +1,7 @@
 # Convenience targets (the reference's Makefile only builds its Sphinx docs).
 PY ?= python
 
-.PHONY: build test test-gpu bench smoke clean lint sanitize-host sanitize-gpu
+.PHONY: build test test-gpu bench smoke clean lint sanitize-host sanitize-gpu sanitize-gpu-small
 
 build:            ## compile the sm_100a kernels and the C++ helpers in-tree
 	$(PY) -c "import __graft_entry__ as g; g.build()"
@@ -34,6 +34,10 @@ sanitize-gpu:
 	  timeout 1800 compute-sanitizer --tool $$tool --error-exitcode 1 --target-processes all \
 	    $(PY) -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "$(SANITIZE_K)" || exit 1; \
 	done
+
+# the quick variant that produced profiles/sanitizer.md: one script with a few CTAs per tcgen05 / TMA kernel
+sanitize-gpu-small:
+	bash tests/gpu_checks/run_r2_sanitize.sh
 
 clean:
 	rm -rf neuronx_distributed_training_b200/ops/_build neuronx_distributed_training_b200/checkpoint/_build build *.egg-info
