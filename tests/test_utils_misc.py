@@ -183,3 +183,23 @@ def test_keep_gathered_input_auto_rule():
     assert not keep_gathered_auto(4, 1, 8192, llama8b, mem)[0]
     assert not keep_gathered_auto(8, 8, 8192, llama8b, mem)[0]      # 8 micro-batches in flight: 30 GB > 8 %
     assert not keep_gathered_auto(8, 1, 8192, [], mem)[0]
+
+
+def test_bench_reference_arm_contract_and_recorded_lines():
+    """`bench.py --impl reference` must exit 0 with ONE JSON line naming why the reference cannot run here, and every line
+    recorded in profiles/bench_results.jsonl carries the keys the driver reads."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and ("unavailable" in d or "value" in d)
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+            "config"}
+    with open(os.path.join(root, "profiles", "bench_results.jsonl")) as f:
+        rows = [json.loads(l) for l in f if l.strip()]
+    assert rows and all(need <= set(row) for row in rows)
+    assert all(row["value"] > 0 and row["n_gpus"] in (1, 2, 4, 8) for row in rows)
