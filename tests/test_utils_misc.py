@@ -203,3 +203,20 @@ def test_bench_reference_arm_contract_and_recorded_lines():
         rows = [json.loads(l) for l in f if l.strip()]
     assert rows and all(need <= set(row) for row in rows)
     assert all(row["value"] > 0 and row["n_gpus"] in (1, 2, 4, 8) for row in rows)
+
+
+def test_every_environment_switch_is_documented():
+    """Every NXDT_* variable read anywhere in the package, bench.py or the examples has a row in docs/USER_GUIDE.md."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    found = set()
+    for base in ("neuronx_distributed_training_b200", "examples", "bench.py", "__graft_entry__.py"):
+        path = os.path.join(root, base)
+        files = [path] if os.path.isfile(path) else [os.path.join(d, f) for d, _, fs in os.walk(path) for f in fs
+                                                      if f.endswith((".py", ".sh", ".cu", ".cuh", ".cpp", ".h"))]
+        for f in files:
+            with open(f, errors="ignore") as fh:
+                found |= set(re.findall(r"NXDT_[A-Z0-9_]+", fh.read()))
+    guide = open(os.path.join(root, "docs", "USER_GUIDE.md")).read()
+    missing = sorted(v for v in found if v not in guide)
+    assert not missing, missing
