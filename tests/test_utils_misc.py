@@ -220,3 +220,39 @@ def test_every_environment_switch_is_documented():
     guide = open(os.path.join(root, "docs", "USER_GUIDE.md")).read()
     missing = sorted(v for v in found if v not in guide)
     assert not missing, missing
+
+
+def test_configure_keep_gathered_walks_the_model(monkeypatch):
+    """BaseModelModule._configure_keep_gathered on a fake CUDA device: collects the input widths of the sequence-parallel
+    column linears of the model, applies the auto rule (TP 8: on for a small model, off when an explicit false is given,
+    environment variable wins) and sets the process-wide switch."""
+    import types
+    import torch
+    from neuronx_distributed_training_b200.config import from_dict
+    from neuronx_distributed_training_b200.parallel import layers as L, state as ps
+    from neuronx_distributed_training_b200.trainer.module import BaseModelModule
+    ps.initialize_model_parallel(1, 1, 1)
+    try:
+        model = torch.nn.Sequential(L.ColumnParallelLinear(64, 128, bias=False), L.ColumnParallelLinear(64, 256, bias=False),
+                                    torch.nn.Linear(4, 4))
+        for m in model:
+            if isinstance(m, L.ColumnParallelLinear):
+                m.sequence_parallel_enabled = True
+        cfg = from_dict({"encoder_seq_length": 512, "data": {"seq_length": 512}})
+        me = types.SimpleNamespace(device=types.SimpleNamespace(type="cuda"), sequence_parallel=True, model=model,
+                                   dims=types.SimpleNamespace(tp=8, pp=1, cp=1), micro_batch_size=1, config=cfg, cfg=cfg)
+        monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(total_memory=191 * 10 ** 9))
+        monkeypatch.delenv("NXDT_KEEP_GATHERED", raising=False)
+        BaseModelModule._configure_keep_gathered(me, from_dict({}))
+        assert L.keep_gathered_input() is True
+        BaseModelModule._configure_keep_gathered(me, from_dict({"keep_gathered_input": False}))
+        assert L.keep_gathered_input() is False
+        me.dims.tp = 4
+        BaseModelModule._configure_keep_gathered(me, from_dict({}))
+        assert L.keep_gathered_input() is False                   # auto: only at the measured TP
+        monkeypatch.setenv("NXDT_KEEP_GATHERED", "1")
+        BaseModelModule._configure_keep_gathered(me, from_dict({"keep_gathered_input": False}))
+        assert L.keep_gathered_input() is True
+    finally:
+        L.set_keep_gathered_input(False)
+        ps.destroy_model_parallel()
