@@ -80,3 +80,89 @@ def test_s3_without_boto3_gives_actionable_error(monkeypatch):
         pass
     with pytest.raises(RuntimeError, match="boto3"):
         storage.get_store("s3://bucket/x")
+
+
+class _FakeS3Client:
+    """In-memory stand-in for ``boto3.client('s3')`` with the calls S3Store makes; list_objects_v2 pages by 3 keys so that
+    the continuation-token loop is exercised, delete_objects rejects more than 1000 keys like the real service."""
+    PAGE = 3
+
+    def __init__(self):
+        self.objects = {}                                   # (bucket, key) -> bytes
+        self.delete_calls = []
+
+    def upload_file(self, local_path, bucket, key):
+        with open(local_path, "rb") as f:
+            self.objects[(bucket, key)] = f.read()
+
+    def download_file(self, bucket, key, local_path):
+        with open(local_path, "wb") as f:
+            f.write(self.objects[(bucket, key)])
+
+    def list_objects_v2(self, Bucket, Prefix, ContinuationToken=None, MaxKeys=None):
+        keys = sorted(k for (b, k) in self.objects if b == Bucket and k.startswith(Prefix))
+        start = int(ContinuationToken or 0)
+        page = self.PAGE if MaxKeys is None else min(self.PAGE, MaxKeys)
+        chunk = keys[start:start + page]
+        more = start + page < len(keys) and MaxKeys is None
+        r = {"Contents": [{"Key": k} for k in chunk], "IsTruncated": more}
+        if more:
+            r["NextContinuationToken"] = str(start + page)
+        return r
+
+    def delete_objects(self, Bucket, Delete):
+        assert len(Delete["Objects"]) <= 1000
+        self.delete_calls.append(len(Delete["Objects"]))
+        for o in Delete["Objects"]:
+            del self.objects[(Bucket, o["Key"])]
+
+
+@pytest.fixture()
+def fake_boto3(monkeypatch, tmp_path):
+    import sys, types
+    client = _FakeS3Client()
+    mod = types.ModuleType("boto3")
+    mod.client = lambda name: client
+    monkeypatch.setitem(sys.modules, "boto3", mod)
+    monkeypatch.setenv("NXDT_CKPT_STAGING", str(tmp_path / "staging"))
+    ps.initialize_model_parallel(1, 1, 1)
+    storage.register_object_store("s3", storage.S3Store)
+    yield client
+    ckpt.finalize_checkpoint()
+    ps.destroy_model_parallel()
+
+
+def test_s3store_calls_against_a_fake_boto3_client(fake_boto3, tmp_path):
+    """The real S3Store class (not the directory emulation): upload / download, paginated listing, exact-key `exists`
+    (a key that is only a PREFIX of another object does not exist), batched prefix removal."""
+    s3 = storage.S3Store()
+    src = tmp_path / "blob.bin"
+    for i in range(8):
+        src.write_bytes(bytes([i]) * (i + 1))
+        s3.upload_file(str(src), f"s3://bkt/run/ckpt/part{i}.pt")
+    s3.upload_file(str(src), "s3://bkt/run/ckpt2/other.pt")
+    listed = s3.list("s3://bkt/run/ckpt")
+    assert listed == [f"s3://bkt/run/ckpt/part{i}.pt" for i in range(8)]          # 3 pages, other prefixes excluded
+    assert s3.exists("s3://bkt/run/ckpt/part3.pt") and not s3.exists("s3://bkt/run/ckpt/part") \
+        and not s3.exists("s3://bkt/run/ckpt/missing.pt")
+    dst = tmp_path / "back.bin"
+    s3.download_file("s3://bkt/run/ckpt/part5.pt", str(dst))
+    assert dst.read_bytes() == bytes([5]) * 6
+    s3.remove_prefix("s3://bkt/run/ckpt")
+    assert s3.list("s3://bkt/run/ckpt") == [] and s3.exists("s3://bkt/run/ckpt2/other.pt")
+    assert fake_boto3.delete_calls == [8]
+
+
+def test_checkpoint_roundtrip_through_s3store_with_fake_boto3(fake_boto3):
+    """save -> has -> load -> remove of a checkpoint with the real S3Store driving the (fake) boto3 client."""
+    m, o, uc = _state()
+    url = "s3://bkt/exp/checkpoints"
+    ckpt.save_checkpoint(url, "step_3", m, o, uc, use_xser=True, async_save=False)
+    ckpt.finalize_checkpoint()
+    assert ckpt.has_checkpoint(url, "step_3") and not ckpt.has_checkpoint(url, "step_4")
+    assert any(k.endswith("/done") for (_, k) in fake_boto3.objects)
+    m2, o2, uc2 = ckpt.load_checkpoint(url, "step_3")
+    assert torch.equal(m2["w"], m["w"]) and torch.equal(m2["nested"]["b"], m["nested"]["b"])
+    assert torch.equal(o2["exp_avg"], o["exp_avg"]) and o2["step"] == 3 and uc2["note"] == "x"
+    ckpt.remove_checkpoint(url + "/step_3", async_remove=False)
+    assert not ckpt.has_checkpoint(url, "step_3") and not fake_boto3.objects
